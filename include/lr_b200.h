@@ -1,0 +1,118 @@
+/* lr_b200.h — C ABI of liblr_b200.so: the B200-native (sm_100a) implementation of LeftRefill's DDIM/UNet hot path.
+ *
+ * Plain pointers and sizes only; no torch / C++ types. All pointers are CUDA device pointers unless stated.
+ * Every entry point returns 0 on success, non-zero on failure; lr_last_error() then gives the reason (thread local).
+ * Calls are asynchronous on the `stream` argument (a cudaStream_t passed as void*); no hidden device synchronisation.
+ * Citations are relative to the reference tree (ewrfcas/LeftRefill @ 893c3220).
+ */
+#ifndef LR_B200_H_
+#define LR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LR_B200_ABI_VERSION 1
+
+/* ---- library ---------------------------------------------------------------------------------------------- */
+int lr_abi_version(void);
+const char* lr_last_error(void);
+/* number of CUDA kernels launched by this library since the last reset (bench.py's gpu_launches) */
+long long lr_launch_count(void);
+void lr_launch_count_reset(void);
+
+/* ---- UNet engine: replaces UNetModel.forward (ldm/modules/diffusionmodules/openaimodel.py:755-787) ------------ */
+typedef struct lr_unet lr_unet;
+
+/* Mirrors the constructor kwargs the yaml passes (openaimodel.py:442-472, configs/ref_inpainting.yaml:20-36). */
+typedef struct lr_unet_cfg {
+  int in_channels;         /* 9 */
+  int model_channels;      /* 320 */
+  int out_channels;        /* 4 */
+  int num_levels;          /* len(channel_mult) */
+  int channel_mult[8];     /* 1,2,4,4 */
+  int num_res_blocks[8];   /* per level */
+  int attention_ds[8];     /* attention_resolutions (downsample rates), n_attention_ds entries */
+  int n_attention_ds;
+  int num_head_channels;   /* 64 (d_head); the attention kernel requires 64 */
+  int transformer_depth;   /* 1 */
+  int context_dim;         /* 1024 */
+  int use_linear_in_transformer; /* 1: nn.Linear proj_in/out, 0: 1x1 conv (same math) */
+  /* multiview variant (ldm/modules/multiview_attention.py:431-468): self-attention runs over view_num views */
+  int view_num;            /* 1 = plain UNetModel */
+  int concat_target;       /* 0/1 (multiview only) */
+} lr_unet_cfg;
+
+/* Host-only: builds the layer graph and the weight table. Device memory is allocated lazily. */
+int lr_unet_create(const lr_unet_cfg* cfg, lr_unet** out);
+void lr_unet_destroy(lr_unet* h);
+
+/* Weight table = the reference state-dict keys relative to UNetModel ("input_blocks.1.0.in_layers.2.weight", ...),
+ * i.e. `model.diffusion_model.<name>` in SD2 checkpoints (test_inpainting.py:26-53). */
+int lr_unet_num_weights(const lr_unet* h);
+const char* lr_unet_weight_name(const lr_unet* h, int index);
+/* shape_out receives up to 4 dims in PyTorch order; returns ndim (or -1). */
+int lr_unet_weight_shape(const lr_unet* h, int index, int64_t shape_out[4]);
+/* Upload one fp32 tensor in its PyTorch layout (OIHW conv, [out,in] linear); the engine repacks it to fp16 GEMM
+ * layout on `stream`. `data` must stay valid until the stream reaches this point. */
+int lr_unet_set_weight(lr_unet* h, const char* name, const float* data, const int64_t* shape, int ndim, void* stream);
+/* Number of weights not yet uploaded (forward refuses to run while > 0). */
+int lr_unet_missing_weights(const lr_unet* h);
+
+/* Cross-attention K/V of `context` [n, L, context_dim] fp32 are step-invariant (attention.py:170-171): compute them
+ * once for all layers. lr_unet_forward with context == NULL reuses this cache. */
+int lr_unet_set_context(lr_unet* h, const float* context, int n, int L, void* stream);
+
+/* x [n, in_channels, H, W] fp32 NCHW, timesteps [n] int64, context [n, L, context_dim] fp32 or NULL (cached),
+ * out [n, out_channels, H, W] fp32 NCHW. */
+int lr_unet_forward(lr_unet* h, const float* x, const int64_t* timesteps, const float* context, int L, float* out,
+                    int n, int H, int W, void* stream);
+/* Algorithmic FLOPs (2*M*N*K convs/linears + 4*Tq*Tk*d attention) of the last planned forward. */
+double lr_unet_last_flops(const lr_unet* h);
+/* Bytes of device memory held by the engine (weights + activation plan). */
+long long lr_unet_device_bytes(const lr_unet* h);
+
+/* ---- fused CFG + DDIM update: replaces p_sample_ddim's tail (ldm/models/diffusion/ddim.py:343,359-381) ----------
+ * eps_uncond/eps_cond: the two halves of the CFG-doubled UNet output (eps_cond may be NULL: no guidance).
+ * noise may be NULL when sigma == 0. All tensors fp32 with `numel` elements. */
+int lr_ddim_update(const float* x, const float* eps_uncond, const float* eps_cond, const float* noise, float cfg_scale,
+                   float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at, float temperature, int64_t numel,
+                   float* x_prev, float* pred_x0, void* stream);
+
+/* ---- op-level entry points (what CrossAttention / ResBlock / SpatialTransformer mirrors call stand-alone) ------
+ * Activations are NHWC fp16: row = (n*H + y)*W + x, channels contiguous. */
+
+/* out[M, n_out] = A[M, K] * W[n_out(*2 if geglu), K]^T (+bias) (+residual) ; geglu: W/bias rows interleaved
+ * (value_j, gate_j) and out[:, j] = v_j * gelu(g_j) (attention.py:51-58). fp16 in/out, fp32 accumulate. */
+int lr_linear_f16(const void* a, int lda, int M, int K, const void* w, int ldw, int n_cols, const float* bias,
+                  const void* residual, int ld_res, void* out, int ld_out, int geglu, int force_block_n, void* stream);
+/* 3x3 conv, pad 1, stride 1|2, over the channel concat of x0 [n,h,w,c0] and optional x1 [n,h,w,c1];
+ * wt [cout, 9*(c0+c1)] fp16 with k = (ky*3+kx)*(c0+c1) + c; bias [cout]; bias_img [n, cout] (time embedding);
+ * residual/out [n*ho*wo, cout] fp16. */
+int lr_conv3x3_f16(const void* x0, int c0, const void* x1, int c1, int n, int h, int w, int stride, const void* wt,
+                   int cout, const float* bias, const float* bias_img, const void* residual, void* out,
+                   int force_block_n, void* stream);
+/* softmax(q k^T * scale) v, d_head = 64. q [batch*tq, ldq] (head h at columns q_col0 + 64h), likewise k, v over tk
+ * tokens; out [batch*tq, ld_out]. Replaces attention.py:176-195. */
+int lr_attention_f16(const void* q, int ldq, int q_col0, const void* k, int ldk, int k_col0, const void* v, int ldv,
+                     int v_col0, void* out, int ld_out, int batch, int heads, int tq, int tk, float scale,
+                     void* stream);
+/* GroupNorm(groups, eps) [+ SiLU] over concat(x0, x1) -> out [n, P, c0+c1] fp16 (util.py:217-219, attention.py:90-91).
+ * scratch: at least n*groups*16 + n*(c0+c1)*8 bytes. */
+int lr_groupnorm_f16(const void* x0, int c0, const void* x1, int c1, int n, int P, int groups, float eps,
+                     const float* gamma, const float* beta, int silu, void* out, void* scratch, void* stream);
+int lr_layernorm_f16(const void* x, int M, int C, const float* gamma, const float* beta, float eps, void* out,
+                     void* stream);
+/* layout helpers for the NCHW fp32 boundary */
+int lr_nchw_f32_to_nhwc_f16(const float* x, int n, int c, int h, int w, void* out, void* stream);
+int lr_nhwc_f16_to_nchw_f32(const void* x, int ld, int n, int c, int h, int w, float* out, void* stream);
+/* fp32 OIHW / [out,in] -> fp16 GEMM layouts used above */
+int lr_repack_conv3x3_weight(const float* w_oihw, int cout, int cin, void* out, void* stream);
+int lr_repack_linear_weight(const float* w, int n_out, int n_in, int geglu, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LR_B200_H_ */

@@ -1,0 +1,1042 @@
+// UNet engine: builds the layer graph of UNetModel (reference ldm/modules/diffusionmodules/openaimodel.py:412-787)
+// from the constructor config, owns fp16 repacked weights, and executes UNetModel.forward as a static plan of
+// tcgen05 GEMM/conv ops, fused attention ops and HBM-bound norm kernels on NHWC fp16 activations.
+#include <algorithm>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/lr_b200.h"
+#include "ops.h"
+
+namespace lr {
+
+enum WKind { K_CONV3, K_LINEAR, K_LINEAR_GEGLU, K_VEC, K_VEC_GEGLU };
+
+struct Weight {
+  std::string name;
+  int64_t shape[4] = {0, 0, 0, 0};
+  int ndim = 0;
+  WKind kind = K_VEC;
+  size_t off = 0;    // element offset into the fp16 arena (matrices) or fp32 arena (vectors)
+  int dst_row0 = 0;  // row offset inside a fused matrix (QKV / KV)
+  int ld = 0;        // row length (elements) of the destination matrix
+  bool loaded = false;
+};
+
+struct ResW {
+  int cin = 0, cout = 0;
+  size_t gn1_g, gn1_b, conv1_w, conv1_b, emb_w, emb_b, gn2_g, gn2_b, conv2_w, conv2_b, skip_w, skip_b;
+  bool has_skip = false;
+  int emb_slot = 0;
+};
+struct TBlockW {
+  size_t ln1_g, ln1_b, qkv_w, out1_w, out1_b;
+  size_t ln2_g, ln2_b, q2_w, kv2_w, out2_w, out2_b;
+  size_t ln3_g, ln3_b, ff1_w, ff1_b, ff2_w, ff2_b;
+  int kv_slot = 0;
+};
+struct STW {
+  int C = 0, heads = 0;
+  size_t gn_g, gn_b, pin_w, pin_b, pout_w, pout_b;
+  std::vector<TBlockW> blocks;
+};
+struct ConvW {
+  int cin = 0, cout = 0;
+  size_t w, b;
+};
+enum NodeKind { N_CONV_IN, N_RES, N_ST, N_DOWN, N_UP };
+struct Node {
+  NodeKind kind;
+  int idx;
+};
+
+struct Act {
+  __half* p = nullptr;
+  int C = 0, H = 0, W = 0;
+};
+
+struct Pool {
+  struct Buf {
+    void* p;
+    size_t bytes;
+    bool used;
+  };
+  std::vector<Buf> bufs;
+  size_t total = 0;
+  int acquire(size_t bytes, void** out) {
+    bytes = (bytes + 255) & ~size_t(255);
+    int best = -1;
+    for (size_t i = 0; i < bufs.size(); ++i)
+      if (!bufs[i].used && bufs[i].bytes >= bytes && (best < 0 || bufs[i].bytes < bufs[best].bytes))
+        best = static_cast<int>(i);
+    if (best >= 0 && bufs[best].bytes <= bytes * 2) {
+      bufs[best].used = true;
+      *out = bufs[best].p;
+      return 0;
+    }
+    void* p = nullptr;
+    LR_CUDA(cudaMalloc(&p, bytes));
+    bufs.push_back({p, bytes, true});
+    total += bytes;
+    *out = p;
+    return 0;
+  }
+  void release(void* p) {
+    for (auto& b : bufs)
+      if (b.p == p) b.used = false;
+  }
+  void clear() {
+    for (auto& b : bufs) cudaFree(b.p);
+    bufs.clear();
+    total = 0;
+  }
+};
+
+}  // namespace lr
+
+using namespace lr;
+
+struct lr_unet {
+  lr_unet_cfg cfg;
+  std::vector<Weight> weights;
+  std::map<std::string, int> windex;
+  size_t half_elems = 0, float_elems = 0;
+  __half* harena = nullptr;
+  float* farena = nullptr;
+
+  std::vector<ResW> res;
+  std::vector<STW> sts;
+  std::vector<ConvW> convs;  // conv_in, downs, ups, head
+  std::vector<std::vector<Node>> input_blocks, output_blocks;
+  std::vector<Node> middle;
+  size_t te0_w, te0_b, te2_w, te2_b, head_gn_g, head_gn_b;
+  int conv_in_idx = 0, head_idx = 0, kpad_in = 0;
+  int n_kv_slots = 0;
+
+  // ---- plan state ----
+  int pn = 0, ph = 0, pw = 0;  // planned shape
+  Pool pool;
+  std::vector<std::function<int(cudaStream_t)>> steps;
+  std::vector<std::unique_ptr<ConvOp>> conv_ops;
+  std::vector<std::unique_ptr<AttnOp>> attn_ops;
+  double flops = 0;
+  const float* in_x = nullptr;     // bound per call
+  const int64_t* in_t = nullptr;
+  float* out_y = nullptr;
+  // context cache
+  int ctx_n = 0, ctx_L = 0;
+  __half* ctx_h = nullptr;               // [n*L, context_dim]
+  std::vector<__half*> kv;               // per kv slot [n*L, 2C]
+  std::vector<int> kv_C;
+  std::vector<std::unique_ptr<ConvOp>> kv_ops;
+  bool ctx_valid = false;
+  size_t persistent_bytes = 0;
+
+  ~lr_unet() {
+    pool.clear();
+    if (harena) cudaFree(harena);
+    if (farena) cudaFree(farena);
+    if (ctx_h) cudaFree(ctx_h);
+    for (auto p : kv)
+      if (p) cudaFree(p);
+  }
+
+  // ------------------------------------------------------------------------------------------------------
+  size_t reg(const std::string& name, std::vector<int64_t> shape, WKind kind, size_t off, int dst_row0, int ld) {
+    Weight w;
+    w.name = name;
+    w.ndim = static_cast<int>(shape.size());
+    for (int i = 0; i < w.ndim; ++i) w.shape[i] = shape[i];
+    w.kind = kind;
+    w.off = off;
+    w.dst_row0 = dst_row0;
+    w.ld = ld;
+    windex[name] = static_cast<int>(weights.size());
+    weights.push_back(w);
+    return off;
+  }
+  size_t halloc(size_t elems) {
+    size_t o = half_elems;
+    half_elems += (elems + 127) & ~size_t(127);
+    return o;
+  }
+  size_t falloc(size_t elems) {
+    size_t o = float_elems;
+    float_elems += (elems + 63) & ~size_t(63);
+    return o;
+  }
+  size_t reg_vec(const std::string& name, int n, bool geglu = false) {
+    return reg(name, {n}, geglu ? K_VEC_GEGLU : K_VEC, falloc(n), 0, 0);
+  }
+  size_t reg_linear(const std::string& name, int O, int I, bool geglu = false) {
+    return reg(name, {O, I}, geglu ? K_LINEAR_GEGLU : K_LINEAR, halloc(static_cast<size_t>(O) * I), 0, I);
+  }
+  size_t reg_conv3(const std::string& name, int O, int I, int ld) {
+    return reg(name, {O, I, 3, 3}, K_CONV3, halloc(static_cast<size_t>(O) * ld), 0, ld);
+  }
+
+  int add_res(const std::string& pfx, int cin, int cout, int temb) {
+    ResW r;
+    r.cin = cin;
+    r.cout = cout;
+    r.gn1_g = reg_vec(pfx + "in_layers.0.weight", cin);
+    r.gn1_b = reg_vec(pfx + "in_layers.0.bias", cin);
+    r.conv1_w = reg_conv3(pfx + "in_layers.2.weight", cout, cin, 9 * cin);
+    r.conv1_b = reg_vec(pfx + "in_layers.2.bias", cout);
+    r.emb_w = reg_linear(pfx + "emb_layers.1.weight", cout, temb);
+    r.emb_b = reg_vec(pfx + "emb_layers.1.bias", cout);
+    r.gn2_g = reg_vec(pfx + "out_layers.0.weight", cout);
+    r.gn2_b = reg_vec(pfx + "out_layers.0.bias", cout);
+    r.conv2_w = reg_conv3(pfx + "out_layers.3.weight", cout, cout, 9 * cout);
+    r.conv2_b = reg_vec(pfx + "out_layers.3.bias", cout);
+    r.has_skip = cin != cout;
+    if (r.has_skip) {
+      // nn.Conv2d(cin, cout, 1): [cout, cin, 1, 1] (openaimodel.py:237-240) — same memory layout as a Linear
+      r.skip_w = reg(pfx + "skip_connection.weight", {cout, cin, 1, 1}, K_LINEAR,
+                     halloc(static_cast<size_t>(cout) * cin), 0, cin);
+      r.skip_b = reg_vec(pfx + "skip_connection.bias", cout);
+    }
+    r.emb_slot = static_cast<int>(res.size());
+    res.push_back(r);
+    return static_cast<int>(res.size()) - 1;
+  }
+  int add_st(const std::string& pfx, int C) {
+    STW s;
+    s.C = C;
+    s.heads = C / cfg.num_head_channels;
+    s.gn_g = reg_vec(pfx + "norm.weight", C);
+    s.gn_b = reg_vec(pfx + "norm.bias", C);
+    if (cfg.use_linear_in_transformer) {
+      s.pin_w = reg_linear(pfx + "proj_in.weight", C, C);
+    } else {
+      s.pin_w = reg(pfx + "proj_in.weight", {C, C, 1, 1}, K_LINEAR, halloc(static_cast<size_t>(C) * C), 0, C);
+    }
+    s.pin_b = reg_vec(pfx + "proj_in.bias", C);
+    const int ctx = cfg.context_dim;
+    for (int d = 0; d < cfg.transformer_depth; ++d) {
+      const std::string b = pfx + "transformer_blocks." + std::to_string(d) + ".";
+      TBlockW t;
+      // key order follows the reference module registration order (attention.py:259-268): attn1, ff, attn2, norms
+      t.qkv_w = halloc(static_cast<size_t>(3) * C * C);
+      reg(b + "attn1.to_q.weight", {C, C}, K_LINEAR, t.qkv_w, 0, C);
+      reg(b + "attn1.to_k.weight", {C, C}, K_LINEAR, t.qkv_w, C, C);
+      reg(b + "attn1.to_v.weight", {C, C}, K_LINEAR, t.qkv_w, 2 * C, C);
+      t.out1_w = reg_linear(b + "attn1.to_out.0.weight", C, C);
+      t.out1_b = reg_vec(b + "attn1.to_out.0.bias", C);
+      t.ff1_w = reg_linear(b + "ff.net.0.proj.weight", 8 * C, C, true);
+      t.ff1_b = reg_vec(b + "ff.net.0.proj.bias", 8 * C, true);
+      t.ff2_w = reg_linear(b + "ff.net.2.weight", C, 4 * C);
+      t.ff2_b = reg_vec(b + "ff.net.2.bias", C);
+      t.q2_w = reg_linear(b + "attn2.to_q.weight", C, C);
+      t.kv2_w = halloc(static_cast<size_t>(2) * C * ctx);
+      reg(b + "attn2.to_k.weight", {C, ctx}, K_LINEAR, t.kv2_w, 0, ctx);
+      reg(b + "attn2.to_v.weight", {C, ctx}, K_LINEAR, t.kv2_w, C, ctx);
+      t.out2_w = reg_linear(b + "attn2.to_out.0.weight", C, C);
+      t.out2_b = reg_vec(b + "attn2.to_out.0.bias", C);
+      t.ln1_g = reg_vec(b + "norm1.weight", C);
+      t.ln1_b = reg_vec(b + "norm1.bias", C);
+      t.ln2_g = reg_vec(b + "norm2.weight", C);
+      t.ln2_b = reg_vec(b + "norm2.bias", C);
+      t.ln3_g = reg_vec(b + "norm3.weight", C);
+      t.ln3_b = reg_vec(b + "norm3.bias", C);
+      t.kv_slot = n_kv_slots++;
+      kv_C.push_back(C);
+      s.blocks.push_back(t);
+    }
+    if (cfg.use_linear_in_transformer) {
+      s.pout_w = reg_linear(pfx + "proj_out.weight", C, C);
+    } else {
+      s.pout_w = reg(pfx + "proj_out.weight", {C, C, 1, 1}, K_LINEAR, halloc(static_cast<size_t>(C) * C), 0, C);
+    }
+    s.pout_b = reg_vec(pfx + "proj_out.bias", C);
+    sts.push_back(s);
+    return static_cast<int>(sts.size()) - 1;
+  }
+  int add_conv(const std::string& pfx, int cin, int cout, int ld) {
+    ConvW c;
+    c.cin = cin;
+    c.cout = cout;
+    c.w = reg_conv3(pfx + "weight", cout, cin, ld);
+    c.b = reg_vec(pfx + "bias", cout);
+    convs.push_back(c);
+    return static_cast<int>(convs.size()) - 1;
+  }
+
+  bool attn_at(int ds) const {
+    for (int i = 0; i < cfg.n_attention_ds; ++i)
+      if (cfg.attention_ds[i] == ds) return true;
+    return false;
+  }
+
+  // Graph construction, same traversal as UNetModel.__init__ (openaimodel.py:527-731)
+  int build_graph() {
+    const int mc = cfg.model_channels, temb = 4 * mc;
+    LR_CHECK(cfg.num_levels >= 1 && cfg.num_levels <= 8, "num_levels out of range");
+    LR_CHECK(cfg.num_head_channels == 64, "only num_head_channels == 64 is supported by the attention kernel");
+    LR_CHECK(mc % 64 == 0, "model_channels must be a multiple of 64");
+    LR_CHECK(cfg.context_dim % 8 == 0, "context_dim must be a multiple of 8");
+    te0_w = reg_linear("time_embed.0.weight", temb, mc);
+    te0_b = reg_vec("time_embed.0.bias", temb);
+    te2_w = reg_linear("time_embed.2.weight", temb, temb);
+    te2_b = reg_vec("time_embed.2.bias", temb);
+    kpad_in = ((9 * cfg.in_channels + 63) / 64) * 64;
+    conv_in_idx = add_conv("input_blocks.0.0.", cfg.in_channels, mc, kpad_in);
+    input_blocks.push_back({Node{N_CONV_IN, conv_in_idx}});
+    std::vector<int> chans{mc};
+    int ch = mc, ds = 1, ib = 1;
+    for (int level = 0; level < cfg.num_levels; ++level) {
+      const int mult = cfg.channel_mult[level];
+      for (int nr = 0; nr < cfg.num_res_blocks[level]; ++nr) {
+        const std::string p = "input_blocks." + std::to_string(ib) + ".";
+        std::vector<Node> blk;
+        blk.push_back({N_RES, add_res(p + "0.", ch, mult * mc, temb)});
+        ch = mult * mc;
+        if (attn_at(ds)) blk.push_back({N_ST, add_st(p + "1.", ch)});
+        input_blocks.push_back(blk);
+        chans.push_back(ch);
+        ++ib;
+      }
+      if (level != cfg.num_levels - 1) {
+        const std::string p = "input_blocks." + std::to_string(ib) + ".0.op.";
+        input_blocks.push_back({Node{N_DOWN, add_conv(p, ch, ch, 9 * ch)}});
+        chans.push_back(ch);
+        ds *= 2;
+        ++ib;
+      }
+    }
+    middle.push_back({N_RES, add_res("middle_block.0.", ch, ch, temb)});
+    middle.push_back({N_ST, add_st("middle_block.1.", ch)});
+    middle.push_back({N_RES, add_res("middle_block.2.", ch, ch, temb)});
+    int ob = 0;
+    for (int level = cfg.num_levels - 1; level >= 0; --level) {
+      const int mult = cfg.channel_mult[level];
+      for (int i = 0; i <= cfg.num_res_blocks[level]; ++i) {
+        const int ich = chans.back();
+        chans.pop_back();
+        const std::string p = "output_blocks." + std::to_string(ob) + ".";
+        std::vector<Node> blk;
+        blk.push_back({N_RES, add_res(p + "0.", ch + ich, mc * mult, temb)});
+        ch = mc * mult;
+        int sub = 1;
+        if (attn_at(ds)) {
+          blk.push_back({N_ST, add_st(p + std::to_string(sub) + ".", ch)});
+          ++sub;
+        }
+        if (level > 0 && i == cfg.num_res_blocks[level]) {
+          blk.push_back({N_UP, add_conv(p + std::to_string(sub) + ".conv.", ch, ch, 9 * ch)});
+          ds /= 2;
+        }
+        output_blocks.push_back(blk);
+        ++ob;
+      }
+    }
+    head_gn_g = reg_vec("out.0.weight", ch);
+    head_gn_b = reg_vec("out.0.bias", ch);
+    LR_CHECK(ch == mc, "head channel mismatch");
+    head_idx = add_conv("out.2.", mc, cfg.out_channels, 9 * mc);
+    return 0;
+  }
+
+  int ensure_arenas() {
+    if (harena == nullptr) {
+      LR_CUDA(cudaMalloc(&harena, half_elems * sizeof(__half)));
+      LR_CUDA(cudaMemset(harena, 0, half_elems * sizeof(__half)));
+      LR_CUDA(cudaMalloc(&farena, float_elems * sizeof(float)));
+      LR_CUDA(cudaMemset(farena, 0, float_elems * sizeof(float)));
+      persistent_bytes += half_elems * sizeof(__half) + float_elems * sizeof(float);
+    }
+    return 0;
+  }
+  __half* H(size_t off) { return harena + off; }
+  float* F(size_t off) { return farena + off; }
+
+  // ------------------------------------------------------------------------------------------------------
+  // plan helpers
+  // ------------------------------------------------------------------------------------------------------
+  int acquire_h(size_t elems, __half** out) {
+    void* p = nullptr;
+    LR_TRY(pool.acquire(elems * sizeof(__half), &p));
+    *out = static_cast<__half*>(p);
+    return 0;
+  }
+  int acquire_f(size_t elems, float** out) {
+    void* p = nullptr;
+    LR_TRY(pool.acquire(elems * sizeof(float), &p));
+    *out = static_cast<float*>(p);
+    return 0;
+  }
+  int add_conv_step(const ConvSpec& s) {
+    auto op = std::make_unique<ConvOp>();
+    LR_TRY(build_conv_op(op.get(), s));
+    flops += op->flops;
+    ConvOp* raw = op.get();
+    conv_ops.push_back(std::move(op));
+    steps.push_back([raw](cudaStream_t st) { return launch_conv_op(*raw, st); });
+    return 0;
+  }
+  int add_linear(const __half* a, int M, int K, const __half* w, int ncols, const float* bias, const __half* residual,
+                 int ld_res, __half* out, int ld_out, int geglu) {
+    ConvSpec s;
+    s.a0 = a;
+    s.c0 = K;
+    s.lda0 = K;
+    s.n_img = 1;
+    s.in_h = 1;
+    s.in_w = M;
+    s.taps = 1;
+    s.w = w;
+    s.ldw = K;
+    s.ncols = ncols;
+    s.bias = bias;
+    s.residual = residual;
+    s.ld_res = ld_res;
+    s.out = out;
+    s.ld_out = ld_out;
+    s.geglu = geglu;
+    return add_conv_step(s);
+  }
+  // scratch for GroupNorm
+  double* gn_stats = nullptr;
+  float* gn_scale = nullptr;
+  float* gn_shift = nullptr;
+  int add_gn(const __half* x0, int c0, const __half* x1, int c1, int n, int P, float eps, const float* g,
+             const float* b, int silu, __half* out) {
+    double* st_ = gn_stats;
+    float *sc = gn_scale, *sh = gn_shift;
+    steps.push_back([=](cudaStream_t st) {
+      return launch_groupnorm(x0, c0, x1, c1, n, P, 32, eps, g, b, silu, st_, sc, sh, out, st);
+    });
+    return 0;
+  }
+  int add_ln(const __half* x, int M, int C, const float* g, const float* b, __half* out) {
+    steps.push_back([=](cudaStream_t st) { return launch_layernorm(x, M, C, g, b, 1e-5f, out, st); });
+    return 0;
+  }
+  int add_attn(const AttnSpec& s) {
+    auto op = std::make_unique<AttnOp>();
+    LR_TRY(build_attn_op(op.get(), s));
+    flops += op->flops;
+    AttnOp* raw = op.get();
+    attn_ops.push_back(std::move(op));
+    steps.push_back([raw](cudaStream_t st) { return launch_attn_op(*raw, st); });
+    return 0;
+  }
+
+  std::vector<float*> emb_out;  // per ResBlock [n, cout]
+
+  // ResBlock._forward (openaimodel.py:254-274), x = concat(x0, x1) when x1.p != nullptr
+  int plan_res(const ResW& r, Act x0, Act x1, int n, Act* out) {
+    const int Hh = x0.H, Ww = x0.W, P = Hh * Ww;
+    const size_t M = static_cast<size_t>(n) * P;
+    LR_CHECK(x0.C + x1.C == r.cin, "resblock: channel mismatch");
+    __half *xn, *h, *hn, *o, *skip = nullptr;
+    LR_TRY(acquire_h(M * r.cin, &xn));
+    LR_TRY(add_gn(x0.p, x0.C, x1.p, x1.C, n, P, 1e-5f, F(r.gn1_g), F(r.gn1_b), 1, xn));
+    LR_TRY(acquire_h(M * r.cout, &h));
+    {
+      ConvSpec s;
+      s.a0 = xn;
+      s.c0 = r.cin;
+      s.lda0 = r.cin;
+      s.n_img = n;
+      s.in_h = Hh;
+      s.in_w = Ww;
+      s.taps = 9;
+      s.w = H(r.conv1_w);
+      s.ldw = 9 * r.cin;
+      s.ncols = r.cout;
+      s.bias = F(r.conv1_b);
+      s.bias_img = emb_out[r.emb_slot];
+      s.out = h;
+      s.ld_out = r.cout;
+      LR_TRY(add_conv_step(s));
+    }
+    pool.release(xn);
+    LR_TRY(acquire_h(M * r.cout, &hn));
+    LR_TRY(add_gn(h, r.cout, nullptr, 0, n, P, 1e-5f, F(r.gn2_g), F(r.gn2_b), 1, hn));
+    pool.release(h);
+    const __half* resid;
+    if (r.has_skip) {
+      LR_TRY(acquire_h(M * r.cout, &skip));
+      ConvSpec s;
+      s.a0 = x0.p;
+      s.c0 = x0.C;
+      s.lda0 = x0.C;
+      s.a1 = x1.p;
+      s.c1 = x1.C;
+      s.lda1 = x1.C;
+      s.n_img = 1;
+      s.in_h = 1;
+      s.in_w = static_cast<int>(M);
+      s.taps = 1;
+      s.w = H(r.skip_w);
+      s.ldw = r.cin;
+      s.ncols = r.cout;
+      s.bias = F(r.skip_b);
+      s.out = skip;
+      s.ld_out = r.cout;
+      LR_TRY(add_conv_step(s));
+      resid = skip;
+    } else {
+      LR_CHECK(x1.p == nullptr, "resblock: identity skip with concat input");
+      resid = x0.p;
+    }
+    LR_TRY(acquire_h(M * r.cout, &o));
+    {
+      ConvSpec s;
+      s.a0 = hn;
+      s.c0 = r.cout;
+      s.lda0 = r.cout;
+      s.n_img = n;
+      s.in_h = Hh;
+      s.in_w = Ww;
+      s.taps = 9;
+      s.w = H(r.conv2_w);
+      s.ldw = 9 * r.cout;
+      s.ncols = r.cout;
+      s.bias = F(r.conv2_b);
+      s.residual = resid;
+      s.ld_res = r.cout;
+      s.out = o;
+      s.ld_out = r.cout;
+      LR_TRY(add_conv_step(s));
+    }
+    pool.release(hn);
+    if (skip) pool.release(skip);
+    out->p = o;
+    out->C = r.cout;
+    out->H = Hh;
+    out->W = Ww;
+    return 0;
+  }
+
+  // SpatialTransformer.forward + BasicTransformerBlock._forward (attention.py:393-419, 279-283)
+  int plan_st(const STW& s, Act x, int n, Act* out) {
+    const int C = s.C, P = x.H * x.W;
+    const int M = n * P;
+    LR_CHECK(x.C == C, "spatial transformer: channel mismatch");
+    __half *xn, *h, *t, *qkv, *a, *g, *o;
+    LR_TRY(acquire_h(static_cast<size_t>(M) * C, &xn));
+    LR_TRY(add_gn(x.p, C, nullptr, 0, n, P, 1e-6f, F(s.gn_g), F(s.gn_b), 0, xn));
+    LR_TRY(acquire_h(static_cast<size_t>(M) * C, &h));
+    LR_TRY(add_linear(xn, M, C, H(s.pin_w), C, F(s.pin_b), nullptr, 0, h, C, 0));
+    pool.release(xn);
+    LR_TRY(acquire_h(static_cast<size_t>(M) * C, &t));
+    LR_TRY(acquire_h(static_cast<size_t>(M) * C, &a));
+    for (const TBlockW& b : s.blocks) {
+      // self-attention: x = attn1(norm1(x)) + x
+      LR_TRY(add_ln(h, M, C, F(b.ln1_g), F(b.ln1_b), t));
+      LR_TRY(acquire_h(static_cast<size_t>(M) * 3 * C, &qkv));
+      LR_TRY(add_linear(t, M, C, H(b.qkv_w), 3 * C, nullptr, nullptr, 0, qkv, 3 * C, 0));
+      {
+        // multiview (multiview_attention.py:448,462, concat_target=False): '(b v) hw c -> b (v hw) c' is a pure
+        // reshape of the token matrix, so only batch / sequence length change.
+        const int v = cfg.view_num > 1 ? cfg.view_num : 1;
+        LR_CHECK(n % v == 0, "multiview: batch not divisible by view_num");
+        AttnSpec as;
+        as.q = qkv; as.ldq = 3 * C; as.q_col0 = 0;
+        as.k = qkv; as.ldk = 3 * C; as.k_col0 = C;
+        as.v = qkv; as.ldv = 3 * C; as.v_col0 = 2 * C;
+        as.out = a; as.ld_out = C;
+        as.batch = n / v; as.heads = s.heads; as.tq = P * v; as.tk = P * v;
+        as.scale = 0.125f;
+        LR_TRY(add_attn(as));
+      }
+      pool.release(qkv);
+      LR_TRY(add_linear(a, M, C, H(b.out1_w), C, F(b.out1_b), h, C, h, C, 0));
+      // cross-attention against the cached context K/V
+      LR_TRY(add_ln(h, M, C, F(b.ln2_g), F(b.ln2_b), t));
+      __half* q2;
+      LR_TRY(acquire_h(static_cast<size_t>(M) * C, &q2));
+      LR_TRY(add_linear(t, M, C, H(b.q2_w), C, nullptr, nullptr, 0, q2, C, 0));
+      {
+        AttnSpec as;
+        as.q = q2; as.ldq = C; as.q_col0 = 0;
+        as.k = kv[b.kv_slot]; as.ldk = 2 * C; as.k_col0 = 0;
+        as.v = kv[b.kv_slot]; as.ldv = 2 * C; as.v_col0 = C;
+        as.out = a; as.ld_out = C;
+        as.batch = n; as.heads = s.heads; as.tq = P; as.tk = ctx_L;
+        as.scale = 0.125f;
+        LR_TRY(add_attn(as));
+      }
+      pool.release(q2);
+      LR_TRY(add_linear(a, M, C, H(b.out2_w), C, F(b.out2_b), h, C, h, C, 0));
+      // GEGLU feed-forward
+      LR_TRY(add_ln(h, M, C, F(b.ln3_g), F(b.ln3_b), t));
+      LR_TRY(acquire_h(static_cast<size_t>(M) * 4 * C, &g));
+      LR_TRY(add_linear(t, M, C, H(b.ff1_w), 8 * C, F(b.ff1_b), nullptr, 0, g, 4 * C, 1));
+      LR_TRY(add_linear(g, M, 4 * C, H(b.ff2_w), C, F(b.ff2_b), h, C, h, C, 0));
+      pool.release(g);
+    }
+    pool.release(t);
+    pool.release(a);
+    LR_TRY(acquire_h(static_cast<size_t>(M) * C, &o));
+    LR_TRY(add_linear(h, M, C, H(s.pout_w), C, F(s.pout_b), x.p, C, o, C, 0));
+    pool.release(h);
+    out->p = o;
+    out->C = C;
+    out->H = x.H;
+    out->W = x.W;
+    return 0;
+  }
+
+  int plan_conv3(const ConvW& c, Act x, int n, int stride, Act* out) {
+    ConvSpec s;
+    s.a0 = x.p;
+    s.c0 = x.C;
+    s.lda0 = x.C;
+    s.n_img = n;
+    s.in_h = x.H;
+    s.in_w = x.W;
+    s.stride = stride;
+    s.taps = 9;
+    s.w = H(c.w);
+    s.ldw = 9 * c.cin;
+    s.ncols = c.cout;
+    s.bias = F(c.b);
+    const int Ho = stride == 1 ? x.H : (x.H - 1) / 2 + 1, Wo = stride == 1 ? x.W : (x.W - 1) / 2 + 1;
+    __half* o;
+    LR_TRY(acquire_h(static_cast<size_t>(n) * Ho * Wo * c.cout, &o));
+    s.out = o;
+    s.ld_out = c.cout;
+    LR_TRY(add_conv_step(s));
+    out->p = o;
+    out->C = c.cout;
+    out->H = Ho;
+    out->W = Wo;
+    return 0;
+  }
+
+  int plan_block(const std::vector<Node>& blk, Act h, Act skip, int n, Act* out, bool release_input) {
+    Act cur = h;
+    bool cur_owned = false;  // whether `cur` is a temporary we may release
+    for (size_t i = 0; i < blk.size(); ++i) {
+      Act nxt;
+      const Node& nd = blk[i];
+      if (nd.kind == N_RES) {
+        LR_TRY(plan_res(res[nd.idx], cur, (i == 0) ? skip : Act{}, n, &nxt));
+      } else if (nd.kind == N_ST) {
+        LR_TRY(plan_st(sts[nd.idx], cur, n, &nxt));
+      } else if (nd.kind == N_DOWN) {
+        LR_TRY(plan_conv3(convs[nd.idx], cur, n, 2, &nxt));
+      } else if (nd.kind == N_UP) {
+        // Upsample.forward (openaimodel.py:108-116): nearest x2 then conv3x3
+        __half* up;
+        LR_TRY(acquire_h(static_cast<size_t>(n) * 4 * cur.H * cur.W * cur.C, &up));
+        const __half* src = cur.p;
+        const int hh = cur.H, ww = cur.W, cc = cur.C;
+        steps.push_back([=](cudaStream_t st) { return launch_upsample2x(src, n, hh, ww, cc, up, st); });
+        Act u{up, cur.C, 2 * cur.H, 2 * cur.W};
+        LR_TRY(plan_conv3(convs[nd.idx], u, n, 1, &nxt));
+        pool.release(up);
+      } else {
+        LR_CHECK(false, "unexpected node");
+      }
+      if (cur_owned || (i == 0 && release_input)) pool.release(cur.p);
+      if (i == 0 && skip.p != nullptr) pool.release(skip.p);
+      cur = nxt;
+      cur_owned = true;
+    }
+    *out = cur;
+    return 0;
+  }
+
+  int build_kv_cache(int n, int L) {
+    if (ctx_n == n && ctx_L == L && ctx_h != nullptr) return 0;
+    if (ctx_h) cudaFree(ctx_h);
+    for (auto p : kv)
+      if (p) cudaFree(p);
+    kv.assign(n_kv_slots, nullptr);
+    kv_ops.clear();
+    const size_t rows = static_cast<size_t>(n) * L;
+    LR_CUDA(cudaMalloc(&ctx_h, rows * cfg.context_dim * sizeof(__half)));
+    for (int i = 0; i < n_kv_slots; ++i) LR_CUDA(cudaMalloc(&kv[i], rows * 2 * kv_C[i] * sizeof(__half)));
+    // one GEMM per transformer block: [n*L, ctx] x [2C, ctx]^T
+    for (const STW& s : sts) {
+      for (const TBlockW& b : s.blocks) {
+        ConvSpec cs;
+        cs.a0 = ctx_h;
+        cs.c0 = cfg.context_dim;
+        cs.lda0 = cfg.context_dim;
+        cs.n_img = 1;
+        cs.in_h = 1;
+        cs.in_w = static_cast<int>(rows);
+        cs.taps = 1;
+        cs.w = H(b.kv2_w);
+        cs.ldw = cfg.context_dim;
+        cs.ncols = 2 * s.C;
+        cs.out = kv[b.kv_slot];
+        cs.ld_out = 2 * s.C;
+        auto op = std::make_unique<ConvOp>();
+        LR_TRY(build_conv_op(op.get(), cs));
+        kv_ops.push_back(std::move(op));
+      }
+    }
+    ctx_n = n;
+    ctx_L = L;
+    ctx_valid = false;
+    pn = 0;  // attention ops hold kv pointers: force a re-plan
+    return 0;
+  }
+
+  int set_context(const float* ctx, int n, int L, cudaStream_t st) {
+    LR_TRY(ensure_arenas());
+    LR_TRY(build_kv_cache(n, L));
+    LR_TRY(launch_cast_f32_f16(ctx, static_cast<size_t>(n) * L * cfg.context_dim, ctx_h, st));
+    for (auto& op : kv_ops) LR_TRY(launch_conv_op(*op, st));
+    ctx_valid = true;
+    return 0;
+  }
+
+  int build_plan(int n, int Hh, int Ww) {
+    if (pn == n && ph == Hh && pw == Ww) return 0;
+    steps.clear();
+    conv_ops.clear();
+    attn_ops.clear();
+    pool.clear();
+    emb_out.clear();
+    flops = 0;
+    pn = 0;
+    const int mc = cfg.model_channels, temb = 4 * mc;
+    int maxC = 0;
+    for (const ResW& r : res) maxC = std::max(maxC, std::max(r.cin, r.cout));
+    {
+      void* p;
+      LR_TRY(pool.acquire(sizeof(double) * n * 32 * 2, &p));
+      gn_stats = static_cast<double*>(p);
+    }
+    LR_TRY(acquire_f(static_cast<size_t>(n) * maxC, &gn_scale));
+    LR_TRY(acquire_f(static_cast<size_t>(n) * maxC, &gn_shift));
+    // --- timestep path (openaimodel.py:768-769 + every ResBlock's emb_layers, :263) ---
+    float *tsin, *e1, *emb;
+    LR_TRY(acquire_f(static_cast<size_t>(n) * mc, &tsin));
+    LR_TRY(acquire_f(static_cast<size_t>(n) * temb, &e1));
+    LR_TRY(acquire_f(static_cast<size_t>(n) * temb, &emb));
+    steps.push_back([=](cudaStream_t st) {
+      return launch_timestep_embedding(reinterpret_cast<const long long*>(this->in_t), n, mc, tsin, st);
+    });
+    {
+      const __half* w0 = H(te0_w);
+      const float* b0 = F(te0_b);
+      const __half* w2 = H(te2_w);
+      const float* b2 = F(te2_b);
+      steps.push_back(
+          [=](cudaStream_t st) { return launch_small_linear(tsin, mc, n, mc, w0, b0, temb, 0, 1, e1, temb, st); });
+      steps.push_back(
+          [=](cudaStream_t st) { return launch_small_linear(e1, temb, n, temb, w2, b2, temb, 0, 0, emb, temb, st); });
+    }
+    for (const ResW& r : res) {
+      float* eo;
+      LR_TRY(acquire_f(static_cast<size_t>(n) * r.cout, &eo));
+      emb_out.push_back(eo);
+      const __half* w = H(r.emb_w);
+      const float* b = F(r.emb_b);
+      const int co = r.cout;
+      steps.push_back(
+          [=](cudaStream_t st) { return launch_small_linear(emb, temb, n, temb, w, b, co, 1, 0, eo, co, st); });
+    }
+    // --- input conv: im2col of the NCHW fp32 boundary tensor, then a GEMM ---
+    const size_t M0 = static_cast<size_t>(n) * Hh * Ww;
+    __half* col;
+    LR_TRY(acquire_h(M0 * kpad_in, &col));
+    {
+      const int cin = cfg.in_channels, kp = kpad_in;
+      steps.push_back(
+          [=](cudaStream_t st) { return launch_im2col_nchw_f32(this->in_x, n, cin, Hh, Ww, kp, col, st); });
+    }
+    Act h;
+    {
+      __half* o;
+      LR_TRY(acquire_h(M0 * mc, &o));
+      const ConvW& c = convs[conv_in_idx];
+      LR_TRY(add_linear(col, static_cast<int>(M0), kpad_in, H(c.w), mc, F(c.b), nullptr, 0, o, mc, 0));
+      h = Act{o, mc, Hh, Ww};
+    }
+    pool.release(col);
+    std::vector<Act> hs{h};
+    for (size_t i = 1; i < input_blocks.size(); ++i) {
+      Act o;
+      LR_TRY(plan_block(input_blocks[i], h, Act{}, n, &o, false));
+      hs.push_back(o);
+      h = o;
+    }
+    {
+      Act o;
+      LR_TRY(plan_block(middle, h, Act{}, n, &o, false));
+      h = o;
+    }
+    for (size_t i = 0; i < output_blocks.size(); ++i) {
+      Act skip = hs.back();
+      hs.pop_back();
+      LR_CHECK(skip.H == h.H && skip.W == h.W, "skip connection spatial mismatch (H, W must be divisible by 2^levels)");
+      Act o;
+      // h is a temporary except right after the middle block when it still aliases nothing in hs
+      LR_TRY(plan_block(output_blocks[i], h, skip, n, &o, true));
+      h = o;
+    }
+    // --- head: GroupNorm32 -> SiLU -> conv3x3 (openaimodel.py:727-731,787) ---
+    {
+      __half *hn, *y;
+      LR_TRY(acquire_h(M0 * mc, &hn));
+      LR_TRY(add_gn(h.p, mc, nullptr, 0, n, Hh * Ww, 1e-5f, F(head_gn_g), F(head_gn_b), 1, hn));
+      const ConvW& c = convs[head_idx];
+      LR_TRY(acquire_h(M0 * c.cout, &y));
+      ConvSpec s;
+      s.a0 = hn;
+      s.c0 = mc;
+      s.lda0 = mc;
+      s.n_img = n;
+      s.in_h = Hh;
+      s.in_w = Ww;
+      s.taps = 9;
+      s.w = H(c.w);
+      s.ldw = 9 * mc;
+      s.ncols = c.cout;
+      s.bias = F(c.b);
+      s.out = y;
+      s.ld_out = c.cout;
+      LR_TRY(add_conv_step(s));
+      const int co = c.cout;
+      steps.push_back(
+          [=](cudaStream_t st) { return launch_nhwc_to_nchw_f32(y, co, n, co, Hh, Ww, this->out_y, st); });
+    }
+    pn = n;
+    ph = Hh;
+    pw = Ww;
+    return 0;
+  }
+};
+
+// ==============================================================================================================
+// C ABI
+// ==============================================================================================================
+extern "C" {
+
+int lr_abi_version(void) { return LR_B200_ABI_VERSION; }
+const char* lr_last_error(void) { return lr::last_error(); }
+long long lr_launch_count(void) { return lr::launches_since_reset(); }
+void lr_launch_count_reset(void) { lr::reset_launch_counter(); }
+
+int lr_unet_create(const lr_unet_cfg* cfg, lr_unet** out) {
+  LR_CHECK(cfg != nullptr && out != nullptr, "lr_unet_create: null argument");
+  auto h = std::make_unique<lr_unet>();
+  h->cfg = *cfg;
+  if (h->cfg.view_num < 1) h->cfg.view_num = 1;
+  LR_CHECK(h->cfg.transformer_depth >= 1, "transformer_depth must be >= 1");
+  LR_CHECK(!(h->cfg.view_num > 1 && h->cfg.concat_target),
+           "multiview concat_target=True re-arranged attention is not implemented yet");
+  LR_TRY(h->build_graph());
+  *out = h.release();
+  return 0;
+}
+void lr_unet_destroy(lr_unet* h) { delete h; }
+
+int lr_unet_num_weights(const lr_unet* h) { return h ? static_cast<int>(h->weights.size()) : 0; }
+const char* lr_unet_weight_name(const lr_unet* h, int i) {
+  if (!h || i < 0 || i >= static_cast<int>(h->weights.size())) return nullptr;
+  return h->weights[i].name.c_str();
+}
+int lr_unet_weight_shape(const lr_unet* h, int i, int64_t shape_out[4]) {
+  if (!h || i < 0 || i >= static_cast<int>(h->weights.size())) return -1;
+  for (int d = 0; d < 4; ++d) shape_out[d] = h->weights[i].shape[d];
+  return h->weights[i].ndim;
+}
+int lr_unet_missing_weights(const lr_unet* h) {
+  int m = 0;
+  for (const auto& w : h->weights) m += w.loaded ? 0 : 1;
+  return m;
+}
+
+int lr_unet_set_weight(lr_unet* h, const char* name, const float* data, const int64_t* shape, int ndim, void* stream) {
+  LR_CHECK(h && name && data && shape, "lr_unet_set_weight: null argument");
+  auto it = h->windex.find(name);
+  LR_CHECK(it != h->windex.end(), std::string("lr_unet_set_weight: unknown weight '") + name + "'");
+  Weight& w = h->weights[it->second];
+  bool ok = (ndim == w.ndim);
+  for (int i = 0; ok && i < ndim; ++i) ok = (shape[i] == w.shape[i]);
+  // a Linear registered as [O, I] also accepts the 1x1-conv form [O, I, 1, 1] and vice versa
+  if (!ok && w.kind == K_LINEAR) {
+    ok = (ndim == 2 || ndim == 4) && shape[0] == w.shape[0] && shape[1] == w.shape[1] &&
+         (ndim == 2 || (shape[2] == 1 && shape[3] == 1));
+  }
+  LR_CHECK(ok, std::string("lr_unet_set_weight: shape mismatch for '") + name + "'");
+  LR_TRY(h->ensure_arenas());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int O = static_cast<int>(w.shape[0]);
+  switch (w.kind) {
+    case K_CONV3:
+      LR_TRY(launch_repack_conv(data, O, static_cast<int>(w.shape[1]), w.ld, h->H(w.off), st));
+      break;
+    case K_LINEAR:
+      LR_TRY(launch_repack_linear(data, O, static_cast<int>(w.shape[1]), 0, w.dst_row0, h->H(w.off), st));
+      break;
+    case K_LINEAR_GEGLU:
+      LR_TRY(launch_repack_linear(data, O, static_cast<int>(w.shape[1]), 1, 0, h->H(w.off), st));
+      break;
+    case K_VEC:
+      LR_TRY(launch_repack_bias(data, O, 0, h->F(w.off), st));
+      break;
+    case K_VEC_GEGLU:
+      LR_TRY(launch_repack_bias(data, O, 1, h->F(w.off), st));
+      break;
+  }
+  w.loaded = true;
+  h->ctx_valid = false;  // cached K/V depend on attn2.to_k / to_v
+  return 0;
+}
+
+int lr_unet_set_context(lr_unet* h, const float* context, int n, int L, void* stream) {
+  LR_CHECK(h && context, "lr_unet_set_context: null argument");
+  LR_CHECK(lr_unet_missing_weights(h) == 0, "lr_unet_set_context: weights missing");
+  return h->set_context(context, n, L, static_cast<cudaStream_t>(stream));
+}
+
+int lr_unet_forward(lr_unet* h, const float* x, const int64_t* timesteps, const float* context, int L, float* out,
+                    int n, int H, int W, void* stream) {
+  LR_CHECK(h && x && timesteps && out, "lr_unet_forward: null argument");
+  LR_CHECK(n > 0 && H > 0 && W > 0, "lr_unet_forward: empty input");
+  const int missing = lr_unet_missing_weights(h);
+  LR_CHECK(missing == 0, "lr_unet_forward: " + std::to_string(missing) + " weights not uploaded");
+  const int div = 1 << (h->cfg.num_levels - 1);
+  LR_CHECK(H % div == 0 && W % div == 0, "lr_unet_forward: H and W must be divisible by 2^(levels-1)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (context != nullptr) {
+    LR_TRY(h->set_context(context, n, L, st));
+  } else {
+    LR_CHECK(h->ctx_valid && h->ctx_n == n, "lr_unet_forward: no cached context for this batch size");
+  }
+  LR_TRY(h->build_plan(n, H, W));
+  h->in_x = x;
+  h->in_t = timesteps;
+  h->out_y = out;
+  for (auto& s : h->steps) LR_TRY(s(st));
+  return 0;
+}
+
+double lr_unet_last_flops(const lr_unet* h) { return h ? h->flops : 0.0; }
+long long lr_unet_device_bytes(const lr_unet* h) {
+  return h ? static_cast<long long>(h->persistent_bytes + h->pool.total) : 0;
+}
+
+int lr_ddim_update(const float* x, const float* eps_uncond, const float* eps_cond, const float* noise, float cfg_scale,
+                   float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at, float temperature, int64_t numel,
+                   float* x_prev, float* pred_x0, void* stream) {
+  LR_CHECK(x && eps_uncond && x_prev && pred_x0 && numel >= 0, "lr_ddim_update: bad argument");
+  if (numel == 0) return 0;
+  return launch_ddim_update(x, eps_uncond, eps_cond, noise, cfg_scale, a_t, a_prev, sigma_t, sqrt_one_minus_at,
+                            temperature, static_cast<size_t>(numel), x_prev, pred_x0,
+                            static_cast<cudaStream_t>(stream));
+}
+
+// ---- op level ----------------------------------------------------------------------------------------------
+int lr_linear_f16(const void* a, int lda, int M, int K, const void* w, int ldw, int n_cols, const float* bias,
+                  const void* residual, int ld_res, void* out, int ld_out, int geglu, int force_block_n, void* stream) {
+  if (M == 0) return 0;
+  ConvSpec s;
+  s.a0 = static_cast<const __half*>(a);
+  s.c0 = K;
+  s.lda0 = lda;
+  s.n_img = 1;
+  s.in_h = 1;
+  s.in_w = M;
+  s.taps = 1;
+  s.w = static_cast<const __half*>(w);
+  s.ldw = ldw;
+  s.ncols = geglu ? 2 * n_cols : n_cols;
+  s.bias = bias;
+  s.residual = static_cast<const __half*>(residual);
+  s.ld_res = ld_res;
+  s.out = static_cast<__half*>(out);
+  s.ld_out = ld_out;
+  s.geglu = geglu;
+  s.force_block_n = force_block_n;
+  ConvOp op;
+  LR_TRY(build_conv_op(&op, s));
+  return launch_conv_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int lr_conv3x3_f16(const void* x0, int c0, const void* x1, int c1, int n, int h, int w, int stride, const void* wt,
+                   int cout, const float* bias, const float* bias_img, const void* residual, void* out,
+                   int force_block_n, void* stream) {
+  if (n == 0) return 0;
+  ConvSpec s;
+  s.a0 = static_cast<const __half*>(x0);
+  s.c0 = c0;
+  s.lda0 = c0;
+  s.a1 = static_cast<const __half*>(x1);
+  s.c1 = x1 ? c1 : 0;
+  s.lda1 = c1;
+  s.n_img = n;
+  s.in_h = h;
+  s.in_w = w;
+  s.stride = stride;
+  s.taps = 9;
+  s.w = static_cast<const __half*>(wt);
+  s.ldw = 9 * (c0 + s.c1);
+  s.ncols = cout;
+  s.bias = bias;
+  s.bias_img = bias_img;
+  s.residual = static_cast<const __half*>(residual);
+  s.ld_res = cout;
+  s.out = static_cast<__half*>(out);
+  s.ld_out = cout;
+  s.force_block_n = force_block_n;
+  ConvOp op;
+  LR_TRY(build_conv_op(&op, s));
+  return launch_conv_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int lr_attention_f16(const void* q, int ldq, int q_col0, const void* k, int ldk, int k_col0, const void* v, int ldv,
+                     int v_col0, void* out, int ld_out, int batch, int heads, int tq, int tk, float scale,
+                     void* stream) {
+  if (batch == 0 || tq == 0) return 0;
+  AttnSpec s;
+  s.q = static_cast<const __half*>(q); s.ldq = ldq; s.q_col0 = q_col0;
+  s.k = static_cast<const __half*>(k); s.ldk = ldk; s.k_col0 = k_col0;
+  s.v = static_cast<const __half*>(v); s.ldv = ldv; s.v_col0 = v_col0;
+  s.out = static_cast<__half*>(out); s.ld_out = ld_out;
+  s.batch = batch; s.heads = heads; s.tq = tq; s.tk = tk; s.scale = scale;
+  AttnOp op;
+  LR_TRY(build_attn_op(&op, s));
+  return launch_attn_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int lr_groupnorm_f16(const void* x0, int c0, const void* x1, int c1, int n, int P, int groups, float eps,
+                     const float* gamma, const float* beta, int silu, void* out, void* scratch, void* stream) {
+  LR_CHECK(x0 && gamma && beta && out && scratch, "lr_groupnorm_f16: null argument");
+  if (n == 0 || P == 0) return 0;
+  const int C = c0 + (x1 ? c1 : 0);
+  double* stats = static_cast<double*>(scratch);
+  float* scale = reinterpret_cast<float*>(stats + static_cast<size_t>(n) * groups * 2);
+  float* shift = scale + static_cast<size_t>(n) * C;
+  return launch_groupnorm(static_cast<const __half*>(x0), c0, static_cast<const __half*>(x1), x1 ? c1 : 0, n, P, groups,
+                          eps, gamma, beta, silu, stats, scale, shift, static_cast<__half*>(out),
+                          static_cast<cudaStream_t>(stream));
+}
+int lr_layernorm_f16(const void* x, int M, int C, const float* gamma, const float* beta, float eps, void* out,
+                     void* stream) {
+  LR_CHECK(x && gamma && beta && out, "lr_layernorm_f16: null argument");
+  if (M == 0) return 0;
+  return launch_layernorm(static_cast<const __half*>(x), M, C, gamma, beta, eps, static_cast<__half*>(out),
+                          static_cast<cudaStream_t>(stream));
+}
+int lr_nchw_f32_to_nhwc_f16(const float* x, int n, int c, int h, int w, void* out, void* stream) {
+  if (static_cast<size_t>(n) * c * h * w == 0) return 0;
+  return launch_nchw_f32_to_nhwc(x, n, c, h, w, static_cast<__half*>(out), static_cast<cudaStream_t>(stream));
+}
+int lr_nhwc_f16_to_nchw_f32(const void* x, int ld, int n, int c, int h, int w, float* out, void* stream) {
+  if (static_cast<size_t>(n) * c * h * w == 0) return 0;
+  return launch_nhwc_to_nchw_f32(static_cast<const __half*>(x), ld, n, c, h, w, out, static_cast<cudaStream_t>(stream));
+}
+int lr_repack_conv3x3_weight(const float* w_oihw, int cout, int cin, void* out, void* stream) {
+  return launch_repack_conv(w_oihw, cout, cin, 9 * cin, static_cast<__half*>(out), static_cast<cudaStream_t>(stream));
+}
+int lr_repack_linear_weight(const float* w, int n_out, int n_in, int geglu, void* out, void* stream) {
+  return launch_repack_linear(w, n_out, n_in, geglu, 0, static_cast<__half*>(out), static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,280 @@
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   out[M, N] = epilogue( sum_{tap, c} A[pixel(m) + tap, c] * Wt[n, tap*Ctot + c] )
+//
+// Activations are NHWC fp16 (pixel-major rows, channels contiguous), so
+//   * a Linear layer is the degenerate geometry  W = M, H = 1, images = 1, taps = 1;
+//   * a 3x3 convolution (ResBlock in/out layers, Downsample, Upsample conv: reference
+//     ldm/modules/diffusionmodules/openaimodel.py:90-118,133-159,200-231) is 9 taps, each a TMA box shifted by
+//     (dy, dx) in the (x, y) coordinates of a 4-D tensor map [C, W, H, N]; TMA out-of-bounds zero fill IS the
+//     conv padding, and the tensor map's element strides implement stride 2.
+//   * the skip concat `th.cat([h, hs.pop()], 1)` (openaimodel.py:781) is never materialised: the K loop walks two
+//     tensor maps (source 0 = h, source 1 = skip) back to back.
+//
+// Structure (one CTA per SM, persistent over output tiles of 128 x block_n):
+//   warp 0 (1 lane)  TMA producer      -> smem ring of {A 128x64, B block_n x 64} fp16 stages, 128B swizzle
+//   warp 1 (1 lane)  tcgen05.mma issue -> fp32 accumulator in TMEM, double buffered (2 x 256 columns)
+//   warps 2..5       epilogue          -> tcgen05.ld, bias / per-image bias (time embedding) / residual / GEGLU,
+//                                         fp16 stores
+#pragma once
+#include "ptx.cuh"
+
+namespace lr {
+
+struct GemmParams {
+  CUtensorMap tmA0;  // source 0 activations [C0, W, H, N] (conv) or [K, M, 1, 1] (linear)
+  CUtensorMap tmA1;  // source 1 (skip connection) or a copy of tmA0
+  CUtensorMap tmB;   // weights [Ktot, Ncols], K contiguous
+  int n_img, H, W;   // OUTPUT pixel grid
+  int bw, bh, bn;    // tile box: bw*bh*bn == 128 output pixels
+  int tiles_x, tiles_y, tiles_b, tiles_n;
+  int stride;        // 1 or 2 (input coordinate = stride * output coordinate + tap offset)
+  int taps;          // 1 or 9
+  int kc0, kc1;      // 64-channel chunks per tap in source 0 / source 1
+  int c0, ctot;      // channels of source 0, total channels (K extent of one tap in B)
+  int ncols;         // GEMM N
+  int block_n;       // UMMA N (multiple of 32, <= 256)
+  int stages;        // smem ring depth
+  const float* bias;       // [ncols] or nullptr
+  const float* bias_img;   // [n_img, ncols] or nullptr (ResBlock emb_layers output, openaimodel.py:263-272)
+  const __half* residual;  // [M, ld_res] or nullptr, added after bias
+  int ld_res;
+  __half* out;             // [M, ld_out]
+  int ld_out;
+  int geglu;               // accumulator columns are (value, gate) pairs -> out[:, j] = v * gelu(g) (attention.py:51-58)
+  int n_valid;             // valid output columns (after GEGLU halving)
+  float out_scale;         // multiplies the final value (1.0 normally)
+};
+
+constexpr int kGemmThreads = 192;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kMaxStages = 8;
+
+__host__ __device__ inline int gemm_stage_bytes(int block_n) { return kATileBytes + block_n * kBlockK * 2; }
+__host__ inline int gemm_smem_bytes(int block_n, int stages) {
+  return 1024 /*align slack*/ + stages * gemm_stage_bytes(block_n) + 256 /*barriers*/;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = gemm_stage_bytes(p.block_n);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* full = bars;                   // [kMaxStages]
+  uint64_t* empty = bars + kMaxStages;     // [kMaxStages]
+  uint64_t* tfull = bars + 2 * kMaxStages; // [2]
+  uint64_t* tempty = tfull + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    tma_prefetch_desc(&p.tmA1);
+    tma_prefetch_desc(&p.tmB);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int num_tiles = tiles_m * p.tiles_n;
+  const int kiters = p.taps * (p.kc0 + p.kc1);
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tn = tile % p.tiles_n;
+        int tm = tile / p.tiles_n;
+        const int tx = tm % p.tiles_x;
+        tm /= p.tiles_x;
+        const int ty = tm % p.tiles_y;
+        const int tb = tm / p.tiles_y;
+        const int x0 = tx * p.bw * p.stride, y0 = ty * p.bh * p.stride, n0 = tb * p.bn;
+        const int ncol0 = tn * p.block_n;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+          const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+          for (int kc = 0; kc < p.kc0 + p.kc1; ++kc) {
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* a_s = smem + s * stage_bytes;
+            uint8_t* b_s = a_s + kATileBytes;
+            mbar_arrive_expect_tx(&full[s], stage_bytes);
+            int kb;
+            if (kc < p.kc0) {
+              tma_load_4d(a_s, &p.tmA0, &full[s], kc * kBlockK, x0 + dx, y0 + dy, n0);
+              kb = tap * p.ctot + kc * kBlockK;
+            } else {
+              tma_load_4d(a_s, &p.tmA1, &full[s], (kc - p.kc0) * kBlockK, x0 + dx, y0 + dy, n0);
+              kb = tap * p.ctot + p.c0 + (kc - p.kc0) * kBlockK;
+            }
+            tma_load_2d(b_s, &p.tmB, &full[s], kb, ncol0);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(kBlockM, p.block_n, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t ad = umma_smem_desc_sw128(a_addr + k * 32, 1024, 16);
+            const uint64_t bd = umma_smem_desc_sw128(b_addr + k * 32, 1024, 16);
+            umma_f16(d_tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps -----------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    int as = 0;
+    uint32_t aph = 0;
+    const bool vec_ok = (p.ld_out % 8 == 0) && (p.residual == nullptr || p.ld_res % 8 == 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tn = tile % p.tiles_n;
+      int tm = tile / p.tiles_n;
+      const int tx = tm % p.tiles_x;
+      tm /= p.tiles_x;
+      const int ty = tm % p.tiles_y;
+      const int tb = tm / p.tiles_y;
+      const int xi = r % p.bw;
+      const int yi = (r / p.bw) % p.bh;
+      const int ni = r / (p.bw * p.bh);
+      const int x = tx * p.bw + xi, y = ty * p.bh + yi, n = tb * p.bn + ni;
+      const bool row_ok = (x < p.W) && (y < p.H) && (n < p.n_img);
+      const size_t grow = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+      const int ncol0 = tn * p.block_n;
+
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
+      for (int c = 0; c < p.block_n; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_row + c, v);
+        tmem_ld_wait();
+        const int col0 = ncol0 + c;
+        if (row_ok && col0 < p.ncols) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.ncols) f[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.bias_img != nullptr) {
+            const float* bi = p.bias_img + static_cast<size_t>(n) * p.ncols + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.ncols) f[j] += __ldg(bi + j);
+          }
+          if (p.geglu) {
+            const int oc0 = col0 >> 1;
+            __half* o = p.out + grow * p.ld_out + oc0;
+            float g[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] = f[2 * j] * gelu_erf(f[2 * j + 1]) * p.out_scale;
+            if (vec_ok && oc0 + 16 <= p.n_valid) {
+              uint4 w0 = make_uint4(pack_half2(g[0], g[1]), pack_half2(g[2], g[3]), pack_half2(g[4], g[5]),
+                                    pack_half2(g[6], g[7]));
+              uint4 w1 = make_uint4(pack_half2(g[8], g[9]), pack_half2(g[10], g[11]), pack_half2(g[12], g[13]),
+                                    pack_half2(g[14], g[15]));
+              reinterpret_cast<uint4*>(o)[0] = w0;
+              reinterpret_cast<uint4*>(o)[1] = w1;
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (oc0 + j < p.n_valid) o[j] = __float2half_rn(g[j]);
+            }
+          } else {
+            __half* o = p.out + grow * p.ld_out + col0;
+            if (vec_ok && col0 + 32 <= p.n_valid) {
+              if (p.residual != nullptr) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + grow * p.ld_res + col0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint4 rv = __ldg(rp + k);
+                  const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int h = 0; h < 4; ++h) {
+                    const float2 t = unpack_half2(rw[h]);
+                    f[k * 8 + h * 2] += t.x;
+                    f[k * 8 + h * 2 + 1] += t.y;
+                  }
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint4 w = make_uint4(pack_half2(f[k * 8 + 0] * p.out_scale, f[k * 8 + 1] * p.out_scale),
+                                     pack_half2(f[k * 8 + 2] * p.out_scale, f[k * 8 + 3] * p.out_scale),
+                                     pack_half2(f[k * 8 + 4] * p.out_scale, f[k * 8 + 5] * p.out_scale),
+                                     pack_half2(f[k * 8 + 6] * p.out_scale, f[k * 8 + 7] * p.out_scale));
+                reinterpret_cast<uint4*>(o)[k] = w;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j) {
+                if (col0 + j < p.n_valid) {
+                  float t = f[j];
+                  if (p.residual != nullptr) t += __half2float(p.residual[grow * p.ld_res + col0 + j]);
+                  o[j] = __float2half_rn(t * p.out_scale);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace lr

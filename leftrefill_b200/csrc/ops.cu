@@ -1,0 +1,377 @@
+// Op layer implementation: TMA descriptor construction, launch geometry heuristics, kernel launches.
+#include "ops.h"
+
+#include <atomic>
+#include <cstring>
+#include <mutex>
+
+#include "attention_tc.cuh"
+#include "elementwise.cuh"
+#include "gemm_tc.cuh"
+
+namespace lr {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error() { return g_err.c_str(); }
+
+static std::atomic<long long> g_launches{0};
+long long launches_since_reset() { return g_launches.load(); }
+void reset_launch_counter() { g_launches.store(0); }
+#define LR_LAUNCHED()                                        \
+  do {                                                       \
+    g_launches.fetch_add(1, std::memory_order_relaxed);      \
+    LR_CUDA(cudaGetLastError());                             \
+  } while (0)
+
+static_assert(sizeof(GemmParams) <= sizeof(ConvOp::params), "GemmParams too large");
+static_assert(sizeof(AttnParams) <= sizeof(AttnOp::params), "AttnParams too large");
+
+// ------------------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// fp16 tensor map, 128B swizzle; dims innermost first; strides (bytes) for dims 1..rank-1.
+static int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box, const uint32_t* estr) {
+  EncodeTiledFn fn = get_encode_fn();
+  LR_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  LR_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA: global address must be 16-byte aligned");
+  for (int i = 0; i < rank - 1; ++i) LR_CHECK(strides[i] % 16 == 0, "TMA: global strides must be multiples of 16 B");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr),
+                  reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides),
+                  reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(estr),
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) + " (rank " +
+              std::to_string(rank) + ", dims " + std::to_string(dims[0]) + "," + std::to_string(dims[1]) + ", box " +
+              std::to_string(box[0]) + "," + std::to_string(box[1]) + ")");
+    return 1;
+  }
+  return 0;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GEMM / conv op
+// ------------------------------------------------------------------------------------------------------------
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+int build_conv_op(ConvOp* op, const ConvSpec& s) {
+  LR_CHECK(s.a0 && s.w && s.out, "conv: null pointer");
+  LR_CHECK(s.taps == 1 || s.taps == 9, "conv: taps must be 1 or 9");
+  LR_CHECK(s.stride == 1 || s.stride == 2, "conv: stride must be 1 or 2");
+  LR_CHECK(s.c0 % 8 == 0 && s.c1 % 8 == 0 && s.lda0 % 8 == 0 && (s.a1 == nullptr || s.lda1 % 8 == 0),
+           "conv: channel counts / leading dims must be multiples of 8 (use the im2col path otherwise)");
+  LR_CHECK(s.ldw % 8 == 0, "conv: weight leading dim must be a multiple of 8");
+  LR_CHECK(s.a1 != nullptr || s.c1 == 0, "conv: c1 without a1");
+  LR_CHECK(s.a1 == nullptr || s.c0 % 64 == 0, "conv: two-source K split requires c0 % 64 == 0");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int Ho = (s.stride == 1) ? s.in_h : (s.in_h - 1) / 2 + 1;
+  const int Wo = (s.stride == 1) ? s.in_w : (s.in_w - 1) / 2 + 1;
+  op->out_h = Ho;
+  op->out_w = Wo;
+  // tile box: power-of-two (bw, bh, bn) with product 128 minimising the number of (partially empty) tiles
+  int best_tiles = INT32_MAX, bw = 128, bh = 1, bn = 1;
+  for (int w = 128; w >= 1; w >>= 1) {
+    for (int h = 128 / w; h >= 1; h >>= 1) {
+      const int n = 128 / (w * h);
+      const long long t = 1LL * cdiv(Wo, w) * cdiv(Ho, h) * cdiv(s.n_img, n);
+      if (t < best_tiles) {
+        best_tiles = static_cast<int>(t);
+        bw = w;
+        bh = h;
+        bn = n;
+      }
+    }
+  }
+  p.n_img = s.n_img;
+  p.H = Ho;
+  p.W = Wo;
+  p.bw = bw;
+  p.bh = bh;
+  p.bn = bn;
+  p.tiles_x = cdiv(Wo, bw);
+  p.tiles_y = cdiv(Ho, bh);
+  p.tiles_b = cdiv(s.n_img, bn);
+  p.stride = s.stride;
+  p.taps = s.taps;
+  p.kc0 = cdiv(s.c0, kBlockK);
+  p.kc1 = cdiv(s.c1, kBlockK);
+  p.c0 = s.c0;
+  p.ctot = s.c0 + s.c1;
+  p.ncols = s.ncols;
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
+  // block_n: minimise waves * (block_n + fixed overhead)
+  int block_n = s.force_block_n;
+  if (block_n == 0) {
+    long long best = INT64_MAX;
+    for (int bnn = 256; bnn >= 32; bnn -= 32) {
+      const long long tiles = 1LL * tiles_m * cdiv(s.ncols, bnn);
+      const long long waves = (tiles + sm_count() - 1) / sm_count();
+      const long long cost = waves * (bnn + 40);
+      if (cost < best) {
+        best = cost;
+        block_n = bnn;
+      }
+    }
+  }
+  LR_CHECK(block_n % 32 == 0 && block_n >= 32 && block_n <= 256, "conv: bad block_n");
+  LR_CHECK(!s.geglu || (s.ncols % 2 == 0), "conv: GEGLU needs an even column count");
+  p.block_n = block_n;
+  p.tiles_n = cdiv(s.ncols, block_n);
+  int stages = (232448 - 1024 - 256) / gemm_stage_bytes(block_n);
+  if (stages > kMaxStages) stages = kMaxStages;
+  LR_CHECK(stages >= 2, "conv: not enough shared memory for 2 stages");
+  p.stages = stages;
+  p.bias = s.bias;
+  p.bias_img = s.bias_img;
+  p.residual = s.residual;
+  p.ld_res = s.ld_res;
+  p.out = s.out;
+  p.ld_out = s.ld_out;
+  p.geglu = s.geglu;
+  p.n_valid = s.geglu ? s.ncols / 2 : s.ncols;
+  p.out_scale = 1.0f;
+  LR_CHECK(!(s.geglu && s.residual), "conv: GEGLU + residual not supported");
+
+  // activations: [C, W, H, N]
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(s.c0), static_cast<uint64_t>(s.in_w), static_cast<uint64_t>(s.in_h),
+                        static_cast<uint64_t>(s.n_img)};
+    uint64_t str[3] = {static_cast<uint64_t>(s.lda0) * 2, static_cast<uint64_t>(s.lda0) * 2 * s.in_w,
+                       static_cast<uint64_t>(s.lda0) * 2 * s.in_w * s.in_h};
+    uint32_t box[4] = {kBlockK, static_cast<uint32_t>(bw * s.stride), static_cast<uint32_t>(bh * s.stride),
+                       static_cast<uint32_t>(bn)};
+    uint32_t es[4] = {1, static_cast<uint32_t>(s.stride), static_cast<uint32_t>(s.stride), 1};
+    LR_TRY(make_tmap(&p.tmA0, s.a0, 4, dims, str, box, es));
+    if (s.a1 != nullptr) {
+      dims[0] = static_cast<uint64_t>(s.c1);
+      str[0] = static_cast<uint64_t>(s.lda1) * 2;
+      str[1] = str[0] * s.in_w;
+      str[2] = str[1] * s.in_h;
+      LR_TRY(make_tmap(&p.tmA1, s.a1, 4, dims, str, box, es));
+    } else {
+      p.tmA1 = p.tmA0;
+    }
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(s.taps) * (s.c0 + s.c1), static_cast<uint64_t>(s.ncols)};
+    LR_CHECK(dims[0] <= static_cast<uint64_t>(s.ldw), "conv: weight leading dim smaller than K");
+    uint64_t str[1] = {static_cast<uint64_t>(s.ldw) * 2};
+    uint32_t box[2] = {kBlockK, static_cast<uint32_t>(block_n)};
+    uint32_t es[2] = {1, 1};
+    LR_TRY(make_tmap(&p.tmB, s.w, 2, dims, str, box, es));
+  }
+  const int num_tiles = tiles_m * p.tiles_n;
+  op->grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  op->smem = gemm_smem_bytes(block_n, stages);
+  op->flops = 2.0 * s.n_img * Ho * Wo * static_cast<double>(s.ncols) * s.taps * (s.c0 + s.c1);
+  memcpy(op->params, &p, sizeof(p));
+  static bool attr_set = false;
+  if (!attr_set) {
+    LR_CUDA(cudaFuncSetAttribute(gemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  return 0;
+}
+
+int launch_conv_op(const ConvOp& op, cudaStream_t st) {
+  const GemmParams* p = reinterpret_cast<const GemmParams*>(op.params);
+  gemm_conv_kernel<<<op.grid, kGemmThreads, op.smem, st>>>(*p);
+  LR_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// attention op
+// ------------------------------------------------------------------------------------------------------------
+int build_attn_op(AttnOp* op, const AttnSpec& s) {
+  LR_CHECK(s.q && s.k && s.v && s.out, "attention: null pointer");
+  LR_CHECK(s.ldq % 8 == 0 && s.ldk % 8 == 0 && s.ldv % 8 == 0 && s.ld_out % 8 == 0,
+           "attention: leading dims must be multiples of 8");
+  LR_CHECK(s.tq > 0 && s.tk > 0 && s.batch > 0 && s.heads > 0, "attention: empty problem");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  auto mk = [&](CUtensorMap* m, const __half* ptr, int ld, int T) -> int {
+    uint64_t dims[3] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(T), static_cast<uint64_t>(s.batch)};
+    uint64_t str[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * T};
+    uint32_t box[3] = {kAttnD, kAttnTile, 1};
+    uint32_t es[3] = {1, 1, 1};
+    return make_tmap(m, ptr, 3, dims, str, box, es);
+  };
+  LR_TRY(mk(&p.tmQ, s.q, s.ldq, s.tq));
+  LR_TRY(mk(&p.tmK, s.k, s.ldk, s.tk));
+  LR_TRY(mk(&p.tmV, s.v, s.ldv, s.tk));
+  p.heads = s.heads;
+  p.tq = s.tq;
+  p.tk = s.tk;
+  p.batch = s.batch;
+  p.q_col0 = s.q_col0;
+  p.k_col0 = s.k_col0;
+  p.v_col0 = s.v_col0;
+  p.out = s.out;
+  p.ld_out = s.ld_out;
+  p.scale_log2 = s.scale * 1.4426950408889634f;
+  op->grid = dim3(cdiv(s.tq, kAttnTile), s.heads, s.batch);
+  op->flops = 4.0 * s.batch * s.heads * static_cast<double>(s.tq) * s.tk * kAttnD;
+  memcpy(op->params, &p, sizeof(p));
+  static bool attr_set = false;
+  if (!attr_set) {
+    LR_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    attr_set = true;
+  }
+  return 0;
+}
+
+int launch_attn_op(const AttnOp& op, cudaStream_t st) {
+  const AttnParams* p = reinterpret_cast<const AttnParams*>(op.params);
+  attention_kernel<<<op.grid, kAttnThreads, kAttnSmemBytes, st>>>(*p);
+  LR_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// normalisation / elementwise
+// ------------------------------------------------------------------------------------------------------------
+int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_img, int P, int groups, float eps,
+                     const float* gamma, const float* beta, int do_silu, double* stats, float* scale, float* shift,
+                     __half* out, cudaStream_t st) {
+  const int C = c0 + c1;
+  LR_CHECK(c0 % 8 == 0 && c1 % 8 == 0, "groupnorm: channels must be multiples of 8");
+  LR_CHECK(C % groups == 0, "groupnorm: channels not divisible by groups");
+  LR_CHECK(C / 8 <= kNormThreads, "groupnorm: too many channels");
+  LR_CHECK(x1 != nullptr || c1 == 0, "groupnorm: c1 without x1");
+  int chunk = P / 64;
+  if (chunk < 16) chunk = 16;
+  if (chunk > 256) chunk = 256;
+  const dim3 grid(cdiv(P, chunk), n_img);
+  LR_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * n_img * groups * 2, st));
+  gn_stats_kernel<<<grid, kNormThreads, 2 * C * sizeof(float), st>>>(x0, c0, x1, c1, P, chunk, groups, stats);
+  LR_LAUNCHED();
+  gn_finalize_kernel<<<cdiv(n_img * C, 256), 256, 0, st>>>(stats, gamma, beta, C, groups, P, eps, scale, shift, n_img);
+  LR_LAUNCHED();
+  gn_apply_kernel<<<grid, kNormThreads, 0, st>>>(x0, c0, x1, c1, P, chunk, scale, shift, do_silu, out);
+  LR_LAUNCHED();
+  return 0;
+}
+
+int launch_layernorm(const __half* x, int M, int C, const float* gamma, const float* beta, float eps, __half* out,
+                     cudaStream_t st) {
+  LR_CHECK(C % 8 == 0, "layernorm: C must be a multiple of 8");
+  const int nvec = C / 8;
+  const int vpl = cdiv(nvec, 32);
+  const int rows_per_block = 8;
+  const dim3 grid(cdiv(M, rows_per_block));
+  switch (vpl) {
+    case 1: layernorm_kernel<1><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, out); break;
+    case 2: layernorm_kernel<2><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, out); break;
+    case 3: layernorm_kernel<3><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, out); break;
+    case 4: layernorm_kernel<4><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, out); break;
+    case 5: layernorm_kernel<5><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, out); break;
+    case 6: case 7: case 8: layernorm_kernel<8><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, out); break;
+    default: LR_CHECK(false, "layernorm: C > 2048 unsupported");
+  }
+  LR_LAUNCHED();
+  return 0;
+}
+
+int launch_im2col_nchw_f32(const float* x, int n_img, int cin, int H, int W, int kpad, __half* out, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(n_img) * H * W * kpad;
+  im2col_nchw_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, n_img, cin, H, W, kpad, out);
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_upsample2x(const __half* x, int n_img, int H, int W, int C, __half* out, cudaStream_t st) {
+  LR_CHECK(C % 8 == 0, "upsample: C must be a multiple of 8");
+  const size_t total = static_cast<size_t>(n_img) * 4 * H * W * (C / 8);
+  upsample2x_nhwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, n_img, H, W, C, out);
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_cast_f32_f16(const float* x, size_t n, __half* out, cudaStream_t st) {
+  cast_f32_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, n, out);
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_nhwc_to_nchw_f32(const __half* x, int ld, int n_img, int cout, int H, int W, float* out, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(n_img) * cout * H * W;
+  nhwc_f16_to_nchw_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, ld, n_img, cout, H, W,
+                                                                                          out);
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_nchw_f32_to_nhwc(const float* x, int n_img, int C, int H, int W, __half* out, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(n_img) * C * H * W;
+  nchw_f32_to_nhwc_f16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, n_img, C, H, W, out);
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_small_linear(const float* in, int ld_in, int n_rows, int K, const __half* w, const float* bias, int n_out,
+                        int silu_in, int silu_out, float* out, int ld_out, cudaStream_t st) {
+  LR_CHECK(K % 8 == 0, "small_linear: K must be a multiple of 8");
+  small_linear_kernel<<<cdiv(n_out, 8), 256, 0, st>>>(in, ld_in, n_rows, K, w, bias, n_out, silu_in, silu_out, out,
+                                                      ld_out);
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_timestep_embedding(const long long* t, int n, int dim, float* out, cudaStream_t st) {
+  const int total = n * (dim / 2);
+  timestep_embedding_kernel<<<cdiv(total, 256), 256, 0, st>>>(t, n, dim, out);
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_ddim_update(const float* x, const float* e_u, const float* e_c, const float* noise, float cfg, float a_t,
+                       float a_prev, float sigma, float sqrt_one_minus_at, float temperature, size_t n, float* x_prev,
+                       float* pred_x0, cudaStream_t st) {
+  ddim_update_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+      x, e_u, e_c, noise, cfg, a_t, a_prev, sigma, sqrt_one_minus_at, temperature, n, x_prev, pred_x0);
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_repack_conv(const float* w, int O, int I, int ldk, __half* out, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(O) * ldk;
+  repack_conv_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(w, O, I, ldk, out);
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_repack_linear(const float* w, int O, int I, int geglu, int dst_row0, __half* out, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(O) * I;
+  repack_linear_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(w, O, I, geglu, dst_row0, out);
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_repack_bias(const float* b, int O, int geglu, float* out, cudaStream_t st) {
+  repack_bias_kernel<<<cdiv(O, 256), 256, 0, st>>>(b, O, geglu, out);
+  LR_LAUNCHED();
+  return 0;
+}
+
+}  // namespace lr

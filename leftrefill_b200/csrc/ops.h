@@ -1,0 +1,109 @@
+// Host-side op layer: builds TMA tensor maps + launch geometry once ("op" objects), launches them on a stream.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace lr {
+
+// ---- error plumbing (C-ABI returns int status; text via lr_last_error) ----
+void set_error(const std::string& msg);
+const char* last_error();
+#define LR_CUDA(expr)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess) {                                                                           \
+      ::lr::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                             \
+      return 1;                                                                                        \
+    }                                                                                                  \
+  } while (0)
+#define LR_CHECK(cond, msg)                                                                            \
+  do {                                                                                                 \
+    if (!(cond)) {                                                                                     \
+      ::lr::set_error(std::string(msg));                                                               \
+      return 1;                                                                                        \
+    }                                                                                                  \
+  } while (0)
+#define LR_TRY(expr)                                                                                   \
+  do {                                                                                                 \
+    int _r = (expr);                                                                                   \
+    if (_r != 0) return _r;                                                                            \
+  } while (0)
+
+// ---- GEMM / implicit conv ----
+struct ConvSpec {
+  const __half* a0 = nullptr;  // source 0, NHWC [n_img, in_h, in_w, c0] with row stride lda0 (elements)
+  int c0 = 0, lda0 = 0;
+  const __half* a1 = nullptr;  // optional source 1 (skip connection), same spatial dims
+  int c1 = 0, lda1 = 0;
+  int n_img = 1, in_h = 1, in_w = 1;
+  int stride = 1;  // 1 or 2
+  int taps = 1;    // 1 (linear / 1x1 conv) or 9 (3x3, pad 1)
+  const __half* w = nullptr;  // [ncols, ldw] fp16, k = tap*(c0+c1) + c
+  int ldw = 0;
+  int ncols = 0;
+  const float* bias = nullptr;
+  const float* bias_img = nullptr;
+  const __half* residual = nullptr;
+  int ld_res = 0;
+  __half* out = nullptr;
+  int ld_out = 0;
+  int geglu = 0;
+  int force_block_n = 0;  // testing hook: 0 = heuristic
+};
+struct ConvOp {
+  alignas(64) unsigned char params[1024];  // GemmParams (opaque here so headers stay CUDA-kernel free)
+  int grid = 0, smem = 0;
+  int out_h = 0, out_w = 0;
+  double flops = 0;
+};
+int build_conv_op(ConvOp* op, const ConvSpec& s);
+int launch_conv_op(const ConvOp& op, cudaStream_t st);
+
+// ---- attention ----
+struct AttnSpec {
+  const __half* q = nullptr; int ldq = 0, q_col0 = 0;
+  const __half* k = nullptr; int ldk = 0, k_col0 = 0;
+  const __half* v = nullptr; int ldv = 0, v_col0 = 0;
+  __half* out = nullptr; int ld_out = 0;
+  int batch = 1, heads = 1, tq = 0, tk = 0;
+  float scale = 0.125f;
+};
+struct AttnOp {
+  alignas(64) unsigned char params[1024];
+  dim3 grid;
+  double flops = 0;
+};
+int build_attn_op(AttnOp* op, const AttnSpec& s);
+int launch_attn_op(const AttnOp& op, cudaStream_t st);
+
+// ---- normalisation / elementwise launchers ----
+// GroupNorm over concat(x0[c0], x1[c1]) -> out [n, P, c0+c1]; stats/scale/shift are caller-provided scratch:
+// stats: double[n*groups*2], scale/shift: float[n*(c0+c1)]
+int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_img, int P, int groups, float eps,
+                     const float* gamma, const float* beta, int do_silu, double* stats, float* scale, float* shift,
+                     __half* out, cudaStream_t st);
+int launch_layernorm(const __half* x, int M, int C, const float* gamma, const float* beta, float eps, __half* out,
+                     cudaStream_t st);
+int launch_im2col_nchw_f32(const float* x, int n_img, int cin, int H, int W, int kpad, __half* out, cudaStream_t st);
+int launch_upsample2x(const __half* x, int n_img, int H, int W, int C, __half* out, cudaStream_t st);
+int launch_cast_f32_f16(const float* x, size_t n, __half* out, cudaStream_t st);
+int launch_nhwc_to_nchw_f32(const __half* x, int ld, int n_img, int cout, int H, int W, float* out, cudaStream_t st);
+int launch_nchw_f32_to_nhwc(const float* x, int n_img, int C, int H, int W, __half* out, cudaStream_t st);
+int launch_small_linear(const float* in, int ld_in, int n_rows, int K, const __half* w, const float* bias, int n_out,
+                        int silu_in, int silu_out, float* out, int ld_out, cudaStream_t st);
+int launch_timestep_embedding(const long long* t, int n, int dim, float* out, cudaStream_t st);
+int launch_ddim_update(const float* x, const float* e_u, const float* e_c, const float* noise, float cfg, float a_t,
+                       float a_prev, float sigma, float sqrt_one_minus_at, float temperature, size_t n, float* x_prev,
+                       float* pred_x0, cudaStream_t st);
+int launch_repack_conv(const float* w, int O, int I, int ldk, __half* out, cudaStream_t st);
+int launch_repack_linear(const float* w, int O, int I, int geglu, int dst_row0, __half* out, cudaStream_t st);
+int launch_repack_bias(const float* b, int O, int geglu, float* out, cudaStream_t st);
+
+long long launches_since_reset();
+void reset_launch_counter();
+
+}  // namespace lr

@@ -1,0 +1,263 @@
+"""GPU bring-up diagnostics for the op-level C ABI. Each case runs in its own subprocess (a trapped kernel poisons the
+CUDA context) with a timeout. Usage on the GPU box:
+
+    python tests/gpu_diag_ops.py            # run all cases, print a table
+    python tests/gpu_diag_ops.py --case X   # run one case in-process
+"""
+import argparse
+import os
+import subprocess
+import sys
+import time
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+
+def report(name, got, ref, tol=2e-2):
+    import torch
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    scale = ref.abs().max().item() + 1e-9
+    bad = err > tol * scale
+    msg = (f"[{name}] max_abs_err={err.max().item():.4e} ref_max={scale:.4e} rel={err.max().item() / scale:.3e} "
+           f"bad_frac={bad.float().mean().item():.4f} finite={bool(torch.isfinite(got).all())}")
+    if bad.any():
+        idx = bad.nonzero()[:6].tolist()
+        msg += f" first_bad={idx}"
+        # row / column structure of the errors helps to decode descriptor mistakes
+        if got.dim() == 2:
+            rows = bad.any(dim=1).nonzero().flatten()
+            cols = bad.any(dim=0).nonzero().flatten()
+            msg += f" bad_rows={rows[:12].tolist()}(+{max(0, rows.numel() - 12)}) bad_cols={cols[:12].tolist()}(+{max(0, cols.numel() - 12)})"
+    ok = (not bad.any().item()) and bool(torch.isfinite(got).all())
+    print(("PASS " if ok else "FAIL ") + msg, flush=True)
+    return ok
+
+
+def case_linear(M, K, Nn, bias=False, residual=False, geglu=False, force=0, seed=0):
+    import torch
+    from leftrefill_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    a = (torch.randn(M, K, generator=g) * 0.5).cuda().half()
+    n_w = 2 * Nn if geglu else Nn
+    w32 = (torch.randn(n_w, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(n_w, generator=g).cuda() if bias else None
+    r = torch.randn(M, Nn, generator=g).cuda().half() if residual else None
+    wp = ops.repack_linear(w32, geglu=geglu)
+    bp = b
+    if geglu and b is not None:
+        bp = torch.empty_like(b)
+        bp[0::2] = b[:Nn]
+        bp[1::2] = b[Nn:]
+    out = ops.linear(a, wp, bias=bp, residual=r, geglu=geglu, force_block_n=force)
+    torch.cuda.synchronize()
+    ref = a.float() @ w32.half().float().t()
+    if b is not None:
+        ref = ref + b
+    if geglu:
+        ref = ref[:, :Nn] * torch.nn.functional.gelu(ref[:, Nn:])
+    if r is not None:
+        ref = ref + r.float()
+    return report(f"linear M={M} K={K} N={Nn} bias={bias} res={residual} geglu={geglu} bn={force}", out, ref)
+
+
+def case_conv(n, h, w, c0, cout, c1=0, stride=1, bias_img=False, residual=False, force=0, seed=0):
+    import torch
+    import torch.nn.functional as F
+    from leftrefill_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = (torch.randn(n, c0 + c1, h, w, generator=g)).cuda()
+    wt = (torch.randn(cout, c0 + c1, 3, 3, generator=g) / (9 * (c0 + c1)) ** 0.5).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    x0 = ops.to_nhwc_f16(x[:, :c0].contiguous())
+    x1 = ops.to_nhwc_f16(x[:, c0:].contiguous()) if c1 else None
+    bi = torch.randn(n, cout, generator=g).cuda() if bias_img else None
+    ho, wo = (h, w) if stride == 1 else ((h - 1) // 2 + 1, (w - 1) // 2 + 1)
+    r = torch.randn(n, ho, wo, cout, generator=g).cuda().half() if residual else None
+    wp = ops.repack_conv3x3(wt)
+    out = ops.conv3x3(x0, wp, bias=b, x1=x1, stride=stride, bias_img=bi, residual=r, force_block_n=force)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.half().float(), wt.half().float(), b, stride=stride, padding=1)
+    if bi is not None:
+        ref = ref + bi[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1)
+    if r is not None:
+        ref = ref + r.float()
+    return report(f"conv n={n} {h}x{w} c={c0}+{c1}->{cout} s={stride} bimg={bias_img} res={residual} bn={force}",
+                  out.reshape(-1, cout), ref.reshape(-1, cout))
+
+
+def case_attn(b, heads, tq, tk, fused_qkv=False, seed=0):
+    import torch
+    from leftrefill_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    C = heads * 64
+    if fused_qkv:
+        assert tq == tk
+        qkv = torch.randn(b, tq, 3 * C, generator=g).cuda().half()
+        q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    else:
+        q = torch.randn(b, tq, C, generator=g).cuda().half()
+        k = torch.randn(b, tk, C, generator=g).cuda().half()
+        v = torch.randn(b, tk, C, generator=g).cuda().half()
+    out = ops.attention(q, k, v, heads)
+    torch.cuda.synchronize()
+    qf = q.float().reshape(b, tq, heads, 64).permute(0, 2, 1, 3)
+    kf = k.float().reshape(b, tk, heads, 64).permute(0, 2, 1, 3)
+    vf = v.float().reshape(b, tk, heads, 64).permute(0, 2, 1, 3)
+    sim = (qf @ kf.transpose(-1, -2)) * 0.125
+    ref = (sim.softmax(-1) @ vf).permute(0, 2, 1, 3).reshape(b, tq, C)
+    return report(f"attn b={b} h={heads} tq={tq} tk={tk} fused={fused_qkv}", out.reshape(-1, C), ref.reshape(-1, C))
+
+
+def case_gn(n, h, w, c0, c1=0, silu=True, eps=1e-5, seed=0):
+    import torch
+    import torch.nn.functional as F
+    from leftrefill_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    C = c0 + c1
+    x = (torch.randn(n, C, h, w, generator=g) * 2 + 0.5).cuda()
+    gamma = torch.randn(C, generator=g).cuda()
+    beta = torch.randn(C, generator=g).cuda()
+    x0 = ops.to_nhwc_f16(x[:, :c0].contiguous())
+    x1 = ops.to_nhwc_f16(x[:, c0:].contiguous()) if c1 else None
+    out = ops.groupnorm(x0, gamma, beta, eps, silu=silu, x1=x1)
+    torch.cuda.synchronize()
+    ref = F.group_norm(x.half().float(), 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    return report(f"groupnorm n={n} {h}x{w} c={c0}+{c1} silu={silu}", out.reshape(-1, C),
+                  ref.permute(0, 2, 3, 1).reshape(-1, C), tol=5e-3)
+
+
+def case_ln(M, C, seed=0):
+    import torch
+    import torch.nn.functional as F
+    from leftrefill_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = (torch.randn(M, C, generator=g) * 2 + 0.3).cuda().half()
+    gamma = torch.randn(C, generator=g).cuda()
+    beta = torch.randn(C, generator=g).cuda()
+    out = ops.layernorm(x, gamma, beta)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    return report(f"layernorm M={M} C={C}", out, ref, tol=5e-3)
+
+
+def case_time(kind):
+    """Rough kernel timings at UNet sizes (CUDA events, L2-cold not enforced: bring-up only)."""
+    import torch
+    from leftrefill_b200 import ops
+    torch.manual_seed(0)
+
+    def timeit(fn, flops, name, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        print(f"TIME [{name}] {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+    if kind == "linear":
+        for (M, K, Nn) in [(65536, 320, 960), (65536, 320, 320), (65536, 1280, 320), (16384, 640, 1920),
+                           (4096, 1280, 3840), (1024, 1280, 1280), (65536, 128, 320)]:
+            a = torch.randn(M, K, device="cuda").half()
+            w = torch.randn(Nn, K, device="cuda").half()
+            timeit(lambda: ops.linear(a, w), 2.0 * M * K * Nn, f"linear {M}x{K}x{Nn}")
+        M, K, Nn = 65536, 320, 1280
+        a = torch.randn(M, K, device="cuda").half()
+        w = torch.randn(2 * Nn, K, device="cuda").half()
+        timeit(lambda: ops.linear(a, w, geglu=True), 2.0 * M * K * 2 * Nn, f"geglu {M}x{K}x{2 * Nn}")
+    elif kind == "conv":
+        for (n, h, w_, c, co) in [(8, 64, 128, 320, 320), (8, 32, 64, 640, 640), (8, 16, 32, 1280, 1280),
+                                  (8, 8, 16, 1280, 1280), (8, 64, 128, 640, 320), (8, 32, 64, 1280, 640)]:
+            x = torch.randn(n, h, w_, c, device="cuda").half()
+            wt = torch.randn(co, 9 * c, device="cuda").half() * 0.01
+            b = torch.zeros(co, device="cuda")
+            timeit(lambda: ops.conv3x3(x, wt, bias=b), 2.0 * n * h * w_ * 9 * c * co, f"conv {n}x{h}x{w_} {c}->{co}")
+    elif kind == "attn":
+        for (b, hd, t, tk) in [(8, 5, 8192, 8192), (8, 10, 2048, 2048), (8, 20, 512, 512), (8, 5, 8192, 77),
+                               (8, 20, 128, 128)]:
+            q = torch.randn(b, t, hd * 64, device="cuda").half()
+            k = torch.randn(b, tk, hd * 64, device="cuda").half()
+            v = torch.randn(b, tk, hd * 64, device="cuda").half()
+            timeit(lambda: ops.attention(q, k, v, hd), 4.0 * b * hd * t * tk * 64, f"attn b={b} h={hd} {t}x{tk}",
+                   iters=5)
+    return True
+
+
+CASES = {
+    "linear_min": lambda: case_linear(128, 64, 32, force=32),
+    "linear_k256": lambda: case_linear(128, 256, 128, force=128),
+    "linear_bn64": lambda: case_linear(512, 320, 320, force=64),
+    "linear_bn160": lambda: case_linear(512, 320, 320, force=160),
+    "linear_bn256": lambda: case_linear(384, 640, 512, force=256),
+    "linear_ragged": lambda: case_linear(1000, 320, 320, bias=True, residual=True),
+    "linear_geglu": lambda: case_linear(512, 320, 1280, bias=True, geglu=True),
+    "linear_n4": lambda: case_linear(300, 128, 4, bias=True),
+    "linear_big": lambda: case_linear(8192, 1280, 1280, bias=True, residual=True),
+    "conv_small": lambda: case_conv(2, 8, 16, 64, 64),
+    "conv_mid": lambda: case_conv(2, 16, 32, 128, 192, bias_img=True, residual=True),
+    "conv_concat": lambda: case_conv(2, 16, 32, 128, 128, c1=64),
+    "conv_w128": lambda: case_conv(1, 8, 128, 64, 64),
+    "conv_odd": lambda: case_conv(3, 24, 40, 64, 96),
+    "conv_tiny": lambda: case_conv(4, 4, 8, 64, 64),
+    "conv_s2": lambda: case_conv(2, 16, 32, 64, 64, stride=2),
+    "conv_s2_big": lambda: case_conv(2, 64, 128, 64, 64, stride=2),
+    "conv_cout4": lambda: case_conv(2, 16, 32, 64, 4),
+    "attn_min": lambda: case_attn(1, 1, 128, 128),
+    "attn_tiles": lambda: case_attn(2, 2, 512, 512),
+    "attn_fused": lambda: case_attn(2, 5, 256, 256, fused_qkv=True),
+    "attn_cross": lambda: case_attn(2, 2, 256, 77),
+    "attn_ragged": lambda: case_attn(1, 3, 200, 300),
+    "attn_long": lambda: case_attn(1, 1, 1024, 4096),
+    "gn": lambda: case_gn(2, 16, 32, 320),
+    "gn_concat": lambda: case_gn(2, 8, 16, 1280, c1=640),
+    "gn_nosilu": lambda: case_gn(3, 8, 8, 64, silu=False, eps=1e-6),
+    "ln": lambda: case_ln(1000, 320),
+    "ln_1280": lambda: case_ln(256, 1280),
+    "time_linear": lambda: case_time("linear"),
+    "time_conv": lambda: case_time("conv"),
+    "time_attn": lambda: case_time("attn"),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", default=None)
+    ap.add_argument("--only", default=None, help="comma separated prefixes")
+    args = ap.parse_args()
+    if args.case:
+        ok = CASES[args.case]()
+        sys.exit(0 if ok else 1)
+    results = {}
+    for name in CASES:
+        if args.only and not any(name.startswith(p) for p in args.only.split(",")):
+            continue
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", name], timeout=180,
+                               capture_output=True, text=True)
+            out = (r.stdout + r.stderr).strip().splitlines()
+            tail = [l for l in out if l.startswith(("PASS", "FAIL", "TIME", "lr_b200"))] or out[-6:]
+            print(f"== {name} rc={r.returncode} ({time.time() - t0:.1f}s)")
+            for l in tail[-12:]:
+                print("   " + l)
+            results[name] = r.returncode
+        except subprocess.TimeoutExpired:
+            print(f"== {name} TIMEOUT")
+            results[name] = -9
+        sys.stdout.flush()
+    bad = [k for k, v in results.items() if v != 0]
+    print(f"SUMMARY: {len(results) - len(bad)}/{len(results)} ok; failing: {bad}")
+
+
+if __name__ == "__main__":
+    main()
