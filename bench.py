@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — LeftRefill DDIM/UNet hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path over one batch of synthetic input = DDIMSampler.sample of `--batch` stitched
+512x1024 canvases (64x128 latents, 9-channel UNet input, cfg 2.5 -> UNet batch 2*batch) for `--ddim-steps` (50) DDIM
+steps: BASELINE.json configs[1] ("batch=4 ref-inpainting, 50 DDIM steps, cfg=2.5, fp16, 1xB200").
+Metric: stitched 512x1024 images/sec @ 50 DDIM steps (whole job, all ranks).
+
+  value  : inputs resident in HBM when the timed region starts (device-timed with CUDA events, max over ranks)
+  e2e    : the same through the public API with HOST (pinned) buffers: H2D of x_T / c_concat / contexts and D2H of the
+           samples inside the timed region, every step
+  roofline     : gemm_conv_kernel (all convs + linears, the dominant kernel by FLOPs), tensor bound: algorithmic FLOPs of
+                 its launches / their summed CUDA-event durations in profiled UNet forwards run inside this process
+  cpu_baseline : the oracle (a port: /root/reference does not exist on the GPU box) timed on the host cores on a bounded
+                 sample (one CFG step of one canvas), extrapolated to the metric's unit
+
+`--impl reference` times the reference's CPU implementation of the path (the oracle port) with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "stitched 512x1024 images/sec @ 50 DDIM steps"
+UNIT = "images/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = str(gpu_index)
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.idx, f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:  # noqa: BLE001
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(threads=None, canvases=1, repeats=1, warmup=1):
+    """Oracle (CPU fp32 restatement of the reference UNet + DDIM step) on the host cores, bounded sample:
+    one CFG step (UNet batch 2) of `canvases` canvas at 64x128 latent, extrapolated: images/s = canvases/(50*t)."""
+    import torch
+    from helpers import O, synthetic_inputs
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = O.DEFAULT_CFG
+    sd = O.make_state_dict(cfg, seed=0)
+    xT, c_cat, ctx, uc = synthetic_inputs(canvases)
+    xc = torch.cat([torch.cat([xT, xT]), torch.cat([c_cat, c_cat])], dim=1)
+    cc = torch.cat([uc, ctx])
+    t = torch.full((2 * canvases,), 981, dtype=torch.long)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + repeats):
+            t0 = time.perf_counter()
+            e = O.unet_forward(sd, cfg, xc, t, cc)
+            e_u, e_c = e.chunk(2)
+            O.ddim_step(xT, e_u, e_c, torch.zeros_like(xT), 2.5, 0.5, 0.6, 0.0)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path (oracle port), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    ddim_steps = args.ddim_steps
+    times, cores = cpu_baseline(threads=os.cpu_count(), canvases=1, repeats=args.steps, warmup=max(1, min(args.warmup, 1)))
+    t = sum(times) / len(times)
+    value = 1.0 / (ddim_steps * t)
+    sample = (f"each step = 1 CFG DDIM step (UNet batch 2, 64x128 latent, fp32) of 1 canvas on {cores} threads; "
+              f"images/s = 1 / ({ddim_steps} x step time)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 * ddim_steps * args.batch,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"batch={args.batch} ref-inpainting canvases, {ddim_steps} DDIM steps, cfg=2.5, "
+                                   "stitched 512x1024 (64x128 latent), SD2-inpainting UNet 865.9M params, random init",
+                       "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from helpers import FakeLDM, O, synthetic_inputs
+    import leftrefill_b200 as lr
+    from leftrefill_b200 import _native as N
+    from leftrefill_b200 import parallel as P
+
+    rank, world = P.init_distributed()
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the native arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B, S = args.batch, args.ddim_steps
+    cfg = O.DEFAULT_CFG
+    H, W = 64, 128
+
+    # ---- model: reference architecture, random init (no checkpoint offline), replicated per rank ----
+    sd = O.make_state_dict(cfg, seed=0)
+    unet = lr.UNetModel(**cfg)
+    unet.load_state_dict(sd, strict=True)
+    del sd
+    unet = unet.to(dev).eval()
+    ldm = FakeLDM(unet, dev)
+
+    # ---- synthetic inputs, rank-specific seed: weak scaling, B canvases per GPU ----
+    xT_h, ccat_h, ctx_h, uc_h = [t.pin_memory() for t in synthetic_inputs(B, h=H, w=W, seed=1234 + rank)]
+    xT, ccat, ctx, uc = [t.to(dev) for t in (xT_h, ccat_h, ctx_h, uc_h)]
+    out_h = torch.empty(B, 4, H, W).pin_memory()
+
+    def one_batch(x_T, c_cat, c_ctx, c_uc):
+        sampler = lr.DDIMSampler(ldm)
+        cond = {"c_concat": [c_cat], "c_crossattn": [c_ctx]}
+        ucond = {"c_concat": [c_cat], "c_crossattn": [c_uc]}
+        samples, _ = sampler.sample(S, B, (4, H, W), cond, eta=1.0, x_T=x_T, verbose=False,
+                                    unconditional_guidance_scale=2.5, unconditional_conditioning=ucond)
+        return samples
+
+    def step_resident():
+        s = one_batch(xT, ccat, ctx, uc)
+        return P.gather_outputs(s, B * world, rank, world)      # the one collective of a batch
+
+    def step_e2e():
+        a, b, c, d = [t.to(dev, non_blocking=True) for t in (xT_h, ccat_h, ctx_h, uc_h)]
+        s = one_batch(a, b, c, d)
+        s = P.gather_outputs(s, B * world, rank, world)
+        out_h.copy_(s[rank * B:(rank + 1) * B], non_blocking=True)
+        torch.cuda.current_stream().synchronize()               # the caller holds the result on the host
+        return s
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return P.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    N.lib().lr_launch_count_reset()
+    t_res = timed(step_resident, args.steps)
+    launches = N.lib().lr_launch_count()
+    clk = clocks.stop() if rank == 0 else None
+    step_e2e()
+    t_e2e = timed(step_e2e, args.steps)
+
+    # ---- per-kernel-class profile of the UNet forward (CUDA events between plan steps, same process) ----
+    import ctypes
+    h = unet.engine()
+    xc = torch.cat([torch.cat([xT, xT]), torch.cat([ccat, ccat])], dim=1).contiguous()
+    tt = torch.full((2 * B,), 981, dtype=torch.long, device=dev)
+    unet.set_context(torch.cat([uc, ctx]).contiguous())
+    N.lib().lr_unet_set_profiling(h, 1)
+    ms_c = (ctypes.c_double * 5)()
+    fl_c = (ctypes.c_double * 5)()
+    n_c = (ctypes.c_int * 5)()
+    acc_ms, acc_fl, acc_n = [0.0] * 5, [0.0] * 5, [0] * 5
+    prof_iters = 5
+    for i in range(prof_iters + 1):
+        unet.forward_native(xc, tt, None)
+        N.check(N.lib().lr_unet_read_profile(h, ms_c, fl_c, n_c), "read_profile")
+        if i == 0:
+            continue  # warm-up of the event pool
+        for c in range(5):
+            acc_ms[c] += ms_c[c]
+            acc_fl[c] += fl_c[c]
+            acc_n[c] += n_c[c]
+    N.lib().lr_unet_set_profiling(h, 0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        unet.forward_native(xc, tt, None)
+    e1.record()
+    torch.cuda.synchronize()
+    unet_ms = e0.elapsed_time(e1) / 10
+    unet_flops = unet.last_flops()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+    sustained, burst, hbm, peak_src = _peaks()
+    names = ["gemm_conv_kernel", "attention_kernel", "groupnorm", "layernorm", "other"]
+    classes = {names[c]: {"ms_per_forward": acc_ms[c] / prof_iters, "tflops": (acc_fl[c] / acc_ms[c] / 1e9) if acc_ms[c] > 0 and acc_fl[c] > 0 else None,
+                          "steps_per_forward": acc_n[c] // prof_iters} for c in range(5)}
+    gemm_launches = acc_n[0]
+    achieved = acc_fl[0] / acc_ms[0] / 1e9
+    roofline = {"kernel": "gemm_conv_kernel (tcgen05 implicit-GEMM conv3x3 + linear, all launches of a UNet forward)",
+                "bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                "frac": achieved / sustained, "traffic": None,
+                "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
+                "flops_per_launch": acc_fl[0] / gemm_launches, "ms_per_launch": acc_ms[0] / gemm_launches,
+                "launches_timed": gemm_launches,
+                "attention_kernel": {"achieved": classes["attention_kernel"]["tflops"], "peak": sustained,
+                                     "frac": (classes["attention_kernel"]["tflops"] or 0) / sustained},
+                "by_class": classes}
+
+    cb_times, cores = cpu_baseline(threads=os.cpu_count(), canvases=1, repeats=1, warmup=1)
+    cb_t = sum(cb_times) / len(cb_times)
+    cb = {"value": 1.0 / (S * cb_t), "unit": UNIT, "cores": cores, "kind": "port",
+          "sample": f"1 CFG DDIM step (UNet batch 2, 64x128 latent, fp32 oracle) of 1 canvas = {cb_t:.2f} s on {cores} "
+                    f"threads; images/s = 1/({S} x step)"}
+
+    images = B * world * args.steps
+    h2d = sum(t.numel() * t.element_size() for t in (xT_h, ccat_h, ctx_h, uc_h))
+    line = {"metric": METRIC, "value": images / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"batch={B} ref-inpainting canvases per GPU, {S} DDIM steps, cfg=2.5, eta=1.0, stitched "
+                                   "512x1024 (64x128 latent, 9-ch input, UNet batch 2*batch), SD2-inpainting UNet 865.9M "
+                                   "params random init (BASELINE.json configs[1])",
+                       "l2": "inputs larger than L2: 1.73 GB fp16 weights + >2 GB activations per UNet forward vs 126 MB",
+                       "parallelism": f"dp{world}: canvases sharded, weights replicated, 1 all-gather per batch",
+                       "precision": "fp16 operands, fp32 accumulate / norm statistics / softmax / DDIM state"},
+            "unet_ms_per_ddim_step": unet_ms, "unet_tflops": unet_flops / unet_ms / 1e9,
+            "unet_tflop_per_forward": unet_flops / 1e12,
+            "e2e": {"value": images / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": out_h.numel() * 4},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cb}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=4, help="stitched canvases per GPU (UNet batch is 2x with CFG)")
+    ap.add_argument("--ddim-steps", type=int, default=50)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,11 @@ int lr_unet_set_context(lr_unet* h, const float* context, int n, int L, void* st
  * out [n, out_channels, H, W] fp32 NCHW. */
 int lr_unet_forward(lr_unet* h, const float* x, const int64_t* timesteps, const float* context, int L, float* out,
                     int n, int H, int W, void* stream);
+/* Per-op CUDA-event timing of forward (bench.py's roofline): when enabled, every forward records an event between
+ * plan steps on `stream`. lr_unet_read_profile waits for the last profiled forward and sums by kernel class:
+ * 0 = gemm_conv_kernel (all convs + linears), 1 = attention_kernel, 2 = GroupNorm kernels, 3 = LayerNorm, 4 = other. */
+int lr_unet_set_profiling(lr_unet* h, int enable);
+int lr_unet_read_profile(lr_unet* h, double ms_by_class[5], double flops_by_class[5], int steps_by_class[5]);
 /* Algorithmic FLOPs (2*M*N*K convs/linears + 4*Tq*Tk*d attention) of the last planned forward. */
 double lr_unet_last_flops(const lr_unet* h);
 /* Bytes of device memory held by the engine (weights + activation plan). */

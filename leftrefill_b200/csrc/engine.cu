@@ -120,7 +120,17 @@ struct lr_unet {
   // ---- plan state ----
   int pn = 0, ph = 0, pw = 0;  // planned shape
   Pool pool;
-  std::vector<std::function<int(cudaStream_t)>> steps;
+  struct Step {
+    std::function<int(cudaStream_t)> fn;
+    int cls;       // 0 gemm/conv (gemm_conv_kernel), 1 attention, 2 groupnorm, 3 layernorm, 4 other
+    double flops;  // algorithmic FLOPs of this step
+  };
+  std::vector<Step> steps;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;  // steps.size() + 1 events of the last profiled forward
+  void push(std::function<int(cudaStream_t)> fn, int cls = 4, double fl = 0.0) {
+    steps.push_back(Step{std::move(fn), cls, fl});
+  }
   std::vector<std::unique_ptr<ConvOp>> conv_ops;
   std::vector<std::unique_ptr<AttnOp>> attn_ops;
   double flops = 0;
@@ -137,6 +147,7 @@ struct lr_unet {
   size_t persistent_bytes = 0;
 
   ~lr_unet() {
+    for (auto e : prof_events) cudaEventDestroy(e);
     pool.clear();
     if (harena) cudaFree(harena);
     if (farena) cudaFree(farena);
@@ -375,7 +386,7 @@ struct lr_unet {
     flops += op->flops;
     ConvOp* raw = op.get();
     conv_ops.push_back(std::move(op));
-    steps.push_back([raw](cudaStream_t st) { return launch_conv_op(*raw, st); });
+    push([raw](cudaStream_t st) { return launch_conv_op(*raw, st); }, 0, raw->flops);
     return 0;
   }
   int add_linear(const __half* a, int M, int K, const __half* w, int ncols, const float* bias, const __half* residual,
@@ -407,13 +418,13 @@ struct lr_unet {
              const float* b, int silu, __half* out) {
     double* st_ = gn_stats;
     float *sc = gn_scale, *sh = gn_shift;
-    steps.push_back([=](cudaStream_t st) {
+    push([=](cudaStream_t st) {
       return launch_groupnorm(x0, c0, x1, c1, n, P, 32, eps, g, b, silu, st_, sc, sh, out, st);
-    });
+    }, 2);
     return 0;
   }
   int add_ln(const __half* x, int M, int C, const float* g, const float* b, __half* out) {
-    steps.push_back([=](cudaStream_t st) { return launch_layernorm(x, M, C, g, b, 1e-5f, out, st); });
+    push([=](cudaStream_t st) { return launch_layernorm(x, M, C, g, b, 1e-5f, out, st); }, 3);
     return 0;
   }
   int add_attn(const AttnSpec& s) {
@@ -422,7 +433,7 @@ struct lr_unet {
     flops += op->flops;
     AttnOp* raw = op.get();
     attn_ops.push_back(std::move(op));
-    steps.push_back([raw](cudaStream_t st) { return launch_attn_op(*raw, st); });
+    push([raw](cudaStream_t st) { return launch_attn_op(*raw, st); }, 1, raw->flops);
     return 0;
   }
 
@@ -629,7 +640,7 @@ struct lr_unet {
         LR_TRY(acquire_h(static_cast<size_t>(n) * 4 * cur.H * cur.W * cur.C, &up));
         const __half* src = cur.p;
         const int hh = cur.H, ww = cur.W, cc = cur.C;
-        steps.push_back([=](cudaStream_t st) { return launch_upsample2x(src, n, hh, ww, cc, up, st); });
+        push([=](cudaStream_t st) { return launch_upsample2x(src, n, hh, ww, cc, up, st); });
         Act u{up, cur.C, 2 * cur.H, 2 * cur.W};
         LR_TRY(plan_conv3(convs[nd.idx], u, n, 1, &nxt));
         pool.release(up);
@@ -716,7 +727,7 @@ struct lr_unet {
     LR_TRY(acquire_f(static_cast<size_t>(n) * mc, &tsin));
     LR_TRY(acquire_f(static_cast<size_t>(n) * temb, &e1));
     LR_TRY(acquire_f(static_cast<size_t>(n) * temb, &emb));
-    steps.push_back([=](cudaStream_t st) {
+    push([=](cudaStream_t st) {
       return launch_timestep_embedding(reinterpret_cast<const long long*>(this->in_t), n, mc, tsin, st);
     });
     {
@@ -724,9 +735,9 @@ struct lr_unet {
       const float* b0 = F(te0_b);
       const __half* w2 = H(te2_w);
       const float* b2 = F(te2_b);
-      steps.push_back(
+      push(
           [=](cudaStream_t st) { return launch_small_linear(tsin, mc, n, mc, w0, b0, temb, 0, 1, e1, temb, st); });
-      steps.push_back(
+      push(
           [=](cudaStream_t st) { return launch_small_linear(e1, temb, n, temb, w2, b2, temb, 0, 0, emb, temb, st); });
     }
     for (const ResW& r : res) {
@@ -736,7 +747,7 @@ struct lr_unet {
       const __half* w = H(r.emb_w);
       const float* b = F(r.emb_b);
       const int co = r.cout;
-      steps.push_back(
+      push(
           [=](cudaStream_t st) { return launch_small_linear(emb, temb, n, temb, w, b, co, 1, 0, eo, co, st); });
     }
     // --- input conv: im2col of the NCHW fp32 boundary tensor, then a GEMM ---
@@ -745,7 +756,7 @@ struct lr_unet {
     LR_TRY(acquire_h(M0 * kpad_in, &col));
     {
       const int cin = cfg.in_channels, kp = kpad_in;
-      steps.push_back(
+      push(
           [=](cudaStream_t st) { return launch_im2col_nchw_f32(this->in_x, n, cin, Hh, Ww, kp, col, st); });
     }
     Act h;
@@ -801,7 +812,7 @@ struct lr_unet {
       s.ld_out = c.cout;
       LR_TRY(add_conv_step(s));
       const int co = c.cout;
-      steps.push_back(
+      push(
           [=](cudaStream_t st) { return launch_nhwc_to_nchw_f32(y, co, n, co, Hh, Ww, this->out_y, st); });
     }
     pn = n;
@@ -913,7 +924,47 @@ int lr_unet_forward(lr_unet* h, const float* x, const int64_t* timesteps, const 
   h->in_x = x;
   h->in_t = timesteps;
   h->out_y = out;
-  for (auto& s : h->steps) LR_TRY(s(st));
+  if (!h->profiling) {
+    for (auto& s : h->steps) LR_TRY(s.fn(st));
+    return 0;
+  }
+  while (h->prof_events.size() < h->steps.size() + 1) {
+    cudaEvent_t e;
+    LR_CUDA(cudaEventCreate(&e));
+    h->prof_events.push_back(e);
+  }
+  LR_CUDA(cudaEventRecord(h->prof_events[0], st));
+  for (size_t i = 0; i < h->steps.size(); ++i) {
+    LR_TRY(h->steps[i].fn(st));
+    LR_CUDA(cudaEventRecord(h->prof_events[i + 1], st));
+  }
+  return 0;
+}
+
+int lr_unet_set_profiling(lr_unet* h, int enable) {
+  LR_CHECK(h != nullptr, "lr_unet_set_profiling: null handle");
+  h->profiling = enable != 0;
+  return 0;
+}
+
+int lr_unet_read_profile(lr_unet* h, double ms_by_class[5], double flops_by_class[5], int steps_by_class[5]) {
+  LR_CHECK(h != nullptr, "lr_unet_read_profile: null handle");
+  LR_CHECK(h->prof_events.size() >= h->steps.size() + 1 && !h->steps.empty(),
+           "lr_unet_read_profile: no profiled forward has run");
+  LR_CUDA(cudaEventSynchronize(h->prof_events[h->steps.size()]));
+  for (int c = 0; c < 5; ++c) {
+    ms_by_class[c] = 0.0;
+    flops_by_class[c] = 0.0;
+    steps_by_class[c] = 0;
+  }
+  for (size_t i = 0; i < h->steps.size(); ++i) {
+    float ms = 0.f;
+    LR_CUDA(cudaEventElapsedTime(&ms, h->prof_events[i], h->prof_events[i + 1]));
+    const int c = h->steps[i].cls;
+    ms_by_class[c] += ms;
+    flops_by_class[c] += h->steps[i].flops;
+    steps_by_class[c] += 1;
+  }
   return 0;
 }
 

@@ -13,23 +13,26 @@ import time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
 
-def report(name, got, ref, tol=2e-2):
+def report(name, got, ref, tol=None, rtol=1e-3, atol_scale=2e-4):
+    """Element-wise criterion |got - ref| <= atol + rtol*|ref| with rtol = 1e-3 (BASELINE north_star) and
+    atol = 2e-4 * max(1, max|ref|): one fp16 rounding of the output (2^-11 relative) plus fp32 accumulation noise."""
     import torch
     got = got.float()
     ref = ref.float()
     err = (got - ref).abs()
     scale = ref.abs().max().item() + 1e-9
-    bad = err > tol * scale
-    msg = (f"[{name}] max_abs_err={err.max().item():.4e} ref_max={scale:.4e} rel={err.max().item() / scale:.3e} "
-           f"bad_frac={bad.float().mean().item():.4f} finite={bool(torch.isfinite(got).all())}")
+    bound = atol_scale * max(1.0, scale) + rtol * ref.abs()
+    bad = err > bound
+    msg = (f"[{name}] max_abs_err={err.max().item():.4e} ref_max={scale:.4e} worst_ratio={(err / bound).max().item():.3f} "
+           f"bad_frac={bad.float().mean().item():.5f} finite={bool(torch.isfinite(got).all())}")
     if bad.any():
         idx = bad.nonzero()[:6].tolist()
         msg += f" first_bad={idx}"
-        # row / column structure of the errors helps to decode descriptor mistakes
         if got.dim() == 2:
             rows = bad.any(dim=1).nonzero().flatten()
             cols = bad.any(dim=0).nonzero().flatten()
-            msg += f" bad_rows={rows[:12].tolist()}(+{max(0, rows.numel() - 12)}) bad_cols={cols[:12].tolist()}(+{max(0, cols.numel() - 12)})"
+            msg += (f" bad_rows={rows[:12].tolist()}(+{max(0, rows.numel() - 12)})"
+                    f" bad_cols={cols[:12].tolist()}(+{max(0, cols.numel() - 12)})")
     ok = (not bad.any().item()) and bool(torch.isfinite(got).all())
     print(("PASS " if ok else "FAIL ") + msg, flush=True)
     return ok
@@ -129,7 +132,7 @@ def case_gn(n, h, w, c0, c1=0, silu=True, eps=1e-5, seed=0):
     if silu:
         ref = F.silu(ref)
     return report(f"groupnorm n={n} {h}x{w} c={c0}+{c1} silu={silu}", out.reshape(-1, C),
-                  ref.permute(0, 2, 3, 1).reshape(-1, C), tol=5e-3)
+                  ref.permute(0, 2, 3, 1).reshape(-1, C))
 
 
 def case_ln(M, C, seed=0):
@@ -143,7 +146,7 @@ def case_ln(M, C, seed=0):
     out = ops.layernorm(x, gamma, beta)
     torch.cuda.synchronize()
     ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
-    return report(f"layernorm M={M} C={C}", out, ref, tol=5e-3)
+    return report(f"layernorm M={M} C={C}", out, ref)
 
 
 def case_time(kind):

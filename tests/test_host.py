@@ -1,0 +1,108 @@
+"""CPU: host-side logic and the C-ABI contract (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, ROOT, FakeLDM, load_golden
+
+import leftrefill_b200
+from leftrefill_b200 import _native as N
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "lr_b200.h")).read()
+    declared = set(re.findall(r"\b(lr_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(N.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in lr_b200.h but not exported"
+    assert declared == set(N.SIGNATURES), "ctypes signature table and header disagree"
+    assert N.lib().lr_abi_version() == 1
+
+
+def _engine_table(model):
+    L, h = N.lib(), model.engine()
+    out = {}
+    for i in range(L.lr_unet_num_weights(h)):
+        shp = (ctypes.c_int64 * 4)()
+        nd = L.lr_unet_weight_shape(h, i, shp)
+        out[L.lr_unet_weight_name(h, i).decode()] = tuple(shp[:nd])
+    return out
+
+
+@pytest.mark.parametrize("cfg", [O.SMALL_CFG, dict(O.SMALL_CFG, use_linear_in_transformer=False, transformer_depth=2,
+                                                   num_res_blocks=[1, 2, 1, 1])])
+def test_state_dict_and_engine_weight_table_match_the_reference_layout(cfg):
+    m = leftrefill_b200.UNetModel(**cfg)
+    spec = O.unet_spec(cfg)
+    sd = m.state_dict()
+    assert list(sd.keys()) == [n for n, _ in spec]              # same keys, same order as the reference module
+    assert all(tuple(sd[n].shape) == tuple(s) for n, s in spec)
+    table = _engine_table(m)
+    assert table == {n: tuple(s) for n, s in spec}              # native weight table == reference state dict
+    assert N.lib().lr_unet_missing_weights(m.engine()) == len(spec)
+
+
+def test_unsupported_options_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        leftrefill_b200.UNetModel(**dict(O.SMALL_CFG, num_head_channels=32))
+    with pytest.raises(NotImplementedError):
+        leftrefill_b200.UNetModel(**dict(O.SMALL_CFG, use_scale_shift_norm=True))
+    with pytest.raises(NotImplementedError):
+        leftrefill_b200.UNetModel(**dict(O.SMALL_CFG, use_spatial_transformer=False, context_dim=None))
+
+
+def test_no_cpu_fallback():
+    m = leftrefill_b200.UNetModel(**O.SMALL_CFG)
+    with pytest.raises(N.LRError):
+        m(torch.zeros(1, 9, 16, 32), torch.zeros(1, dtype=torch.long), context=torch.zeros(1, 77, 256))
+
+
+def test_error_reporting_through_the_abi():
+    L = N.lib()
+    h = ctypes.c_void_p()
+    cfg = N.UNetCfg()
+    cfg.model_channels, cfg.num_levels, cfg.num_head_channels, cfg.transformer_depth = 60, 1, 64, 1
+    assert L.lr_unet_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
+    assert b"model_channels" in L.lr_last_error()
+    with pytest.raises(N.LRError):
+        N.check(L.lr_unet_create(None, ctypes.byref(h)), "create")
+
+
+def test_install_routes_reference_module_paths():
+    leftrefill_b200.install()
+    import importlib
+    om = importlib.import_module("ldm.modules.diffusionmodules.openaimodel")
+    at = importlib.import_module("ldm.modules.attention")
+    dd = importlib.import_module("ldm.models.diffusion.ddim")
+    assert om.UNetModel is leftrefill_b200.UNetModel
+    assert at.CrossAttention is leftrefill_b200.CrossAttention
+    assert dd.DDIMSampler is leftrefill_b200.DDIMSampler
+    # the plugin mechanism of the reference: instantiate_from_config resolves `target` with importlib (ldm/util.py:71-86)
+    target = "ldm.modules.diffusionmodules.openaimodel.UNetModel"
+    module, cls = target.rsplit(".", 1)
+    assert getattr(importlib.import_module(module), cls) is leftrefill_b200.UNetModel
+
+
+def test_ddim_schedule_matches_reference_golden():
+    g = load_golden("ddim_small.npz")
+    s = leftrefill_b200.DDIMSampler(FakeLDM(None, torch.device("cpu")))
+    s.make_schedule(50, ddim_eta=1.0, verbose=False)
+    assert (s.ddim_timesteps == g["sched50.timesteps"]).all()
+    assert np.abs(s.ddim_alphas - g["sched50.alphas"]).max() < 1e-6
+    assert np.abs(s.ddim_alphas_prev - g["sched50.alphas_prev"]).max() < 1e-6
+    assert np.abs(s.ddim_sigmas - g["sched50.sigmas"]).max() < 1e-6
+    assert np.abs(s.ddim_sqrt_one_minus_alphas - g["sched50.sqrt_one_minus_alphas"]).max() < 1e-6
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "leftrefill_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"

@@ -1,0 +1,71 @@
+"""GPU parity tests of the op-level C ABI (lr_linear_f16, lr_conv3x3_f16, lr_attention_f16, lr_groupnorm_f16,
+lr_layernorm_f16, lr_ddim_update) against fp32 references on identical fp16-rounded inputs.
+Tolerance: |err| <= 2e-4*max(1, max|ref|) + 1e-3*|ref| element-wise (see gpu_diag_ops.report)."""
+import pytest
+import torch
+
+import helpers
+from helpers import O
+import gpu_diag_ops as D
+
+pytestmark = pytest.mark.gpu
+
+PARITY_CASES = [k for k in D.CASES if not k.startswith("time_")]
+
+
+@pytest.mark.parametrize("name", PARITY_CASES)
+def test_op_parity(name):
+    assert D.CASES[name]()
+
+
+def test_empty_inputs_are_noops():
+    from leftrefill_b200 import ops
+    a = torch.zeros(0, 64, dtype=torch.float16, device="cuda")
+    w = torch.zeros(32, 64, dtype=torch.float16, device="cuda")
+    assert ops.linear(a, w).shape == (0, 32)
+    x = torch.zeros(0, 8, 8, 64, dtype=torch.float16, device="cuda")
+    assert ops.conv3x3(x, torch.zeros(64, 576, dtype=torch.float16, device="cuda")).shape == (0, 8, 8, 64)
+
+
+def test_bad_arguments_raise():
+    from leftrefill_b200 import ops, _native as N
+    a = torch.zeros(8, 60, dtype=torch.float16, device="cuda")  # K not a multiple of 8
+    w = torch.zeros(32, 60, dtype=torch.float16, device="cuda")
+    with pytest.raises(N.LRError):
+        ops.linear(a, w)
+
+
+@pytest.mark.parametrize("cfg_scale,sigma", [(2.5, 0.0), (2.5, 0.37), (1.0, 0.2)])
+def test_ddim_update_matches_oracle(cfg_scale, sigma):
+    from leftrefill_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x, eu, ec, nz = (torch.randn(3, 4, 16, 32, generator=g) for _ in range(4))
+    a_t, a_prev = 0.4321, 0.5678
+    ref_prev, ref_x0 = O.ddim_step(x, eu, ec if cfg_scale != 1.0 else None, nz, cfg_scale, a_t, a_prev, sigma)
+    got_prev, got_x0 = ops.ddim_update(x.cuda(), eu.cuda(), ec.cuda() if cfg_scale != 1.0 else None, nz.cuda(),
+                                       cfg_scale, a_t, a_prev, sigma, (1 - a_t) ** 0.5)
+    assert torch.allclose(got_prev.cpu(), ref_prev, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(got_x0.cpu(), ref_x0, rtol=1e-5, atol=1e-5)
+
+
+def test_cross_attention_module_matches_oracle():
+    """CrossAttention.forward stand-alone (attention.py:165-196) vs the oracle's _attention on the same weights."""
+    from leftrefill_b200 import CrossAttention
+    torch.manual_seed(0)
+    m = CrossAttention(query_dim=320, context_dim=1024, heads=5, dim_head=64).cuda()
+    x = torch.randn(2, 200, 320, device="cuda")
+    ctx = torch.randn(2, 77, 1024, device="cuda")
+    sd = {"a." + k: v.detach().half().float().cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref_cross = O._attention(sd, "a.", x.half().float().cpu(), ctx.half().float().cpu(), 5)
+        got_cross = m(x, context=ctx)
+    s = helpers.err_stats(got_cross, ref_cross)
+    assert s["finite"] and s["rel_rms"] < 2e-3 and s["max_abs"] < 5e-3 * max(1.0, s["ref_max"]), s
+    ms = CrossAttention(query_dim=320, heads=5, dim_head=64).cuda()
+    sd = {"a." + k: v.detach().half().float().cpu() for k, v in ms.state_dict().items()}
+    with torch.no_grad():
+        xr = x.half().float().cpu()
+        ref_self = O._attention(sd, "a.", xr, xr, 5)
+        got_self = ms(x)
+    s = helpers.err_stats(got_self, ref_self)
+    assert s["finite"] and s["rel_rms"] < 2e-3, s

@@ -1,0 +1,208 @@
+"""GPU parity tests of the UNet engine and the drop-in DDIMSampler, through the C ABI (lr_unet_*).
+
+Bars (tolerance stated here, as BASELINE.json asks):
+  * vs the REFERENCE's fp32 outputs (golden fixtures produced by the unmodified reference modules): relative RMS
+    error <= 4e-3 and max |err| <= 1.5e-2 * max|ref|. An fp16 tensor-core pipeline through ~60 layers cannot meet
+    rtol 1e-3 / atol 1e-4 end to end — the reference's own torch.autocast path sits at rel-RMS ~2.3e-3 from its fp32
+    self — so the second bar is relative to that floor:
+  * native error <= 1.25 x the error of the oracle run under torch.autocast (the reference's precision recipe on a
+    GPU), measured in the same test on the same inputs.
+"""
+import pytest
+import torch
+
+import helpers
+from helpers import FakeLDM, O, err_stats, load_golden, synthetic_inputs
+
+pytestmark = pytest.mark.gpu
+
+REL_RMS_BAR = 4e-3
+MAX_ABS_BAR = 1.5e-2
+FLOOR_FACTOR = 1.25
+
+
+def _build(cfg, seed, multiview=None):
+    import leftrefill_b200 as lr
+    sd = O.make_state_dict(cfg, seed=seed)
+    if multiview is None:
+        m = lr.UNetModel(**cfg)
+    else:
+        m = lr.MultiViewUnetModel(**cfg, view_num=multiview[0], concat_target=multiview[1])
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval(), sd
+
+
+def _floor(sd, cfg, x, t, ctx, **kw):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad(), torch.autocast("cuda"):
+        return O.unet_forward(sdc, cfg, x.cuda(), t.cuda(), ctx.cuda(), **kw).float()
+
+
+def _assert_parity(got, ref, floor=None):
+    s = err_stats(got, ref)
+    assert s["finite"], s
+    assert s["rel_rms"] <= REL_RMS_BAR, s
+    assert s["max_abs"] <= MAX_ABS_BAR * s["ref_max"], s
+    if floor is not None:
+        f = err_stats(floor, ref)
+        assert s["rms"] <= FLOOR_FACTOR * f["rms"], (s, f)
+    return s
+
+
+@pytest.fixture(scope="module")
+def small():
+    return _build(O.SMALL_CFG, 0)
+
+
+@pytest.mark.parametrize("name", ["unet_small.npz", "unet_small_ragged.npz"])
+def test_unet_small_vs_reference_golden(small, name):
+    m, sd = small
+    g = load_golden(name)
+    x, t, ctx = torch.tensor(g["x"]), torch.tensor(g["t"]), torch.tensor(g["context"])
+    with torch.no_grad():
+        y = m(x.cuda(), t.cuda(), context=ctx.cuda())
+    assert y.dtype == torch.float32 and y.shape == g["out"].shape
+    _assert_parity(y, g["out"], _floor(sd, O.SMALL_CFG, x, t, ctx))
+
+
+def test_unet_fresh_inputs_vs_oracle(small):
+    """Seeded inputs that are not in the fixtures: native vs the CPU oracle, incl. per-sample timesteps, batch 3."""
+    m, sd = small
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(3, 9, 32, 16, generator=g)
+    ctx = torch.randn(3, 77, 256, generator=g)
+    t = torch.tensor([1, 500, 999])
+    with torch.no_grad():
+        ref = O.unet_forward(sd, O.SMALL_CFG, x, t, ctx)
+        y = m(x.cuda(), t.cuda(), context=ctx.cuda())
+    _assert_parity(y, ref, _floor(sd, O.SMALL_CFG, x, t, ctx))
+
+
+def test_weight_update_is_picked_up(small):
+    m, sd = small
+    g = load_golden("unet_small.npz")
+    x, t, ctx = (torch.tensor(g[k]).cuda() for k in ("x", "t", "context"))
+    with torch.no_grad():
+        y0 = m(x, t, context=ctx)
+        w = m.out[2].weight
+        old = w.clone()
+        w.mul_(2.0)                       # in-place update bumps the version counter -> re-upload
+        y1 = m(x, t, context=ctx)
+        w.copy_(old)
+        y2 = m(x, t, context=ctx)
+    b = m.out[2].bias.detach()[None, :, None, None]
+    assert torch.allclose(y1 - b, 2 * (y0 - b), rtol=2e-3, atol=2e-3)
+    assert torch.allclose(y2, y0, rtol=1e-3, atol=1e-3)
+
+
+def test_autocast_and_no_grad_context(small):
+    m, _ = small
+    g = load_golden("unet_small.npz")
+    x, t, ctx = (torch.tensor(g[k]).cuda() for k in ("x", "t", "context"))
+    with torch.no_grad(), torch.autocast("cuda"):
+        y = m(x, t, context=ctx)
+    assert y.dtype == torch.float16      # what the reference returns under autocast
+    _assert_parity(y.float(), g["out"])
+
+
+def test_multiview_v2_vs_reference_golden():
+    g = load_golden("multiview_v2.npz")
+    mv = (int(g["view_num"]), bool(g["concat_target"]))
+    m, sd = _build(O.SMALL_CFG, 1, multiview=mv)
+    x, t, ctx = torch.tensor(g["x"]), torch.tensor(g["t"]), torch.tensor(g["context"])
+    with torch.no_grad():
+        y = m(x.cuda(), t.cuda(), context=ctx.cuda())
+    _assert_parity(y, g["out"], _floor(sd, O.SMALL_CFG, x, t, ctx, view_num=mv[0], concat_target=mv[1]))
+
+
+@pytest.mark.parametrize("tag,eta", [("eta0", 0.0), ("eta1", 1.0)])
+def test_ddim_sampler_vs_reference_golden(small, tag, eta):
+    """Drop-in DDIMSampler.sample (hoisted native fast path) vs the reference sampler's golden samples."""
+    import leftrefill_b200 as lr
+    m, _ = small
+    g = load_golden("ddim_small.npz")
+    dev = torch.device("cuda")
+    noises = torch.tensor(g[f"{tag}.noises"]).to(dev)
+    s = lr.DDIMSampler(FakeLDM(m, dev))
+    s.noise_source = lambda shape, device, i: noises[i]
+    cond = {"c_concat": [torch.tensor(g["c_concat"]).to(dev)], "c_crossattn": [torch.tensor(g["context"]).to(dev)]}
+    uc = {"c_concat": [torch.tensor(g["c_concat"]).to(dev)], "c_crossattn": [torch.tensor(g["uc_context"]).to(dev)]}
+    samples, inter = s.sample(4, 1, (4, 16, 32), cond, eta=eta, x_T=torch.tensor(g["x_T"]).to(dev), verbose=False,
+                              unconditional_guidance_scale=2.5, unconditional_conditioning=uc, log_every_t=1)
+    assert len(inter["x_inter"]) == int(g[f"{tag}.n_inter"]) and len(inter["pred_x0"]) == len(inter["x_inter"])
+    _assert_parity(samples, g[f"{tag}.samples"])
+    _assert_parity(inter["pred_x0"][-1], g[f"{tag}.pred_x0_last"])
+
+
+def test_sampler_generic_path_equals_fast_path(small):
+    """apply_model route (any model) and the hoisted native route must agree; RNG consumption must be identical."""
+    import leftrefill_b200 as lr
+    m, _ = small
+    dev = torch.device("cuda")
+    x_T, c_cat, ctx, uc = synthetic_inputs(2, h=16, w=32, ctx_dim=256, device=dev)
+    cond = {"c_concat": [c_cat], "c_crossattn": [ctx]}
+    ucond = {"c_concat": [c_cat], "c_crossattn": [uc]}
+    outs = []
+    for fast in (True, False):
+        ldm = FakeLDM(m, dev)
+        if not fast:
+            ldm.model.conditioning_key = "hybrid-generic"  # defeats the fast-path detection only
+            ldm.apply_model = lambda x, t, c, _m=m: _m(torch.cat([x] + c["c_concat"], 1), t,
+                                                        context=torch.cat(c["c_crossattn"], 1))
+        torch.manual_seed(123)
+        s = lr.DDIMSampler(ldm)
+        y, _ = s.sample(3, 2, (4, 16, 32), cond, eta=1.0, verbose=False, unconditional_guidance_scale=2.5,
+                        unconditional_conditioning=ucond)
+        outs.append((y, torch.rand(1, device=dev)))
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=2e-3, atol=2e-3)
+    assert torch.equal(outs[0][1], outs[1][1])  # both routes consumed the same number of random draws
+
+
+@pytest.fixture(scope="module")
+def full():
+    return _build(O.DEFAULT_CFG, 0)
+
+
+def test_unet_full_config_vs_reference_golden(full):
+    m, sd = full
+    g = load_golden("unet_full_16x32.npz")
+    x, t, ctx = torch.tensor(g["x"]), torch.tensor(g["t"]), torch.tensor(g["context"])
+    with torch.no_grad():
+        y = m(x.cuda(), t.cuda(), context=ctx.cuda())
+    _assert_parity(y, g["out"], _floor(sd, O.DEFAULT_CFG, x, t, ctx))
+
+
+def test_unet_full_size_properties(full):
+    """BASELINE config C2 size (4 canvases + CFG = UNet batch 8, 64x128 latent, 865.9 M params): size-independent
+    properties, plus direct parity of one canvas against the fp32 oracle (run on the GPU to finish in seconds)."""
+    m, sd = full
+    dev = "cuda"
+    xT, c_cat, ctx, uc = synthetic_inputs(4, device=dev)
+    xc = torch.cat([torch.cat([xT, xT]), torch.cat([c_cat, c_cat])], dim=1).contiguous()
+    cc = torch.cat([uc, ctx]).contiguous()
+    t = torch.full((8,), 981, dtype=torch.long, device=dev)
+    with torch.no_grad():
+        y = m(xc, t, context=cc)
+        assert torch.isfinite(y).all() and y.shape == (8, 4, 64, 128)
+        # batch-permutation equivariance: samples are independent
+        perm = torch.tensor([5, 2, 7, 0, 3, 6, 1, 4], device=dev)
+        yp = m(xc[perm].contiguous(), t, context=cc[perm].contiguous())
+        s = err_stats(yp, y[perm])
+        assert s["rel_rms"] < 1e-3, s
+        # identical cond / uncond inputs give identical halves -> CFG is the identity for any scale
+        ysame = m(xc, t, context=torch.cat([ctx, ctx]).contiguous())
+        s = err_stats(ysame[:4], ysame[4:])
+        assert s["rel_rms"] < 1e-3, s
+        # run-to-run determinism within fp16 noise (GroupNorm partial sums use atomics)
+        s = err_stats(m(xc, t, context=cc), y)
+        assert s["rel_rms"] < 5e-4, s
+        # direct parity of canvas 0 (cond row) against the fp32 oracle
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        sdc = {k: v.cuda() for k, v in sd.items()}
+        ref = O.unet_forward(sdc, O.DEFAULT_CFG, xc[4:5], t[:1], cc[4:5])
+        with torch.autocast("cuda"):
+            floor = O.unet_forward(sdc, O.DEFAULT_CFG, xc[4:5], t[:1], cc[4:5]).float()
+    _assert_parity(y[4:5], ref, floor)
