@@ -74,6 +74,9 @@ int lr_unet_forward(lr_unet* h, const float* x, const int64_t* timesteps, const 
  * 0 = gemm_conv_kernel (all convs + linears), 1 = attention_kernel, 2 = GroupNorm kernels, 3 = LayerNorm, 4 = other. */
 int lr_unet_set_profiling(lr_unet* h, int enable);
 int lr_unet_read_profile(lr_unet* h, double ms_by_class[5], double flops_by_class[5], int steps_by_class[5]);
+/* Per plan step: duration of the last profiled forward (ms, -1 if none), algorithmic FLOPs, class, description. */
+int lr_unet_num_steps(const lr_unet* h);
+int lr_unet_step_info(lr_unet* h, int index, double* ms, double* flops, int* cls, char* desc, int desc_len);
 /* Algorithmic FLOPs (2*M*N*K convs/linears + 4*Tq*Tk*d attention) of the last planned forward. */
 double lr_unet_last_flops(const lr_unet* h);
 /* Bytes of device memory held by the engine (weights + activation plan). */

@@ -51,6 +51,9 @@ SIGNATURES = {
                                 c_void_p]),
     "lr_unet_set_profiling": (c_int, [c_void_p, c_int]),
     "lr_unet_read_profile": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int)]),
+    "lr_unet_num_steps": (c_int, [c_void_p]),
+    "lr_unet_step_info": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_double), POINTER(c_int), c_char_p,
+                                  c_int]),
     "lr_unet_last_flops": (c_double, [c_void_p]),
     "lr_unet_device_bytes": (c_longlong, [c_void_p]),
     "lr_ddim_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float,

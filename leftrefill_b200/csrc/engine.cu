@@ -2,6 +2,7 @@
 // from the constructor config, owns fp16 repacked weights, and executes UNetModel.forward as a static plan of
 // tcgen05 GEMM/conv ops, fused attention ops and HBM-bound norm kernels on NHWC fp16 activations.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -124,12 +125,13 @@ struct lr_unet {
     std::function<int(cudaStream_t)> fn;
     int cls;       // 0 gemm/conv (gemm_conv_kernel), 1 attention, 2 groupnorm, 3 layernorm, 4 other
     double flops;  // algorithmic FLOPs of this step
+    std::string desc;
   };
   std::vector<Step> steps;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;  // steps.size() + 1 events of the last profiled forward
-  void push(std::function<int(cudaStream_t)> fn, int cls = 4, double fl = 0.0) {
-    steps.push_back(Step{std::move(fn), cls, fl});
+  void push(std::function<int(cudaStream_t)> fn, int cls = 4, double fl = 0.0, std::string desc = "") {
+    steps.push_back(Step{std::move(fn), cls, fl, std::move(desc)});
   }
   std::vector<std::unique_ptr<ConvOp>> conv_ops;
   std::vector<std::unique_ptr<AttnOp>> attn_ops;
@@ -386,7 +388,11 @@ struct lr_unet {
     flops += op->flops;
     ConvOp* raw = op.get();
     conv_ops.push_back(std::move(op));
-    push([raw](cudaStream_t st) { return launch_conv_op(*raw, st); }, 0, raw->flops);
+    char d[200];
+    snprintf(d, sizeof(d), "%s n=%d %dx%d s%d c=%d+%d->%d%s bn=%d st=%d tiles=%d",
+             s.taps == 9 ? "conv3x3" : "linear", s.n_img, s.in_h, s.in_w, s.stride, s.c0, s.c1, s.ncols,
+             s.geglu ? " geglu" : (s.residual ? " +res" : ""), raw->block_n, raw->stages, raw->tiles);
+    push([raw](cudaStream_t st) { return launch_conv_op(*raw, st); }, 0, raw->flops, d);
     return 0;
   }
   int add_linear(const __half* a, int M, int K, const __half* w, int ncols, const float* bias, const __half* residual,
@@ -420,11 +426,13 @@ struct lr_unet {
     float *sc = gn_scale, *sh = gn_shift;
     push([=](cudaStream_t st) {
       return launch_groupnorm(x0, c0, x1, c1, n, P, 32, eps, g, b, silu, st_, sc, sh, out, st);
-    }, 2);
+    }, 2, 0.0, "groupnorm n=" + std::to_string(n) + " P=" + std::to_string(P) + " c=" + std::to_string(c0) + "+" +
+                   std::to_string(c1));
     return 0;
   }
   int add_ln(const __half* x, int M, int C, const float* g, const float* b, __half* out) {
-    push([=](cudaStream_t st) { return launch_layernorm(x, M, C, g, b, 1e-5f, out, st); }, 3);
+    push([=](cudaStream_t st) { return launch_layernorm(x, M, C, g, b, 1e-5f, out, st); }, 3, 0.0,
+         "layernorm M=" + std::to_string(M) + " C=" + std::to_string(C));
     return 0;
   }
   int add_attn(const AttnSpec& s) {
@@ -433,7 +441,9 @@ struct lr_unet {
     flops += op->flops;
     AttnOp* raw = op.get();
     attn_ops.push_back(std::move(op));
-    push([raw](cudaStream_t st) { return launch_attn_op(*raw, st); }, 1, raw->flops);
+    char d[200];
+    snprintf(d, sizeof(d), "attention b=%d h=%d tq=%d tk=%d", s.batch, s.heads, s.tq, s.tk);
+    push([raw](cudaStream_t st) { return launch_attn_op(*raw, st); }, 1, raw->flops, d);
     return 0;
   }
 
@@ -964,6 +974,24 @@ int lr_unet_read_profile(lr_unet* h, double ms_by_class[5], double flops_by_clas
     ms_by_class[c] += ms;
     flops_by_class[c] += h->steps[i].flops;
     steps_by_class[c] += 1;
+  }
+  return 0;
+}
+
+int lr_unet_num_steps(const lr_unet* h) { return h ? static_cast<int>(h->steps.size()) : 0; }
+
+int lr_unet_step_info(lr_unet* h, int i, double* ms, double* flops, int* cls, char* desc, int desc_len) {
+  LR_CHECK(h != nullptr && i >= 0 && i < static_cast<int>(h->steps.size()), "lr_unet_step_info: bad index");
+  *ms = -1.0;
+  if (h->prof_events.size() >= h->steps.size() + 1) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, h->prof_events[i], h->prof_events[i + 1]) == cudaSuccess) *ms = t;
+  }
+  *flops = h->steps[i].flops;
+  *cls = h->steps[i].cls;
+  if (desc && desc_len > 0) {
+    strncpy(desc, h->steps[i].desc.c_str(), desc_len - 1);
+    desc[desc_len - 1] = 0;
   }
   return 0;
 }

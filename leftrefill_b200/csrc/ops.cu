@@ -193,6 +193,9 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   const int num_tiles = tiles_m * p.tiles_n;
   op->grid = num_tiles < sm_count() ? num_tiles : sm_count();
   op->smem = gemm_smem_bytes(block_n, stages);
+  op->block_n = block_n;
+  op->stages = stages;
+  op->tiles = num_tiles;
   op->flops = 2.0 * s.n_img * Ho * Wo * static_cast<double>(s.ncols) * s.taps * (s.c0 + s.c1);
   memcpy(op->params, &p, sizeof(p));
   static bool attr_set = false;

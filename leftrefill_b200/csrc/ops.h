@@ -58,6 +58,7 @@ struct ConvOp {
   alignas(64) unsigned char params[1024];  // GemmParams (opaque here so headers stay CUDA-kernel free)
   int grid = 0, smem = 0;
   int out_h = 0, out_w = 0;
+  int block_n = 0, stages = 0, tiles = 0;
   double flops = 0;
 };
 int build_conv_op(ConvOp* op, const ConvSpec& s);

@@ -93,7 +93,8 @@ def test_weight_update_is_picked_up(small):
         w.copy_(old)
         y2 = m(x, t, context=ctx)
     b = m.out[2].bias.detach()[None, :, None, None]
-    assert torch.allclose(y1 - b, 2 * (y0 - b), rtol=2e-3, atol=2e-3)
+    assert not torch.allclose(y1, y0, rtol=1e-2, atol=1e-2)
+    assert torch.allclose(y1 - b, 2 * (y0 - b), rtol=5e-3, atol=8e-3)  # outputs are fp16-rounded (ulp 2e-3 at |y|~2)
     assert torch.allclose(y2, y0, rtol=1e-3, atol=1e-3)
 
 
