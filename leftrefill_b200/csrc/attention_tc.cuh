@@ -3,13 +3,16 @@
 // materialises the [b*h, Tq, Tk] fp32 logits (1.34 GB per canvas at T = 8192). Precision islands are kept:
 // fp16 operands, fp32 QK^T accumulation (the reference's _ATTN_PRECISION="fp32" path), fp32 softmax statistics.
 //
-// One CTA = one (batch, head, 128-query tile). d_head = 64.
-//   warp 0 (1 lane): TMA — Q once, then a 2-stage ring of {K_j, V_j} 128-token tiles (OOB rows zero-filled)
-//   warp 1 (1 lane): tcgen05.mma — S = Q K_j^T (128x128, TMEM cols 0..127), O += P_j V_j (128x64, cols 128..191)
-//   warps 2..5     : softmax — thread <-> query row (tcgen05.ld 32x32b), online max with lazy rescaling of the
-//                    TMEM-resident O, P_j written as fp16 into a 128B-swizzled smem tile that feeds the PV MMA.
+// One CTA = one (batch, head, 256-query block) = two 128-row query tiles that ping-pong on the tensor core. d_head = 64.
+//   warp 0 (1 lane)   : TMA — Q0/Q1 once, then a 3-stage ring of {K_j, V_j} 128-token tiles shared by both query tiles
+//   warp 1 (1 lane)   : tcgen05.mma — S_t = Q_t K_j^T (128x128 fp32, TMEM), O_t += P_t V_j (128x64 fp32, TMEM).
+//                       S_t(j+1) is issued as soon as warpgroup t has pulled S_t(j) into registers, so the tensor pipe
+//                       computes the next logits / the other tile's PV while a warpgroup is in its exp phase.
+//   warps 4..7, 8..11 : softmax warpgroup for tile 0 / tile 1 — thread <-> query row (tcgen05.ld 32x32b), the whole
+//                       128-wide logits row lives in registers (setmaxnreg moves registers from warps 0..3), online max
+//                       with lazy rescaling of the TMEM-resident O (threshold 2^8), P_t written as fp16 into a
+//                       128B-swizzled smem tile that is the A operand of the PV MMA.
 // V is consumed as an MN-major B operand straight from the [token, d] layout the QKV GEMM produces: no transposes.
-// ~113 KB smem and 256 TMEM columns per CTA, so two CTAs share an SM and overlap each other's MMA/softmax phases.
 #pragma once
 #include "ptx.cuh"
 
@@ -24,12 +27,15 @@ struct AttnParams {
   float scale_log2;            // softmax scale * log2(e)
 };
 
-constexpr int kAttnThreads = 192;
-constexpr int kAttnTile = 128;
+constexpr int kAttnThreads = 384;
+constexpr int kAttnTile = 128;                          // rows of one query tile / keys per KV tile
+constexpr int kAttnQBlock = 2 * kAttnTile;              // queries per CTA
 constexpr int kAttnD = 64;
 constexpr int kAttnTileBytes = kAttnTile * kAttnD * 2;  // 16 KB
-constexpr int kAttnStages = 2;
-constexpr int kAttnSmemBytes = kAttnTileBytes * (1 + 2 * kAttnStages) + 2 * kAttnTileBytes /*P*/ + 128 /*barriers*/;
+constexpr int kAttnStages = 3;
+constexpr int kAttnPBytes = 2 * kAttnTileBytes;         // one P tile: 128 x 128 fp16 = two swizzle atoms
+constexpr int kAttnSmemBytes = 2 * kAttnTileBytes /*Q0,Q1*/ + kAttnStages * 2 * kAttnTileBytes /*K,V ring*/ +
+                               2 * kAttnPBytes /*P0,P1*/ + 256 /*barriers*/;
 constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P stays <= 256, exact in fp16/fp32 accumulators
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -37,26 +43,35 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 
-__global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* q_s = smem;
-  uint8_t* k_s = q_s + kAttnTileBytes;                       // [stages]
+  uint8_t* q_s = smem;                                       // [2] query tiles
+  uint8_t* k_s = q_s + 2 * kAttnTileBytes;                   // [stages]
   uint8_t* v_s = k_s + kAttnStages * kAttnTileBytes;         // [stages]
-  uint8_t* p_s = v_s + kAttnStages * kAttnTileBytes;         // 2 swizzle atoms of [128 x 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 2 * kAttnTileBytes);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint8_t* p_s = v_s + kAttnStages * kAttnTileBytes;         // [2] P tiles (2 swizzle atoms of [128 x 64] each)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 2 * kAttnPBytes);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* kv_full = bars + 1;     // [3]
+  uint64_t* kv_empty = bars + 4;    // [3]
+  uint64_t* s_full = bars + 7;      // [2] S_t(j) is in TMEM
+  uint64_t* s_empty = bars + 9;     // [2] warpgroup t holds S_t(j) in registers
+  uint64_t* p_full = bars + 11;     // [2] P_t(j) is in smem
+  uint64_t* pv_done = bars + 13;    // [2] O_t += P_t(j) V_j has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int qb = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int ntiles = (p.tk + kAttnTile - 1) / kAttnTile;
+  // the second query tile may lie completely beyond tq (e.g. the 8x16 level has 128 tokens): it is then skipped
+  // everywhere (no fully out-of-bounds TMA box, no MMA, no softmax work)
+  const int ntq = (qb * kAttnQBlock + kAttnTile < p.tq) ? 2 : 1;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -71,26 +86,32 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_empty[t], 128);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&pv_done[t], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + 128;
+  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
 
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kAttnTileBytes);
-      tma_load_3d(q_s, &p.tmQ, q_full, p.q_col0 + head * kAttnD, qt * kAttnTile, b);
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (warp == 0 && lane == 0) {
+      // ------------------------------- TMA producer -------------------------------
+      mbar_arrive_expect_tx(q_full, ntq * kAttnTileBytes);
+      tma_load_3d(q_s, &p.tmQ, q_full, p.q_col0 + head * kAttnD, qb * kAttnQBlock, b);
+      if (ntq == 2)
+        tma_load_3d(q_s + kAttnTileBytes, &p.tmQ, q_full, p.q_col0 + head * kAttnD, qb * kAttnQBlock + kAttnTile, b);
       for (int j = 0; j < ntiles; ++j) {
         const int s = j % kAttnStages;
         const uint32_t ph = (j / kAttnStages) & 1;
@@ -99,62 +120,102 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         tma_load_3d(k_s + s * kAttnTileBytes, &p.tmK, &kv_full[s], p.k_col0 + head * kAttnD, j * kAttnTile, b);
         tma_load_3d(v_s + s * kAttnTileBytes, &p.tmV, &kv_full[s], p.v_col0 + head * kAttnD, j * kAttnTile, b);
       }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
+    } else if (warp == 1 && lane == 0) {
+      // ------------------------------- MMA issuer ---------------------------------
       const uint32_t idesc_s = umma_idesc_f16(128, kAttnTile, 0);  // S: N = 128 keys, K-major B
       const uint32_t idesc_o = umma_idesc_f16(128, kAttnD, 1);     // O: N = 64 channels, MN-major B (V)
       const uint32_t q_addr = smem_u32(q_s);
       const uint32_t p_addr = smem_u32(p_s);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % kAttnStages;
-        const uint32_t ph = (j / kAttnStages) & 1;
-        mbar_wait(&kv_full[s], ph);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(k_s + s * kAttnTileBytes);
-        const uint32_t v_addr = smem_u32(v_s + s * kAttnTileBytes);
+      auto issue_s = [&](int t, int stage) {
+        const uint32_t k_addr = smem_u32(k_s + stage * kAttnTileBytes);
+        const uint32_t qa = q_addr + t * kAttnTileBytes;
 #pragma unroll
         for (int k = 0; k < kAttnD / 16; ++k) {
-          umma_f16(tmem_S, umma_smem_desc_sw128(q_addr + k * 32, 1024, 16),
+          umma_f16(tmem_base + t * 128, umma_smem_desc_sw128(qa + k * 32, 1024, 16),
                    umma_smem_desc_sw128(k_addr + k * 32, 1024, 16), idesc_s, k != 0 ? 1u : 0u);
         }
-        umma_commit(s_full);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int stage, bool accumulate) {
+        const uint32_t v_addr = smem_u32(v_s + stage * kAttnTileBytes);
+        const uint32_t pa0 = p_addr + t * kAttnPBytes;
 #pragma unroll
         for (int k = 0; k < kAttnTile / 16; ++k) {
-          const uint32_t pa = p_addr + (k >> 2) * kAttnTileBytes + (k & 3) * 32;
+          const uint32_t pa = pa0 + (k >> 2) * kAttnTileBytes + (k & 3) * 32;
           const uint32_t va = v_addr + k * 16 * 128;  // 16 token rows of 128 B
-          umma_f16(tmem_O, umma_smem_desc_sw128(pa, 1024, 16), umma_smem_desc_sw128(va, 1024, 16), idesc_o,
-                   (j | k) != 0 ? 1u : 0u);
+          umma_f16(tmem_base + 256 + t * 64, umma_smem_desc_sw128(pa, 1024, 16), umma_smem_desc_sw128(va, 1024, 16),
+                   idesc_o, (accumulate || k != 0) ? 1u : 0u);
         }
-        umma_commit(&kv_empty[s]);
-        if (j == ntiles - 1) umma_commit(o_full);
+        umma_commit(&pv_done[t]);
+      };
+      mbar_wait(q_full, 0);
+      for (int j = 0; j <= ntiles; ++j) {
+        if (j < ntiles) {
+          const int s = j % kAttnStages;
+          mbar_wait(&kv_full[s], (j / kAttnStages) & 1);
+          tc_fence_after();
+          for (int t = 0; t < ntq; ++t) {
+            if (j > 0) {
+              mbar_wait(&s_empty[t], (j - 1) & 1);
+              tc_fence_after();
+            }
+            issue_s(t, s);
+          }
+        }
+        if (j > 0) {
+          const int sp = (j - 1) % kAttnStages;
+          for (int t = 0; t < ntq; ++t) {
+            mbar_wait(&p_full[t], (j - 1) & 1);
+            tc_fence_after();
+            issue_pv(t, sp, j - 1 > 0);
+          }
+          umma_commit(&kv_empty[sp]);
+        }
       }
     }
   } else {
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
+    // ------------------------------- softmax warpgroups ---------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const int t = (warp - 4) >> 2;  // query tile of this warpgroup
+    const int q = warp & 3;         // TMEM lane quarter
+    const int r = q * 32 + lane;    // row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tmem_S = tmem_base + t * 128 + lane_addr;
+    const uint32_t tmem_O = tmem_base + 256 + t * 64 + lane_addr;
+    uint8_t* prow = p_s + t * kAttnPBytes + r * 128;
     float m_used = -INFINITY;  // max the current O / l are scaled against (raw logit units)
     float l = 0.f;
-    for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(s_full, j & 1);  // also implies PV_{j-1} has completed (commit covers all prior MMAs)
+    const int my_tiles = (t < ntq) ? ntiles : 0;
+    for (int j = 0; j < my_tiles; ++j) {
+      mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      const int kv_valid = min(kAttnTile, p.tk - j * kAttnTile);
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < kAttnTile; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_addr + c, v);
+      uint32_t s[128];
+      {
+        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+        uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+        uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+        tmem_ld32(tmem_S + 0, s0);
+        tmem_ld32(tmem_S + 32, s1);
+        tmem_ld32(tmem_S + 64, s2);
+        tmem_ld32(tmem_S + 96, s3);
         tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
-      const float m_new = fmaxf(m_used, mx);
+      tc_fence_before();
+      mbar_arrive(&s_empty[t]);  // S_t may be overwritten by the next QK^T
+      const int kv_valid = p.tk - j * kAttnTile;
+      if (kv_valid < kAttnTile) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+      }
+      const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
       const bool need = (m_new - m_used) * p.scale_log2 > kRescaleThreshold;  // true on the first tile (-inf)
       float alpha = 1.0f;
       if (need) {
@@ -162,58 +223,63 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         m_used = m_new;
         l *= alpha;
       }
-      if (j > 0 && __any_sync(0xffffffffu, need)) {
-        // rescale the TMEM-resident O row (warp-collective; lanes that do not need it use alpha = 1)
-#pragma unroll 1
-        for (int c = 0; c < kAttnD; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_O + lane_addr + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st32(tmem_O + lane_addr + c, v);
-        }
-        tmem_st_wait();
-      }
-      // pass 2: P = exp2((s - m_used) * scale_log2) -> fp16, swizzled K-major smem tile
+      // P = exp2((s - m_used) * scale_log2) -> packed fp16 in registers (no shared-memory traffic yet, so this phase
+      // overlaps the previous PV MMA that is still reading P_t from smem)
       const float moff = m_used * p.scale_log2;
-      uint8_t* prow = p_s + r * 128;
+      float l0 = 0.f, l1 = 0.f;
+      uint32_t h[64];
+#pragma unroll
+      for (int c = 0; c < 128; c += 8) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = fast_exp2(fmaf(__uint_as_float(s[c + i]), p.scale_log2, -moff));
+        l0 += (e[0] + e[1]) + (e[2] + e[3]);
+        l1 += (e[4] + e[5]) + (e[6] + e[7]);
+        h[(c >> 1) + 0] = pack_half2(e[0], e[1]);
+        h[(c >> 1) + 1] = pack_half2(e[2], e[3]);
+        h[(c >> 1) + 2] = pack_half2(e[4], e[5]);
+        h[(c >> 1) + 3] = pack_half2(e[6], e[7]);
+      }
+      if (j > 0) {
+        mbar_wait(&pv_done[t], (j - 1) & 1);  // PV(j-1) finished: P_t smem and O_t may be touched
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+          // rescale the TMEM-resident O row (warp-collective; lanes that do not need it use alpha = 1)
 #pragma unroll 1
-      for (int c = 0; c < kAttnTile; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_addr + c, v);
-        tmem_ld_wait();
-        uint32_t h[16];
+          for (int c = 0; c < kAttnD; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_O + c, v);
+            tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (c + i < kv_valid) ? fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - moff) : 0.f;
-          float p1 = (c + i + 1 < kv_valid) ? fast_exp2(__uint_as_float(v[i + 1]) * p.scale_log2 - moff) : 0.f;
-          l += p0 + p1;
-          h[i >> 1] = pack_half2(p0, p1);
-        }
-        // columns [c, c+32) = 4 chunks of 16 B inside atom (c / 64)
-        uint8_t* atom = prow + (c >> 6) * kAttnTileBytes;
-        const int chunk0 = (c & 63) >> 3;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int ch = (chunk0 + k) ^ (r & 7);
-          *reinterpret_cast<uint4*>(atom + ch * 16) = make_uint4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(tmem_O + c, v);
+          }
+          tmem_st_wait();
         }
       }
+      // swizzled K-major smem tile: columns [c, c+8) = 16-byte chunk ((c & 63) >> 3) of atom (c >> 6), XOR row
+#pragma unroll
+      for (int c = 0; c < 128; c += 8) {
+        const int ch = ((c & 63) >> 3) ^ (r & 7);
+        *reinterpret_cast<uint4*>(prow + (c >> 6) * kAttnTileBytes + ch * 16) =
+            make_uint4(h[(c >> 1)], h[(c >> 1) + 1], h[(c >> 1) + 2], h[(c >> 1) + 3]);
+      }
+      l += l0 + l1;
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[t]);
     }
     // epilogue: O / l -> fp16
-    mbar_wait(o_full, 0);
+    if (t < ntq) {
+    mbar_wait(&pv_done[t], (ntiles - 1) & 1);
     tc_fence_after();
-    const int row = qt * kAttnTile + r;
+    const int row = qb * kAttnQBlock + t * kAttnTile + r;
     const float inv_l = 1.0f / l;
     __half* o = p.out + (static_cast<size_t>(b) * p.tq + row) * p.ld_out + head * kAttnD;
 #pragma unroll 1
     for (int c = 0; c < kAttnD; c += 32) {
       uint32_t v[32];
-      tmem_ld32(tmem_O + lane_addr + c, v);
+      tmem_ld32(tmem_O + c, v);
       tmem_ld_wait();
       if (row < p.tq) {
 #pragma unroll
@@ -227,11 +293,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         }
       }
     }
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace lr

@@ -14,8 +14,8 @@
 // Structure (one CTA per SM, persistent over output tiles of 128 x block_n):
 //   warp 0 (1 lane)  TMA producer      -> smem ring of {A 128x64, B block_n x 64} fp16 stages, 128B swizzle
 //   warp 1 (1 lane)  tcgen05.mma issue -> fp32 accumulator in TMEM, double buffered (2 x 256 columns)
-//   warps 2..5       epilogue          -> tcgen05.ld, bias / per-image bias (time embedding) / residual / GEGLU,
-//                                         fp16 stores
+//   warps 2..9       epilogue          -> tcgen05.ld, bias (smem staged) / per-image bias (time embedding) /
+//                                         residual (prefetched one chunk ahead) / GEGLU, fp16 stores
 #pragma once
 #include "ptx.cuh"
 
@@ -46,18 +46,36 @@ struct GemmParams {
   float out_scale;         // multiplies the final value (1.0 normally)
 };
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kMaxStages = 8;
+constexpr int kGemmAuxBytes = 256 /*barriers*/ + 2 * 256 * 4 /*bias staging, double buffered*/;
 
 __host__ __device__ inline int gemm_stage_bytes(int block_n) { return kATileBytes + block_n * kBlockK * 2; }
 __host__ inline int gemm_smem_bytes(int block_n, int stages) {
-  return 1024 /*align slack*/ + stages * gemm_stage_bytes(block_n) + 256 /*barriers*/;
+  return 1024 /*align slack*/ + stages * gemm_stage_bytes(block_n) + kGemmAuxBytes;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf with |abs error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): one MUFU.RCP + one MUFU.EX2 + 8 FMA-pipe ops.
+// GELU here is the exact-erf form of F.gelu (attention.py:58); the output is rounded to fp16 (2^-11) afterwards.
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
+  return copysignf(fmaf(-p, e, 1.0f), x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
 
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -69,6 +87,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   uint64_t* tfull = bars + 2 * kMaxStages; // [2]
   uint64_t* tempty = tfull + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -83,7 +102,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -168,8 +187,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     }
   } else {
     // ------------------------------- epilogue warps -----------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // 8 warps: warp (2+w) reads TMEM lane quarter (w & 3); the two warps of a quarter interleave 32-column chunks.
+    const int ew = warp - 2;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access (hardware: warp id % 4)
+    const int half = ew >> 2;
     const int r = q * 32 + lane;
+    const int etid = threadIdx.x - 64;
     int as = 0;
     uint32_t aph = 0;
     const bool vec_ok = (p.ld_out % 8 == 0) && (p.residual == nullptr || p.ld_res % 8 == 0);
@@ -188,22 +211,49 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       const size_t grow = (static_cast<size_t>(n) * p.H + y) * p.W + x;
       const int ncol0 = tn * p.block_n;
 
+      // stage this tile's bias slice (double buffered by accumulator stage; the named barrier orders reuse)
+      float* sb = sbias + as * 256;
+      for (int i = etid; i < p.block_n; i += kEpiThreads)
+        sb[i] = (p.bias != nullptr && ncol0 + i < p.ncols) ? __ldg(p.bias + ncol0 + i) : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+
+      // residual of the first chunk is fetched before the accumulator is ready (it does not depend on the MMA)
+      const bool fast = vec_ok && row_ok && !p.geglu;
+      const __half* res_row = (p.residual != nullptr) ? p.residual + grow * p.ld_res : nullptr;
+      uint4 rnext[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      int c = half * 32;
+      if (fast && res_row != nullptr && c < p.block_n && ncol0 + c + 32 <= p.n_valid) {
+        const uint4* rp = reinterpret_cast<const uint4*>(res_row + ncol0 + c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rnext[k] = __ldg(rp + k);
+      }
+
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
-      for (int c = 0; c < p.block_n; c += 32) {
+      for (; c < p.block_n; c += 64) {
         uint32_t v[32];
         tmem_ld32(t_row + c, v);
+        uint4 rcur[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rcur[k] = rnext[k];
+        const int cn = c + 64;
+        if (fast && res_row != nullptr && cn < p.block_n && ncol0 + cn + 32 <= p.n_valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(res_row + ncol0 + cn);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rnext[k] = __ldg(rp + k);
+        }
         tmem_ld_wait();
         const int col0 = ncol0 + c;
         if (row_ok && col0 < p.ncols) {
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.ncols) f[j] += __ldg(p.bias + col0 + j);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + c + j);
+            f[j] = __uint_as_float(v[j]) + b4.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
           }
           if (p.bias_img != nullptr) {
             const float* bi = p.bias_img + static_cast<size_t>(n) * p.ncols + col0;
@@ -231,12 +281,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
           } else {
             __half* o = p.out + grow * p.ld_out + col0;
             if (vec_ok && col0 + 32 <= p.n_valid) {
-              if (p.residual != nullptr) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + grow * p.ld_res + col0);
+              if (res_row != nullptr) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  const uint4 rv = __ldg(rp + k);
-                  const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+                  const uint32_t rw[4] = {rcur[k].x, rcur[k].y, rcur[k].z, rcur[k].w};
 #pragma unroll
                   for (int h = 0; h < 4; ++h) {
                     const float2 t = unpack_half2(rw[h]);
@@ -257,7 +305,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
               for (int j = 0; j < 32; ++j) {
                 if (col0 + j < p.n_valid) {
                   float t = f[j];
-                  if (p.residual != nullptr) t += __half2float(p.residual[grow * p.ld_res + col0 + j]);
+                  if (res_row != nullptr) t += __half2float(res_row[col0 + j]);
                   o[j] = __float2half_rn(t * p.out_scale);
                 }
               }

@@ -147,7 +147,7 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   LR_CHECK(!s.geglu || (s.ncols % 2 == 0), "conv: GEGLU needs an even column count");
   p.block_n = block_n;
   p.tiles_n = cdiv(s.ncols, block_n);
-  int stages = (232448 - 1024 - 256) / gemm_stage_bytes(block_n);
+  int stages = (232448 - 1024 - kGemmAuxBytes) / gemm_stage_bytes(block_n);
   if (stages > kMaxStages) stages = kMaxStages;
   LR_CHECK(stages >= 2, "conv: not enough shared memory for 2 stages");
   p.stages = stages;
@@ -243,7 +243,7 @@ int build_attn_op(AttnOp* op, const AttnSpec& s) {
   p.out = s.out;
   p.ld_out = s.ld_out;
   p.scale_log2 = s.scale * 1.4426950408889634f;
-  op->grid = dim3(cdiv(s.tq, kAttnTile), s.heads, s.batch);
+  op->grid = dim3(cdiv(s.tq, kAttnQBlock), s.heads, s.batch);
   op->flops = 4.0 * s.batch * s.heads * static_cast<double>(s.tq) * s.tk * kAttnD;
   memcpy(op->params, &p, sizeof(p));
   static bool attr_set = false;

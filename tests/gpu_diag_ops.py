@@ -216,6 +216,8 @@ CASES = {
     "conv_s2_big": lambda: case_conv(2, 64, 128, 64, 64, stride=2),
     "conv_cout4": lambda: case_conv(2, 16, 32, 64, 4),
     "attn_min": lambda: case_attn(1, 1, 128, 128),
+    "attn_q384": lambda: case_attn(2, 1, 384, 256),
+    "attn_k4": lambda: case_attn(1, 2, 256, 512),
     "attn_tiles": lambda: case_attn(2, 2, 512, 512),
     "attn_fused": lambda: case_attn(2, 5, 256, 256, fused_qkv=True),
     "attn_cross": lambda: case_attn(2, 2, 256, 77),
@@ -246,7 +248,7 @@ def main():
             continue
         t0 = time.time()
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", name], timeout=180,
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", name], timeout=int(os.environ.get("LR_CASE_TIMEOUT", "120")),
                                capture_output=True, text=True)
             out = (r.stdout + r.stderr).strip().splitlines()
             tail = [l for l in out if l.startswith(("PASS", "FAIL", "TIME", "lr_b200"))] or out[-6:]
