@@ -223,23 +223,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         m_used = m_new;
         l *= alpha;
       }
-      // P = exp2((s - m_used) * scale_log2) -> packed fp16 in registers (no shared-memory traffic yet, so this phase
-      // overlaps the previous PV MMA that is still reading P_t from smem)
-      const float moff = m_used * p.scale_log2;
-      float l0 = 0.f, l1 = 0.f;
-      uint32_t h[64];
-#pragma unroll
-      for (int c = 0; c < 128; c += 8) {
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) e[i] = fast_exp2(fmaf(__uint_as_float(s[c + i]), p.scale_log2, -moff));
-        l0 += (e[0] + e[1]) + (e[2] + e[3]);
-        l1 += (e[4] + e[5]) + (e[6] + e[7]);
-        h[(c >> 1) + 0] = pack_half2(e[0], e[1]);
-        h[(c >> 1) + 1] = pack_half2(e[2], e[3]);
-        h[(c >> 1) + 2] = pack_half2(e[4], e[5]);
-        h[(c >> 1) + 3] = pack_half2(e[6], e[7]);
-      }
       if (j > 0) {
         mbar_wait(&pv_done[t], (j - 1) & 1);  // PV(j-1) finished: P_t smem and O_t may be touched
         tc_fence_after();
@@ -257,12 +240,21 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
           tmem_st_wait();
         }
       }
-      // swizzled K-major smem tile: columns [c, c+8) = 16-byte chunk ((c & 63) >> 3) of atom (c >> 6), XOR row
+      // P = exp2((s - m_used) * scale_log2) -> fp16, swizzled K-major smem tile (stores interleave with the exps)
+      const float moff = m_used * p.scale_log2;
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 128; c += 8) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = fast_exp2(fmaf(__uint_as_float(s[c + i]), p.scale_log2, -moff));
+        l0 += (e[0] + e[1]) + (e[2] + e[3]);
+        l1 += (e[4] + e[5]) + (e[6] + e[7]);
+        const uint4 w = make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]),
+                                   pack_half2(e[6], e[7]));
+        // columns [c, c+8) = 16-byte chunk ((c & 63) >> 3) of atom (c >> 6), XOR-swizzled with the row
         const int ch = ((c & 63) >> 3) ^ (r & 7);
-        *reinterpret_cast<uint4*>(prow + (c >> 6) * kAttnTileBytes + ch * 16) =
-            make_uint4(h[(c >> 1)], h[(c >> 1) + 1], h[(c >> 1) + 2], h[(c >> 1) + 3]);
+        *reinterpret_cast<uint4*>(prow + (c >> 6) * kAttnTileBytes + ch * 16) = w;
       }
       l += l0 + l1;
       fence_proxy_async_smem();

@@ -61,7 +61,20 @@ __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __half* __
       ld = c1;
     }
     base += static_cast<size_t>(n) * P * ld;
-    for (int p = p_begin + rsub; p < p_end; p += rpi) {
+    int p = p_begin + rsub;
+    for (; p + 3 * rpi < p_end; p += 4 * rpi) {  // 4 independent 16-byte loads in flight per thread
+      float f0[8], f1[8], f2[8], f3[8];
+      load8(base + static_cast<size_t>(p) * ld, f0);
+      load8(base + static_cast<size_t>(p + rpi) * ld, f1);
+      load8(base + static_cast<size_t>(p + 2 * rpi) * ld, f2);
+      load8(base + static_cast<size_t>(p + 3 * rpi) * ld, f3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+        ss[j] += (f0[j] * f0[j] + f1[j] * f1[j]) + (f2[j] * f2[j] + f3[j] * f3[j]);
+      }
+    }
+    for (; p < p_end; p += rpi) {
       float f[8];
       load8(base + static_cast<size_t>(p) * ld, f);
 #pragma unroll
@@ -89,31 +102,14 @@ __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __half* __
   }
 }
 
-// stats -> per (n, channel) affine: y = x * scale + shift. Also re-zeroes nothing: stats are cleared by memset.
-__global__ void gn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, int C, int groups, int P, float eps,
-                                   float* __restrict__ scale, float* __restrict__ shift, int n_img) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_img * C) return;
-  const int n = i / C, c = i % C;
-  const int cpg = C / groups;
-  const int g = c / cpg;
-  const double cnt = static_cast<double>(P) * cpg;
-  const double mean = stats[(static_cast<size_t>(n) * groups + g) * 2] / cnt;
-  double var = stats[(static_cast<size_t>(n) * groups + g) * 2 + 1] / cnt - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  const float sc = rstd * gamma[c];
-  scale[i] = sc;
-  shift[i] = beta[c] - static_cast<float>(mean) * sc;
-}
-
 // y = [silu](x * scale + shift) -> out [n, P, C] fp16 (the concat is materialised only here, already normalised).
+// scale/shift are derived in-kernel from the fp64 (sum, sum of squares) statistics: one launch less per GroupNorm.
 __global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __half* __restrict__ x0, int c0,
                                                                 const __half* __restrict__ x1, int c1, int P,
-                                                                int chunk, const float* __restrict__ scale,
-                                                                const float* __restrict__ shift, int do_silu,
-                                                                __half* __restrict__ out) {
+                                                                int chunk, const double* __restrict__ stats,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, int groups, float eps,
+                                                                int do_silu, __half* __restrict__ out) {
   const int C = c0 + c1;
   const int nvec = C / 8;
   const int n = blockIdx.y;
@@ -124,11 +120,24 @@ __global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __half* __
   const int rsub = threadIdx.x / nvec;
   if (rsub >= rpi) return;
   const int ch = vec * 8;
+  const int cpg = C / groups;
+  const double cnt = static_cast<double>(P) * cpg;
   float sc[8], sh[8];
+  int g_prev = -1;
+  float mean_f = 0.f, rstd = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    sc[j] = scale[static_cast<size_t>(n) * C + ch + j];
-    sh[j] = shift[static_cast<size_t>(n) * C + ch + j];
+    const int g = (ch + j) / cpg;
+    if (g != g_prev) {
+      const double mean = stats[(static_cast<size_t>(n) * groups + g) * 2] / cnt;
+      double var = stats[(static_cast<size_t>(n) * groups + g) * 2 + 1] / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      mean_f = static_cast<float>(mean);
+      g_prev = g;
+    }
+    sc[j] = rstd * gamma[ch + j];
+    sh[j] = beta[ch + j] - mean_f * sc[j];
   }
   const __half* base;
   int ld;
@@ -141,12 +150,27 @@ __global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __half* __
   }
   base += static_cast<size_t>(n) * P * ld;
   __half* o = out + static_cast<size_t>(n) * P * C + ch;
-  for (int p = p_begin + rsub; p < p_end; p += rpi) {
+  int p = p_begin + rsub;
+  for (; p + 3 * rpi < p_end; p += 4 * rpi) {
+    float f[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load8(base + static_cast<size_t>(p + u * rpi) * ld, f[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y = f[u][j] * sc[j] + sh[j];
+        f[u][j] = do_silu ? silu_f(y) : y;
+      }
+      store8(o + static_cast<size_t>(p + u * rpi) * C, f[u]);
+    }
+  }
+  for (; p < p_end; p += rpi) {
     float f[8];
     load8(base + static_cast<size_t>(p) * ld, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float y = f[j] * sc[j] + sh[j];
+      const float y = f[j] * sc[j] + sh[j];
       f[j] = do_silu ? silu_f(y) : y;
     }
     store8(o + static_cast<size_t>(p) * C, f);
@@ -202,11 +226,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
     const int vi = lane + v * 32;
     if (vi < nvec) {
       float y[8];
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + vi * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + vi * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + vi * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(beta + vi * 8 + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = vi * 8 + j;
-        y[j] = (f[v][j] - mean) * rstd * gamma[c] + beta[c];
-      }
+      for (int j = 0; j < 8; ++j) y[j] = (f[v][j] - mean) * rstd * gg[j] + bb[j];
       store8(out + static_cast<size_t>(row) * C + vi * 8, y);
     }
   }
@@ -311,42 +338,62 @@ __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, int n_i
 // One warp per output feature; handles up to kMaxSmallBatch batch rows per pass.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kMaxSmallBatch = 8;
+constexpr int kSmallOutPerWarp = 4;
+// dynamic smem: min(n_rows, 8) * K floats (the activation block, SiLU already applied when silu_in)
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in, int ld_in, int n_rows, int K,
                                                            const __half* __restrict__ w,
                                                            const float* __restrict__ bias, int n_out, int silu_in,
                                                            int silu_out, float* __restrict__ out, int ld_out) {
-  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (o >= n_out) return;
+  extern __shared__ float act[];  // [rows][K]
   const int lane = threadIdx.x & 31;
+  const int o0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kSmallOutPerWarp;
   for (int r0 = 0; r0 < n_rows; r0 += kMaxSmallBatch) {
-    float acc[kMaxSmallBatch];
+    const int rows = min(kMaxSmallBatch, n_rows - r0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * K; i += blockDim.x) {
+      float a = in[static_cast<size_t>(r0 + i / K) * ld_in + (i % K)];
+      act[i] = silu_in ? silu_f(a) : a;
+    }
+    __syncthreads();
+    if (o0 < n_out) {
+      float acc[kSmallOutPerWarp][kMaxSmallBatch];
 #pragma unroll
-    for (int r = 0; r < kMaxSmallBatch; ++r) acc[r] = 0.f;
-    for (int k = lane * 8; k < K; k += 32 * 8) {
-      float wv[8];
-      load8(w + static_cast<size_t>(o) * K + k, wv);
+      for (int u = 0; u < kSmallOutPerWarp; ++u)
 #pragma unroll
-      for (int r = 0; r < kMaxSmallBatch; ++r) {
-        if (r0 + r < n_rows) {
-          const float* ip = in + static_cast<size_t>(r0 + r) * ld_in + k;
+        for (int r = 0; r < kMaxSmallBatch; ++r) acc[u][r] = 0.f;
+      for (int k = lane * 8; k < K; k += 32 * 8) {
+        float wv[kSmallOutPerWarp][8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float a = ip[j];
-            if (silu_in) a = silu_f(a);
-            acc[r] += a * wv[j];
+        for (int u = 0; u < kSmallOutPerWarp; ++u) {
+          const int o = min(o0 + u, n_out - 1);
+          load8(w + static_cast<size_t>(o) * K + k, wv[u]);
+        }
+#pragma unroll
+        for (int r = 0; r < kMaxSmallBatch; ++r) {
+          if (r < rows) {
+            const float4 a0 = *reinterpret_cast<const float4*>(act + r * K + k);
+            const float4 a1 = *reinterpret_cast<const float4*>(act + r * K + k + 4);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int u = 0; u < kSmallOutPerWarp; ++u)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[u][r] += av[j] * wv[u][j];
           }
         }
       }
-    }
 #pragma unroll
-    for (int r = 0; r < kMaxSmallBatch; ++r) {
-      float a = acc[r];
+      for (int u = 0; u < kSmallOutPerWarp; ++u) {
 #pragma unroll
-      for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-      if (lane == 0 && r0 + r < n_rows) {
-        a += bias ? bias[o] : 0.f;
-        if (silu_out) a = silu_f(a);
-        out[static_cast<size_t>(r0 + r) * ld_out + o] = a;
+        for (int r = 0; r < kMaxSmallBatch; ++r) {
+          float a = acc[u][r];
+#pragma unroll
+          for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+          if (lane == 0 && r < rows && o0 + u < n_out) {
+            a += bias ? bias[o0 + u] : 0.f;
+            if (silu_out) a = silu_f(a);
+            out[static_cast<size_t>(r0 + r) * ld_out + o0 + u] = a;
+          }
+        }
       }
     }
   }

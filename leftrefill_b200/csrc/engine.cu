@@ -26,13 +26,14 @@ struct Weight {
   int dst_row0 = 0;  // row offset inside a fused matrix (QKV / KV)
   int ld = 0;        // row length (elements) of the destination matrix
   bool loaded = false;
+  int region = 0;    // 0: off is final; 1 / 2: off is relative to the contiguous emb_layers weight / bias block
 };
 
 struct ResW {
   int cin = 0, cout = 0;
   size_t gn1_g, gn1_b, conv1_w, conv1_b, emb_w, emb_b, gn2_g, gn2_b, conv2_w, conv2_b, skip_w, skip_b;
   bool has_skip = false;
-  int emb_slot = 0;
+  int emb_col0 = 0;  // column offset of this block's emb_layers output inside the batched [n, emb_total] buffer
 };
 struct TBlockW {
   size_t ln1_g, ln1_b, qkv_w, out1_w, out1_b;
@@ -117,6 +118,9 @@ struct lr_unet {
   size_t te0_w, te0_b, te2_w, te2_b, head_gn_g, head_gn_b;
   int conv_in_idx = 0, head_idx = 0, kpad_in = 0;
   int n_kv_slots = 0;
+  int emb_total = 0;            // sum of ResBlock out_channels
+  size_t emb_w_base = 0, emb_b_base = 0;
+  int n_gn_sites = 0;
 
   // ---- plan state ----
   int pn = 0, ph = 0, pw = 0;  // planned shape
@@ -200,8 +204,13 @@ struct lr_unet {
     r.gn1_b = reg_vec(pfx + "in_layers.0.bias", cin);
     r.conv1_w = reg_conv3(pfx + "in_layers.2.weight", cout, cin, 9 * cin);
     r.conv1_b = reg_vec(pfx + "in_layers.2.bias", cout);
-    r.emb_w = reg_linear(pfx + "emb_layers.1.weight", cout, temb);
-    r.emb_b = reg_vec(pfx + "emb_layers.1.bias", cout);
+    // all emb_layers (openaimodel.py:217-223) live in one contiguous [emb_total, temb] matrix: one launch per forward
+    r.emb_col0 = emb_total;
+    r.emb_w = reg(pfx + "emb_layers.1.weight", {cout, temb}, K_LINEAR, static_cast<size_t>(emb_total) * temb, 0, temb);
+    weights.back().region = 1;
+    r.emb_b = reg(pfx + "emb_layers.1.bias", {cout}, K_VEC, static_cast<size_t>(emb_total), 0, 0);
+    weights.back().region = 2;
+    emb_total += cout;
     r.gn2_g = reg_vec(pfx + "out_layers.0.weight", cout);
     r.gn2_b = reg_vec(pfx + "out_layers.0.bias", cout);
     r.conv2_w = reg_conv3(pfx + "out_layers.3.weight", cout, cout, 9 * cout);
@@ -213,7 +222,6 @@ struct lr_unet {
                      halloc(static_cast<size_t>(cout) * cin), 0, cin);
       r.skip_b = reg_vec(pfx + "skip_connection.bias", cout);
     }
-    r.emb_slot = static_cast<int>(res.size());
     res.push_back(r);
     return static_cast<int>(res.size()) - 1;
   }
@@ -351,6 +359,12 @@ struct lr_unet {
     head_gn_b = reg_vec("out.0.bias", ch);
     LR_CHECK(ch == mc, "head channel mismatch");
     head_idx = add_conv("out.2.", mc, cfg.out_channels, 9 * mc);
+    emb_w_base = halloc(static_cast<size_t>(emb_total) * temb);
+    emb_b_base = falloc(emb_total);
+    for (Weight& w : weights) {
+      if (w.region == 1) w.off += emb_w_base;
+      if (w.region == 2) w.off += emb_b_base;
+    }
     return 0;
   }
 
@@ -416,16 +430,15 @@ struct lr_unet {
     s.geglu = geglu;
     return add_conv_step(s);
   }
-  // scratch for GroupNorm
+  // GroupNorm statistics: one (sum, sumsq) slot per call site, all zeroed by a single memset at the start of forward
   double* gn_stats = nullptr;
-  float* gn_scale = nullptr;
-  float* gn_shift = nullptr;
+  int gn_sites_planned = 0, gn_sites_cap = 0;
   int add_gn(const __half* x0, int c0, const __half* x1, int c1, int n, int P, float eps, const float* g,
              const float* b, int silu, __half* out) {
-    double* st_ = gn_stats;
-    float *sc = gn_scale, *sh = gn_shift;
+    LR_CHECK(gn_sites_planned < gn_sites_cap, "internal: GroupNorm statistics arena too small");
+    double* st_ = gn_stats + static_cast<size_t>(gn_sites_planned++) * n * 32 * 2;
     push([=](cudaStream_t st) {
-      return launch_groupnorm(x0, c0, x1, c1, n, P, 32, eps, g, b, silu, st_, sc, sh, out, st);
+      return launch_groupnorm(x0, c0, x1, c1, n, P, 32, eps, g, b, silu, st_, 1, out, st);
     }, 2, 0.0, "groupnorm n=" + std::to_string(n) + " P=" + std::to_string(P) + " c=" + std::to_string(c0) + "+" +
                    std::to_string(c1));
     return 0;
@@ -447,7 +460,7 @@ struct lr_unet {
     return 0;
   }
 
-  std::vector<float*> emb_out;  // per ResBlock [n, cout]
+  float* emb_all = nullptr;  // [n, emb_total]: every ResBlock's emb_layers output
 
   // ResBlock._forward (openaimodel.py:254-274), x = concat(x0, x1) when x1.p != nullptr
   int plan_res(const ResW& r, Act x0, Act x1, int n, Act* out) {
@@ -471,7 +484,8 @@ struct lr_unet {
       s.ldw = 9 * r.cin;
       s.ncols = r.cout;
       s.bias = F(r.conv1_b);
-      s.bias_img = emb_out[r.emb_slot];
+      s.bias_img = emb_all + r.emb_col0;
+      s.ld_bias_img = emb_total;
       s.out = h;
       s.ld_out = r.cout;
       LR_TRY(add_conv_step(s));
@@ -719,24 +733,32 @@ struct lr_unet {
     conv_ops.clear();
     attn_ops.clear();
     pool.clear();
-    emb_out.clear();
     flops = 0;
     pn = 0;
     const int mc = cfg.model_channels, temb = 4 * mc;
-    int maxC = 0;
-    for (const ResW& r : res) maxC = std::max(maxC, std::max(r.cin, r.cout));
     {
+      gn_sites_cap = 2 * static_cast<int>(res.size()) + static_cast<int>(sts.size()) + 1;
+      gn_sites_planned = 0;
+      const size_t bytes = sizeof(double) * gn_sites_cap * n * 32 * 2;
       void* p;
-      LR_TRY(pool.acquire(sizeof(double) * n * 32 * 2, &p));
+      LR_TRY(pool.acquire(bytes, &p));
       gn_stats = static_cast<double*>(p);
+      double* gs = gn_stats;
+      push([=](cudaStream_t st) {
+        cudaError_t e = cudaMemsetAsync(gs, 0, bytes, st);
+        if (e != cudaSuccess) {
+          set_error(std::string("cudaMemsetAsync(gn stats): ") + cudaGetErrorString(e));
+          return 1;
+        }
+        return 0;
+      });
     }
-    LR_TRY(acquire_f(static_cast<size_t>(n) * maxC, &gn_scale));
-    LR_TRY(acquire_f(static_cast<size_t>(n) * maxC, &gn_shift));
-    // --- timestep path (openaimodel.py:768-769 + every ResBlock's emb_layers, :263) ---
+    // --- timestep path (openaimodel.py:768-769 + every ResBlock's emb_layers, :263): 4 launches per forward ---
     float *tsin, *e1, *emb;
     LR_TRY(acquire_f(static_cast<size_t>(n) * mc, &tsin));
     LR_TRY(acquire_f(static_cast<size_t>(n) * temb, &e1));
     LR_TRY(acquire_f(static_cast<size_t>(n) * temb, &emb));
+    LR_TRY(acquire_f(static_cast<size_t>(n) * emb_total, &emb_all));
     push([=](cudaStream_t st) {
       return launch_timestep_embedding(reinterpret_cast<const long long*>(this->in_t), n, mc, tsin, st);
     });
@@ -745,20 +767,13 @@ struct lr_unet {
       const float* b0 = F(te0_b);
       const __half* w2 = H(te2_w);
       const float* b2 = F(te2_b);
-      push(
-          [=](cudaStream_t st) { return launch_small_linear(tsin, mc, n, mc, w0, b0, temb, 0, 1, e1, temb, st); });
-      push(
-          [=](cudaStream_t st) { return launch_small_linear(e1, temb, n, temb, w2, b2, temb, 0, 0, emb, temb, st); });
-    }
-    for (const ResW& r : res) {
-      float* eo;
-      LR_TRY(acquire_f(static_cast<size_t>(n) * r.cout, &eo));
-      emb_out.push_back(eo);
-      const __half* w = H(r.emb_w);
-      const float* b = F(r.emb_b);
-      const int co = r.cout;
-      push(
-          [=](cudaStream_t st) { return launch_small_linear(emb, temb, n, temb, w, b, co, 1, 0, eo, co, st); });
+      const __half* wa = H(emb_w_base);
+      const float* ba = F(emb_b_base);
+      float* ea = emb_all;
+      const int et = emb_total;
+      push([=](cudaStream_t st) { return launch_small_linear(tsin, mc, n, mc, w0, b0, temb, 0, 1, e1, temb, st); });
+      push([=](cudaStream_t st) { return launch_small_linear(e1, temb, n, temb, w2, b2, temb, 0, 0, emb, temb, st); });
+      push([=](cudaStream_t st) { return launch_small_linear(emb, temb, n, temb, wa, ba, et, 1, 0, ea, et, st); });
     }
     // --- input conv: im2col of the NCHW fp32 boundary tensor, then a GEMM ---
     const size_t M0 = static_cast<size_t>(n) * Hh * Ww;
@@ -1088,12 +1103,9 @@ int lr_groupnorm_f16(const void* x0, int c0, const void* x1, int c1, int n, int 
                      const float* gamma, const float* beta, int silu, void* out, void* scratch, void* stream) {
   LR_CHECK(x0 && gamma && beta && out && scratch, "lr_groupnorm_f16: null argument");
   if (n == 0 || P == 0) return 0;
-  const int C = c0 + (x1 ? c1 : 0);
   double* stats = static_cast<double*>(scratch);
-  float* scale = reinterpret_cast<float*>(stats + static_cast<size_t>(n) * groups * 2);
-  float* shift = scale + static_cast<size_t>(n) * C;
   return launch_groupnorm(static_cast<const __half*>(x0), c0, static_cast<const __half*>(x1), x1 ? c1 : 0, n, P, groups,
-                          eps, gamma, beta, silu, stats, scale, shift, static_cast<__half*>(out),
+                          eps, gamma, beta, silu, stats, 0, static_cast<__half*>(out),
                           static_cast<cudaStream_t>(stream));
 }
 int lr_layernorm_f16(const void* x, int M, int C, const float* gamma, const float* beta, float eps, void* out,

@@ -36,7 +36,8 @@ struct GemmParams {
   int block_n;       // UMMA N (multiple of 32, <= 256)
   int stages;        // smem ring depth
   const float* bias;       // [ncols] or nullptr
-  const float* bias_img;   // [n_img, ncols] or nullptr (ResBlock emb_layers output, openaimodel.py:263-272)
+  const float* bias_img;   // [n_img, ld_bias_img] or nullptr (ResBlock emb_layers output, openaimodel.py:263-272)
+  int ld_bias_img;
   const __half* residual;  // [M, ld_res] or nullptr, added after bias
   int ld_res;
   __half* out;             // [M, ld_out]
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
             f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
           }
           if (p.bias_img != nullptr) {
-            const float* bi = p.bias_img + static_cast<size_t>(n) * p.ncols + col0;
+            const float* bi = p.bias_img + static_cast<size_t>(n) * p.ld_bias_img + col0;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.ncols) f[j] += __ldg(bi + j);

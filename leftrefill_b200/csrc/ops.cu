@@ -153,6 +153,7 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   p.stages = stages;
   p.bias = s.bias;
   p.bias_img = s.bias_img;
+  p.ld_bias_img = s.ld_bias_img > 0 ? s.ld_bias_img : s.ncols;
   p.residual = s.residual;
   p.ld_res = s.ld_res;
   p.out = s.out;
@@ -265,7 +266,7 @@ int launch_attn_op(const AttnOp& op, cudaStream_t st) {
 // normalisation / elementwise
 // ------------------------------------------------------------------------------------------------------------
 int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_img, int P, int groups, float eps,
-                     const float* gamma, const float* beta, int do_silu, double* stats, float* scale, float* shift,
+                     const float* gamma, const float* beta, int do_silu, double* stats, int stats_are_zero,
                      __half* out, cudaStream_t st) {
   const int C = c0 + c1;
   LR_CHECK(c0 % 8 == 0 && c1 % 8 == 0, "groupnorm: channels must be multiples of 8");
@@ -276,12 +277,11 @@ int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_i
   if (chunk < 16) chunk = 16;
   if (chunk > 256) chunk = 256;
   const dim3 grid(cdiv(P, chunk), n_img);
-  LR_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * n_img * groups * 2, st));
+  if (!stats_are_zero) LR_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * n_img * groups * 2, st));
   gn_stats_kernel<<<grid, kNormThreads, 2 * C * sizeof(float), st>>>(x0, c0, x1, c1, P, chunk, groups, stats);
   LR_LAUNCHED();
-  gn_finalize_kernel<<<cdiv(n_img * C, 256), 256, 0, st>>>(stats, gamma, beta, C, groups, P, eps, scale, shift, n_img);
-  LR_LAUNCHED();
-  gn_apply_kernel<<<grid, kNormThreads, 0, st>>>(x0, c0, x1, c1, P, chunk, scale, shift, do_silu, out);
+  gn_apply_kernel<<<grid, kNormThreads, 0, st>>>(x0, c0, x1, c1, P, chunk, stats, gamma, beta, groups, eps, do_silu,
+                                                 out);
   LR_LAUNCHED();
   return 0;
 }
@@ -340,8 +340,11 @@ int launch_nchw_f32_to_nhwc(const float* x, int n_img, int C, int H, int W, __ha
 int launch_small_linear(const float* in, int ld_in, int n_rows, int K, const __half* w, const float* bias, int n_out,
                         int silu_in, int silu_out, float* out, int ld_out, cudaStream_t st) {
   LR_CHECK(K % 8 == 0, "small_linear: K must be a multiple of 8");
-  small_linear_kernel<<<cdiv(n_out, 8), 256, 0, st>>>(in, ld_in, n_rows, K, w, bias, n_out, silu_in, silu_out, out,
-                                                      ld_out);
+  const int rows = n_rows < kMaxSmallBatch ? n_rows : kMaxSmallBatch;
+  const size_t smem = static_cast<size_t>(rows) * K * sizeof(float);
+  LR_CHECK(smem <= 48 * 1024, "small_linear: K too large for the activation staging buffer");
+  small_linear_kernel<<<cdiv(n_out, 8 * kSmallOutPerWarp), 256, smem, st>>>(in, ld_in, n_rows, K, w, bias, n_out,
+                                                                             silu_in, silu_out, out, ld_out);
   LR_LAUNCHED();
   return 0;
 }

@@ -46,7 +46,8 @@ struct ConvSpec {
   int ldw = 0;
   int ncols = 0;
   const float* bias = nullptr;
-  const float* bias_img = nullptr;
+  const float* bias_img = nullptr;  // [n_img, ld_bias_img] per-image additive bias (0 -> ld = ncols)
+  int ld_bias_img = 0;
   const __half* residual = nullptr;
   int ld_res = 0;
   __half* out = nullptr;
@@ -82,10 +83,10 @@ int build_attn_op(AttnOp* op, const AttnSpec& s);
 int launch_attn_op(const AttnOp& op, cudaStream_t st);
 
 // ---- normalisation / elementwise launchers ----
-// GroupNorm over concat(x0[c0], x1[c1]) -> out [n, P, c0+c1]; stats/scale/shift are caller-provided scratch:
-// stats: double[n*groups*2], scale/shift: float[n*(c0+c1)]
+// GroupNorm over concat(x0[c0], x1[c1]) -> out [n, P, c0+c1]; stats: caller-provided double[n*groups*2] scratch
+// (zeroed here unless the caller guarantees stats_are_zero).
 int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_img, int P, int groups, float eps,
-                     const float* gamma, const float* beta, int do_silu, double* stats, float* scale, float* shift,
+                     const float* gamma, const float* beta, int do_silu, double* stats, int stats_are_zero,
                      __half* out, cudaStream_t st);
 int launch_layernorm(const __half* x, int M, int C, const float* gamma, const float* beta, float eps, __half* out,
                      cudaStream_t st);
