@@ -26,23 +26,34 @@ __device__ __forceinline__ void store8(__half* p, const float (&f)[8]) {
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 // ------------------------------------------------------------------------------------------------------------
-// GroupNorm statistics (reference: GroupNorm32, ldm/modules/diffusionmodules/util.py:217-219, fp32 math;
-// Normalize, ldm/modules/attention.py:90-91). Sources x0 [n, P, c0] and x1 [n, P, c1] form the channel concat.
-// Each thread owns one 8-channel vector column and walks pixels; per-channel partials are folded to groups in
-// shared memory and accumulated across CTAs in fp64 (sum, sum of squares) -> stats[n][group][2].
-// grid = (pixel chunks, n); block = kNormThreads.
+// GroupNorm (reference: GroupNorm32, ldm/modules/diffusionmodules/util.py:217-219, fp32 math; Normalize,
+// ldm/modules/attention.py:90-91). Sources x0 [n, P, c0] and x1 [n, P, c1] form the channel concat.
+//
+// Statistics: each thread owns one 8-channel vector column and walks pixels (4 loads in flight); the CTA reduces its
+// partials in a FIXED order in shared memory (bit-reproducible), folds channels to groups in fp64 and adds one
+// (sum, sum of squares) pair per group to the per-site scratch with fp64 atomics. The last CTA of an image (ticket
+// counter) turns the sums into (mean, rstd) floats, so the apply kernel needs no fp64 and no extra launch.
+// Scratch layout per call site (zeroed by the caller): double sums[n][G][2]; float2 mr[n][G]; unsigned ticket[n].
+// grid = (pixel chunks, n); block = kNormThreads; dynamic smem = rpi * 2 * C floats.
 // ------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t gn_scratch_bytes(int n, int groups) {
+  return static_cast<size_t>(n) * groups * (2 * sizeof(double) + sizeof(float2)) + static_cast<size_t>(n) * 8;
+}
+
 __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __half* __restrict__ x0, int c0,
                                                                 const __half* __restrict__ x1, int c1, int P,
-                                                                int chunk, int groups, double* __restrict__ stats) {
-  extern __shared__ float sm[];  // [2][C]
+                                                                int chunk, int groups, float eps,
+                                                                unsigned char* __restrict__ scratch) {
+  extern __shared__ float sm[];  // [rpi][2][C]
   const int C = c0 + c1;
   const int nvec = C / 8;
   const int n = blockIdx.y;
+  const int n_img = gridDim.y;
+  double* sums = reinterpret_cast<double*>(scratch);
+  float2* mr = reinterpret_cast<float2*>(sums + static_cast<size_t>(n_img) * groups * 2);
+  unsigned* ticket = reinterpret_cast<unsigned*>(mr + static_cast<size_t>(n_img) * groups);
   const int p_begin = blockIdx.x * chunk;
   const int p_end = min(P, p_begin + chunk);
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   const int rpi = blockDim.x / nvec;  // pixel rows handled per sweep
   const int vec = threadIdx.x % nvec;
   const int rsub = threadIdx.x / nvec;
@@ -83,11 +94,18 @@ __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __half* __
         ss[j] += f[j] * f[j];
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sm[ch + j], s[j]);
-      atomicAdd(&sm[C + ch + j], ss[j]);
-    }
+    float* dst = sm + static_cast<size_t>(rsub) * 2 * C + ch;
+    *reinterpret_cast<float4*>(dst) = make_float4(s[0], s[1], s[2], s[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(s[4], s[5], s[6], s[7]);
+    *reinterpret_cast<float4*>(dst + C) = make_float4(ss[0], ss[1], ss[2], ss[3]);
+    *reinterpret_cast<float4*>(dst + C + 4) = make_float4(ss[4], ss[5], ss[6], ss[7]);
+  }
+  __syncthreads();
+  // fixed-order reduction over the rpi row-slices, in place into slice 0
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float a = sm[i];
+    for (int rr = 1; rr < rpi; ++rr) a += sm[static_cast<size_t>(rr) * 2 * C + i];
+    sm[i] = a;
   }
   __syncthreads();
   const int cpg = C / groups;
@@ -97,22 +115,44 @@ __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __half* __
       a += static_cast<double>(sm[g * cpg + j]);
       b += static_cast<double>(sm[C + g * cpg + j]);
     }
-    atomicAdd(&stats[(static_cast<size_t>(n) * groups + g) * 2 + 0], a);
-    atomicAdd(&stats[(static_cast<size_t>(n) * groups + g) * 2 + 1], b);
+    atomicAdd(&sums[(static_cast<size_t>(n) * groups + g) * 2 + 0], a);
+    atomicAdd(&sums[(static_cast<size_t>(n) * groups + g) * 2 + 1], b);
+  }
+  // last CTA of this image finalises (mean, rstd)
+  __shared__ unsigned s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&ticket[n], 1u);
+  __syncthreads();
+  if (s_ticket == gridDim.x - 1) {
+    __threadfence();
+    const double cnt = static_cast<double>(P) * cpg;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      const double sum = __ldcg(&sums[(static_cast<size_t>(n) * groups + g) * 2 + 0]);
+      const double sq = __ldcg(&sums[(static_cast<size_t>(n) * groups + g) * 2 + 1]);
+      const double mean = sum / cnt;
+      double var = sq / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      mr[static_cast<size_t>(n) * groups + g] =
+          make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+    }
   }
 }
 
-// y = [silu](x * scale + shift) -> out [n, P, C] fp16 (the concat is materialised only here, already normalised).
-// scale/shift are derived in-kernel from the fp64 (sum, sum of squares) statistics: one launch less per GroupNorm.
+// y = [silu]((x - mean) * rstd * gamma + beta) -> out [n, P, C] fp16 (the concat is materialised only here, already
+// normalised).
 __global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __half* __restrict__ x0, int c0,
                                                                 const __half* __restrict__ x1, int c1, int P,
-                                                                int chunk, const double* __restrict__ stats,
+                                                                int chunk, const unsigned char* __restrict__ scratch,
                                                                 const float* __restrict__ gamma,
-                                                                const float* __restrict__ beta, int groups, float eps,
+                                                                const float* __restrict__ beta, int groups,
                                                                 int do_silu, __half* __restrict__ out) {
   const int C = c0 + c1;
   const int nvec = C / 8;
   const int n = blockIdx.y;
+  const int n_img = gridDim.y;
+  const float2* mr = reinterpret_cast<const float2*>(reinterpret_cast<const double*>(scratch) +
+                                                     static_cast<size_t>(n_img) * groups * 2);
   const int p_begin = blockIdx.x * chunk;
   const int p_end = min(P, p_begin + chunk);
   const int rpi = blockDim.x / nvec;
@@ -121,23 +161,12 @@ __global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __half* __
   if (rsub >= rpi) return;
   const int ch = vec * 8;
   const int cpg = C / groups;
-  const double cnt = static_cast<double>(P) * cpg;
   float sc[8], sh[8];
-  int g_prev = -1;
-  float mean_f = 0.f, rstd = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int g = (ch + j) / cpg;
-    if (g != g_prev) {
-      const double mean = stats[(static_cast<size_t>(n) * groups + g) * 2] / cnt;
-      double var = stats[(static_cast<size_t>(n) * groups + g) * 2 + 1] / cnt - mean * mean;
-      if (var < 0.0) var = 0.0;
-      rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-      mean_f = static_cast<float>(mean);
-      g_prev = g;
-    }
-    sc[j] = rstd * gamma[ch + j];
-    sh[j] = beta[ch + j] - mean_f * sc[j];
+    const float2 m = mr[static_cast<size_t>(n) * groups + (ch + j) / cpg];
+    sc[j] = m.y * gamma[ch + j];
+    sh[j] = beta[ch + j] - m.x * sc[j];
   }
   const __half* base;
   int ld;

@@ -431,12 +431,13 @@ struct lr_unet {
     return add_conv_step(s);
   }
   // GroupNorm statistics: one (sum, sumsq) slot per call site, all zeroed by a single memset at the start of forward
-  double* gn_stats = nullptr;
+  unsigned char* gn_stats = nullptr;
+  size_t gn_site_bytes = 0;
   int gn_sites_planned = 0, gn_sites_cap = 0;
   int add_gn(const __half* x0, int c0, const __half* x1, int c1, int n, int P, float eps, const float* g,
              const float* b, int silu, __half* out) {
     LR_CHECK(gn_sites_planned < gn_sites_cap, "internal: GroupNorm statistics arena too small");
-    double* st_ = gn_stats + static_cast<size_t>(gn_sites_planned++) * n * 32 * 2;
+    unsigned char* st_ = gn_stats + static_cast<size_t>(gn_sites_planned++) * gn_site_bytes;
     push([=](cudaStream_t st) {
       return launch_groupnorm(x0, c0, x1, c1, n, P, 32, eps, g, b, silu, st_, 1, out, st);
     }, 2, 0.0, "groupnorm n=" + std::to_string(n) + " P=" + std::to_string(P) + " c=" + std::to_string(c0) + "+" +
@@ -739,11 +740,12 @@ struct lr_unet {
     {
       gn_sites_cap = 2 * static_cast<int>(res.size()) + static_cast<int>(sts.size()) + 1;
       gn_sites_planned = 0;
-      const size_t bytes = sizeof(double) * gn_sites_cap * n * 32 * 2;
+      gn_site_bytes = groupnorm_scratch_bytes(n, 32);
+      const size_t bytes = gn_site_bytes * gn_sites_cap;
       void* p;
       LR_TRY(pool.acquire(bytes, &p));
-      gn_stats = static_cast<double*>(p);
-      double* gs = gn_stats;
+      gn_stats = static_cast<unsigned char*>(p);
+      unsigned char* gs = gn_stats;
       push([=](cudaStream_t st) {
         cudaError_t e = cudaMemsetAsync(gs, 0, bytes, st);
         if (e != cudaSuccess) {
@@ -1103,9 +1105,8 @@ int lr_groupnorm_f16(const void* x0, int c0, const void* x1, int c1, int n, int 
                      const float* gamma, const float* beta, int silu, void* out, void* scratch, void* stream) {
   LR_CHECK(x0 && gamma && beta && out && scratch, "lr_groupnorm_f16: null argument");
   if (n == 0 || P == 0) return 0;
-  double* stats = static_cast<double*>(scratch);
   return launch_groupnorm(static_cast<const __half*>(x0), c0, static_cast<const __half*>(x1), x1 ? c1 : 0, n, P, groups,
-                          eps, gamma, beta, silu, stats, 0, static_cast<__half*>(out),
+                          eps, gamma, beta, silu, scratch, 0, static_cast<__half*>(out),
                           static_cast<cudaStream_t>(stream));
 }
 int lr_layernorm_f16(const void* x, int M, int C, const float* gamma, const float* beta, float eps, void* out,

@@ -265,8 +265,10 @@ int launch_attn_op(const AttnOp& op, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------------------
 // normalisation / elementwise
 // ------------------------------------------------------------------------------------------------------------
+size_t groupnorm_scratch_bytes(int n_img, int groups) { return (gn_scratch_bytes(n_img, groups) + 255) & ~size_t(255); }
+
 int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_img, int P, int groups, float eps,
-                     const float* gamma, const float* beta, int do_silu, double* stats, int stats_are_zero,
+                     const float* gamma, const float* beta, int do_silu, void* scratch, int scratch_is_zero,
                      __half* out, cudaStream_t st) {
   const int C = c0 + c1;
   LR_CHECK(c0 % 8 == 0 && c1 % 8 == 0, "groupnorm: channels must be multiples of 8");
@@ -277,11 +279,14 @@ int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_i
   if (chunk < 16) chunk = 16;
   if (chunk > 256) chunk = 256;
   const dim3 grid(cdiv(P, chunk), n_img);
-  if (!stats_are_zero) LR_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * n_img * groups * 2, st));
-  gn_stats_kernel<<<grid, kNormThreads, 2 * C * sizeof(float), st>>>(x0, c0, x1, c1, P, chunk, groups, stats);
+  if (!scratch_is_zero) LR_CUDA(cudaMemsetAsync(scratch, 0, gn_scratch_bytes(n_img, groups), st));
+  const int rpi = kNormThreads / (C / 8);
+  const size_t smem = static_cast<size_t>(rpi) * 2 * C * sizeof(float);
+  gn_stats_kernel<<<grid, kNormThreads, smem, st>>>(x0, c0, x1, c1, P, chunk, groups, eps,
+                                                    static_cast<unsigned char*>(scratch));
   LR_LAUNCHED();
-  gn_apply_kernel<<<grid, kNormThreads, 0, st>>>(x0, c0, x1, c1, P, chunk, stats, gamma, beta, groups, eps, do_silu,
-                                                 out);
+  gn_apply_kernel<<<grid, kNormThreads, 0, st>>>(x0, c0, x1, c1, P, chunk, static_cast<const unsigned char*>(scratch),
+                                                 gamma, beta, groups, do_silu, out);
   LR_LAUNCHED();
   return 0;
 }

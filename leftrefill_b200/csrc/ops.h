@@ -83,10 +83,11 @@ int build_attn_op(AttnOp* op, const AttnSpec& s);
 int launch_attn_op(const AttnOp& op, cudaStream_t st);
 
 // ---- normalisation / elementwise launchers ----
-// GroupNorm over concat(x0[c0], x1[c1]) -> out [n, P, c0+c1]; stats: caller-provided double[n*groups*2] scratch
-// (zeroed here unless the caller guarantees stats_are_zero).
+// GroupNorm over concat(x0[c0], x1[c1]) -> out [n, P, c0+c1]; scratch: groupnorm_scratch_bytes(n, groups) bytes
+// (zeroed here unless the caller guarantees scratch_is_zero).
+size_t groupnorm_scratch_bytes(int n_img, int groups);
 int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_img, int P, int groups, float eps,
-                     const float* gamma, const float* beta, int do_silu, double* stats, int stats_are_zero,
+                     const float* gamma, const float* beta, int do_silu, void* scratch, int scratch_is_zero,
                      __half* out, cudaStream_t st);
 int launch_layernorm(const __half* x, int M, int C, const float* gamma, const float* beta, float eps, __half* out,
                      cudaStream_t st);

@@ -154,7 +154,7 @@ def test_sampler_generic_path_equals_fast_path(small):
                                                         context=torch.cat(c["c_crossattn"], 1))
         torch.manual_seed(123)
         s = lr.DDIMSampler(ldm)
-        y, _ = s.sample(3, 2, (4, 16, 32), cond, eta=1.0, verbose=False, unconditional_guidance_scale=2.5,
+        y, _ = s.sample(4, 2, (4, 16, 32), cond, eta=1.0, verbose=False, unconditional_guidance_scale=2.5,
                         unconditional_conditioning=ucond)
         outs.append((y, torch.rand(1, device=dev)))
     assert torch.allclose(outs[0][0], outs[1][0], rtol=2e-3, atol=2e-3)
