@@ -92,7 +92,9 @@ int lr_ddim_update(const float* x, const float* eps_uncond, const float* eps_con
 /* ---- op-level entry points (what CrossAttention / ResBlock / SpatialTransformer mirrors call stand-alone) ------
  * Activations are NHWC fp16: row = (n*H + y)*W + x, channels contiguous. */
 
-/* out[M, n_out] = A[M, K] * W[n_out(*2 if geglu), K]^T (+bias) (+residual) ; geglu: W/bias rows interleaved
+/* force_block_n (testing hook, 0 = heuristic): 1000*cg + block_n with cg in {0: heuristic, 1: single CTA, 2: CTA pair
+ * (tcgen05 cta_group::2)} and block_n a multiple of 32 (0 = heuristic).
+ * out[M, n_out] = A[M, K] * W[n_out(*2 if geglu), K]^T (+bias) (+residual) ; geglu: W/bias rows interleaved
  * (value_j, gate_j) and out[:, j] = v_j * gelu(g_j) (attention.py:51-58). fp16 in/out, fp32 accumulate. */
 int lr_linear_f16(const void* a, int lda, int M, int K, const void* w, int ldw, int n_cols, const float* bias,
                   const void* residual, int ld_res, void* out, int ld_out, int geglu, int force_block_n, void* stream);

@@ -5,14 +5,15 @@
 //
 // One CTA = one (batch, head, 256-query block) = two 128-row query tiles that ping-pong on the tensor core. d_head = 64.
 //   warp 0 (1 lane)   : TMA — Q0/Q1 once, then a 3-stage ring of {K_j, V_j} 128-token tiles shared by both query tiles
-//   warp 1 (1 lane)   : tcgen05.mma — S_t = Q_t K_j^T (128x128 fp32, TMEM), O_t += P_t V_j (128x64 fp32, TMEM).
-//                       S_t(j+1) is issued as soon as warpgroup t has pulled S_t(j) into registers, so the tensor pipe
-//                       computes the next logits / the other tile's PV while a warpgroup is in its exp phase.
+//   warp 1 (1 lane)   : tcgen05.mma — S_t = Q_t K_j^T (128x128 fp32 in TMEM), O_t += P_t V_j (128x64 fp32 in TMEM) with
+//                       P_t read from TENSOR MEMORY (fp16 pairs, 64 columns): the softmax result never touches shared
+//                       memory. S_t(j+1) is issued as soon as warpgroup t has pulled S_t(j) into registers, so in
+//                       steady state a warpgroup never waits for the tensor pipe.
 //   warps 4..7, 8..11 : softmax warpgroup for tile 0 / tile 1 — thread <-> query row (tcgen05.ld 32x32b), the whole
-//                       128-wide logits row lives in registers (setmaxnreg moves registers from warps 0..3), online max
-//                       with lazy rescaling of the TMEM-resident O (threshold 2^8), P_t written as fp16 into a
-//                       128B-swizzled smem tile that is the A operand of the PV MMA.
+//                       128-wide logits row lives in registers, online max with lazy rescaling of the TMEM-resident O
+//                       (threshold 2^8), P_t = exp2(.) packed to fp16 pairs and stored with tcgen05.st.
 // V is consumed as an MN-major B operand straight from the [token, d] layout the QKV GEMM produces: no transposes.
+// TMEM (512 columns): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512).
 #pragma once
 #include "ptx.cuh"
 
@@ -33,10 +34,15 @@ constexpr int kAttnQBlock = 2 * kAttnTile;              // queries per CTA
 constexpr int kAttnD = 64;
 constexpr int kAttnTileBytes = kAttnTile * kAttnD * 2;  // 16 KB
 constexpr int kAttnStages = 3;
-constexpr int kAttnPBytes = 2 * kAttnTileBytes;         // one P tile: 128 x 128 fp16 = two swizzle atoms
 constexpr int kAttnSmemBytes = 2 * kAttnTileBytes /*Q0,Q1*/ + kAttnStages * 2 * kAttnTileBytes /*K,V ring*/ +
-                               2 * kAttnPBytes /*P0,P1*/ + 256 /*barriers*/;
+                               256 /*barriers*/;
+constexpr int kTmemS = 0, kTmemP = 256, kTmemO = 384;  // column bases (S: 128 per tile, P: 64, O: 64)
 constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P stays <= 256, exact in fp16/fp32 accumulators
+
+template <bool B>
+struct BoolTag {
+  static constexpr bool value = B;
+};
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -54,14 +60,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   uint8_t* q_s = smem;                                       // [2] query tiles
   uint8_t* k_s = q_s + 2 * kAttnTileBytes;                   // [stages]
   uint8_t* v_s = k_s + kAttnStages * kAttnTileBytes;         // [stages]
-  uint8_t* p_s = v_s + kAttnStages * kAttnTileBytes;         // [2] P tiles (2 swizzle atoms of [128 x 64] each)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 2 * kAttnPBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + kAttnStages * kAttnTileBytes);
   uint64_t* q_full = bars;          // 1
   uint64_t* kv_full = bars + 1;     // [3]
   uint64_t* kv_empty = bars + 4;    // [3]
   uint64_t* s_full = bars + 7;      // [2] S_t(j) is in TMEM
   uint64_t* s_empty = bars + 9;     // [2] warpgroup t holds S_t(j) in registers
-  uint64_t* p_full = bars + 11;     // [2] P_t(j) is in smem
+  uint64_t* p_full = bars + 11;     // [2] P_t(j) is in TMEM
   uint64_t* pv_done = bars + 13;    // [2] O_t += P_t(j) V_j has completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
@@ -102,10 +107,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
-
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     if (warp == 0 && lane == 0) {
       // ------------------------------- TMA producer -------------------------------
       mbar_arrive_expect_tx(q_full, ntq * kAttnTileBytes);
@@ -125,68 +127,84 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       const uint32_t idesc_s = umma_idesc_f16(128, kAttnTile, 0);  // S: N = 128 keys, K-major B
       const uint32_t idesc_o = umma_idesc_f16(128, kAttnD, 1);     // O: N = 64 channels, MN-major B (V)
       const uint32_t q_addr = smem_u32(q_s);
-      const uint32_t p_addr = smem_u32(p_s);
       auto issue_s = [&](int t, int stage) {
         const uint32_t k_addr = smem_u32(k_s + stage * kAttnTileBytes);
         const uint32_t qa = q_addr + t * kAttnTileBytes;
 #pragma unroll
         for (int k = 0; k < kAttnD / 16; ++k) {
-          umma_f16(tmem_base + t * 128, umma_smem_desc_sw128(qa + k * 32, 1024, 16),
+          umma_f16(tmem_base + kTmemS + t * 128, umma_smem_desc_sw128(qa + k * 32, 1024, 16),
                    umma_smem_desc_sw128(k_addr + k * 32, 1024, 16), idesc_s, k != 0 ? 1u : 0u);
         }
         umma_commit(&s_full[t]);
       };
       auto issue_pv = [&](int t, int stage, bool accumulate) {
         const uint32_t v_addr = smem_u32(v_s + stage * kAttnTileBytes);
-        const uint32_t pa0 = p_addr + t * kAttnPBytes;
 #pragma unroll
         for (int k = 0; k < kAttnTile / 16; ++k) {
-          const uint32_t pa = pa0 + (k >> 2) * kAttnTileBytes + (k & 3) * 32;
-          const uint32_t va = v_addr + k * 16 * 128;  // 16 token rows of 128 B
-          umma_f16(tmem_base + 256 + t * 64, umma_smem_desc_sw128(pa, 1024, 16), umma_smem_desc_sw128(va, 1024, 16),
-                   idesc_o, (accumulate || k != 0) ? 1u : 0u);
+          // A = P_t from TMEM (8 columns = 16 fp16 per k step); B = 16 token rows of V (128 B each), MN-major
+          umma_f16_ts(tmem_base + kTmemO + t * 64, tmem_base + kTmemP + t * 64 + k * 8,
+                      umma_smem_desc_sw128(v_addr + k * 16 * 128, 1024, 16), idesc_o, (accumulate || k != 0) ? 1u : 0u);
         }
         umma_commit(&pv_done[t]);
       };
       mbar_wait(q_full, 0);
-      for (int j = 0; j <= ntiles; ++j) {
-        if (j < ntiles) {
-          const int s = j % kAttnStages;
-          mbar_wait(&kv_full[s], (j / kAttnStages) & 1);
-          tc_fence_after();
-          for (int t = 0; t < ntq; ++t) {
-            if (j > 0) {
-              mbar_wait(&s_empty[t], (j - 1) & 1);
-              tc_fence_after();
-            }
-            issue_s(t, s);
+      // Event-driven issue: whichever of {S_t(next), PV_t(next)} has its inputs ready goes first, so a slow warpgroup
+      // never blocks the other tile's MMAs (no head-of-line blocking on a fixed t = 0, 1 order).
+      int ns[2] = {0, 0};   // next S index per tile
+      int npv[2] = {0, 0};  // next PV index per tile
+      int freed = 0;        // KV stages released so far
+      long long t0 = clock64();
+      while (npv[0] < ntiles || (ntq == 2 && npv[1] < ntiles)) {
+        bool progress = false;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t >= ntq) continue;
+          const int j = ns[t];
+          if (j < ntiles && j - npv[t] < 1 + 1 &&  // S_t(j) may run ahead of PV_t by one tile (S is single-buffered)
+              mbar_test(&kv_full[j % kAttnStages], (j / kAttnStages) & 1) &&
+              (j == 0 || mbar_test(&s_empty[t], (j - 1) & 1))) {
+            tc_fence_after();
+            issue_s(t, j % kAttnStages);
+            ns[t] = j + 1;
+            progress = true;
+          }
+          const int i = npv[t];
+          if (i < ns[t] && mbar_test(&p_full[t], i & 1)) {
+            tc_fence_after();
+            issue_pv(t, i % kAttnStages, i > 0);
+            npv[t] = i + 1;
+            progress = true;
           }
         }
-        if (j > 0) {
-          const int sp = (j - 1) % kAttnStages;
-          for (int t = 0; t < ntq; ++t) {
-            mbar_wait(&p_full[t], (j - 1) & 1);
-            tc_fence_after();
-            issue_pv(t, sp, j - 1 > 0);
-          }
-          umma_commit(&kv_empty[sp]);
+        const int done = (ntq == 2) ? min(npv[0], npv[1]) : npv[0];
+        while (freed < done) {
+          umma_commit(&kv_empty[freed % kAttnStages]);
+          ++freed;
+        }
+        if (progress) {
+          t0 = clock64();
+        } else if (clock64() - t0 > 4000000000LL) {
+          printf("lr_b200: attention MMA issue loop stalled block=(%d,%d,%d) ns=%d,%d npv=%d,%d\n", blockIdx.x, blockIdx.y,
+                 blockIdx.z, ns[0], ns[1], npv[0], npv[1]);
+          __trap();
         }
       }
     }
   } else {
     // ------------------------------- softmax warpgroups ---------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     const int t = (warp - 4) >> 2;  // query tile of this warpgroup
     const int q = warp & 3;         // TMEM lane quarter
     const int r = q * 32 + lane;    // row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tmem_S = tmem_base + t * 128 + lane_addr;
-    const uint32_t tmem_O = tmem_base + 256 + t * 64 + lane_addr;
-    uint8_t* prow = p_s + t * kAttnPBytes + r * 128;
+    const uint32_t tmem_S = tmem_base + kTmemS + t * 128 + lane_addr;
+    const uint32_t tmem_P = tmem_base + kTmemP + t * 64 + lane_addr;
+    const uint32_t tmem_O = tmem_base + kTmemO + t * 64 + lane_addr;
     float m_used = -INFINITY;  // max the current O / l are scaled against (raw logit units)
     float l = 0.f;
     const int my_tiles = (t < ntq) ? ntiles : 0;
-    for (int j = 0; j < my_tiles; ++j) {
+
+    auto tile_body = [&](int j, auto mask_tag) {
+      constexpr bool kMask = decltype(mask_tag)::value;
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       uint32_t s[128];
@@ -202,20 +220,25 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         tmem_ld_wait();
       }
       tc_fence_before();
-      mbar_arrive(&s_empty[t]);  // S_t may be overwritten by the next QK^T
-      const int kv_valid = p.tk - j * kAttnTile;
-      if (kv_valid < kAttnTile) {
+      mbar_arrive(&s_empty[t]);  // S_t may be overwritten by the next QK^T right away
+      if (kMask) {               // only the last KV tile can be partial (keys beyond tk were zero-filled by TMA)
+        const int kv_valid = p.tk - j * kAttnTile;
 #pragma unroll
         for (int i = 0; i < 128; ++i)
           if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+      float mx[8];
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
-        mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+      for (int c = 0; c < 8; ++c) mx[c] = fmax3(__uint_as_float(s[c]), __uint_as_float(s[c + 8]), __uint_as_float(s[c + 16]));
+#pragma unroll
+      for (int i = 24; i < 120; i += 16) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mx[c] = fmax3(mx[c], __uint_as_float(s[i + c]), __uint_as_float(s[i + c + 8]));
       }
-      const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mx[c] = fmaxf(mx[c], __uint_as_float(s[120 + c]));
+      const float mrow = fmaxf(fmax3(mx[0], mx[1], mx[2]), fmaxf(fmax3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+      const float m_new = fmaxf(m_used, mrow);
       const bool need = (m_new - m_used) * p.scale_log2 > kRescaleThreshold;  // true on the first tile (-inf)
       float alpha = 1.0f;
       if (need) {
@@ -223,8 +246,26 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         m_used = m_new;
         l *= alpha;
       }
+      // P = exp2((s - m_used) * scale_log2) as fp16 pairs, kept in registers until the previous PV has released P_t
+      const float moff = m_used * p.scale_log2;
+      uint32_t h[64];
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        const float e0 = fast_exp2(fmaf(__uint_as_float(s[2 * i]), p.scale_log2, -moff));
+        const float e1 = fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), p.scale_log2, -moff));
+        const float e2 = fast_exp2(fmaf(__uint_as_float(s[2 * i + 2]), p.scale_log2, -moff));
+        const float e3 = fast_exp2(fmaf(__uint_as_float(s[2 * i + 3]), p.scale_log2, -moff));
+        l0 += e0;
+        l1 += e1;
+        l2 += e2;
+        l3 += e3;
+        h[i] = pack_half2(e0, e1);
+        h[i + 1] = pack_half2(e2, e3);
+      }
+      l += (l0 + l1) + (l2 + l3);
       if (j > 0) {
-        mbar_wait(&pv_done[t], (j - 1) & 1);  // PV(j-1) finished: P_t smem and O_t may be touched
+        mbar_wait(&pv_done[t], (j - 1) & 1);  // PV(j-1) finished reading P_t and updating O_t
         tc_fence_after();
         if (__any_sync(0xffffffffu, need)) {
           // rescale the TMEM-resident O row (warp-collective; lanes that do not need it use alpha = 1)
@@ -237,54 +278,46 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
             tmem_st32(tmem_O + c, v);
           }
-          tmem_st_wait();
         }
       }
-      // P = exp2((s - m_used) * scale_log2) -> fp16, swizzled K-major smem tile (stores interleave with the exps)
-      const float moff = m_used * p.scale_log2;
-      float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < 128; c += 8) {
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) e[i] = fast_exp2(fmaf(__uint_as_float(s[c + i]), p.scale_log2, -moff));
-        l0 += (e[0] + e[1]) + (e[2] + e[3]);
-        l1 += (e[4] + e[5]) + (e[6] + e[7]);
-        const uint4 w = make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]),
-                                   pack_half2(e[6], e[7]));
-        // columns [c, c+8) = 16-byte chunk ((c & 63) >> 3) of atom (c >> 6), XOR-swizzled with the row
-        const int ch = ((c & 63) >> 3) ^ (r & 7);
-        *reinterpret_cast<uint4*>(prow + (c >> 6) * kAttnTileBytes + ch * 16) = w;
+      {
+        uint32_t(&h0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&h[0]);
+        uint32_t(&h1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&h[32]);
+        tmem_st32(tmem_P, h0);
+        tmem_st32(tmem_P + 32, h1);
       }
-      l += l0 + l1;
-      fence_proxy_async_smem();
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
-    }
-    // epilogue: O / l -> fp16
+    };
+
+    for (int j = 0; j < my_tiles - 1; ++j) tile_body(j, BoolTag<false>{});
+    if (my_tiles > 0) tile_body(my_tiles - 1, BoolTag<true>{});
+
+    // epilogue: O / rowsum -> fp16
     if (t < ntq) {
-    mbar_wait(&pv_done[t], (ntiles - 1) & 1);
-    tc_fence_after();
-    const int row = qb * kAttnQBlock + t * kAttnTile + r;
-    const float inv_l = 1.0f / l;
-    __half* o = p.out + (static_cast<size_t>(b) * p.tq + row) * p.ld_out + head * kAttnD;
+      mbar_wait(&pv_done[t], (ntiles - 1) & 1);
+      tc_fence_after();
+      const int row = qb * kAttnQBlock + t * kAttnTile + r;
+      const float inv_l = 1.0f / l;
+      __half* o = p.out + (static_cast<size_t>(b) * p.tq + row) * p.ld_out + head * kAttnD;
 #pragma unroll 1
-    for (int c = 0; c < kAttnD; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_O + c, v);
-      tmem_ld_wait();
-      if (row < p.tq) {
+      for (int c = 0; c < kAttnD; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_O + c, v);
+        tmem_ld_wait();
+        if (row < p.tq) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint4 w;
-          w.x = pack_half2(__uint_as_float(v[8 * k + 0]) * inv_l, __uint_as_float(v[8 * k + 1]) * inv_l);
-          w.y = pack_half2(__uint_as_float(v[8 * k + 2]) * inv_l, __uint_as_float(v[8 * k + 3]) * inv_l);
-          w.z = pack_half2(__uint_as_float(v[8 * k + 4]) * inv_l, __uint_as_float(v[8 * k + 5]) * inv_l);
-          w.w = pack_half2(__uint_as_float(v[8 * k + 6]) * inv_l, __uint_as_float(v[8 * k + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(o + c + 8 * k) = w;
+          for (int k = 0; k < 4; ++k) {
+            uint4 w;
+            w.x = pack_half2(__uint_as_float(v[8 * k + 0]) * inv_l, __uint_as_float(v[8 * k + 1]) * inv_l);
+            w.y = pack_half2(__uint_as_float(v[8 * k + 2]) * inv_l, __uint_as_float(v[8 * k + 3]) * inv_l);
+            w.z = pack_half2(__uint_as_float(v[8 * k + 4]) * inv_l, __uint_as_float(v[8 * k + 5]) * inv_l);
+            w.w = pack_half2(__uint_as_float(v[8 * k + 6]) * inv_l, __uint_as_float(v[8 * k + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(o + c + 8 * k) = w;
+          }
         }
       }
-    }
     }
   }
 

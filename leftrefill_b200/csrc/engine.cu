@@ -1049,7 +1049,8 @@ int lr_linear_f16(const void* a, int lda, int M, int K, const void* w, int ldw, 
   s.out = static_cast<__half*>(out);
   s.ld_out = ld_out;
   s.geglu = geglu;
-  s.force_block_n = force_block_n;
+  s.force_block_n = force_block_n % 1000;
+  s.force_cg = force_block_n / 1000;
   ConvOp op;
   LR_TRY(build_conv_op(&op, s));
   return launch_conv_op(op, static_cast<cudaStream_t>(stream));
@@ -1080,7 +1081,8 @@ int lr_conv3x3_f16(const void* x0, int c0, const void* x1, int c1, int n, int h,
   s.ld_res = cout;
   s.out = static_cast<__half*>(out);
   s.ld_out = cout;
-  s.force_block_n = force_block_n;
+  s.force_block_n = force_block_n % 1000;
+  s.force_cg = force_block_n / 1000;
   ConvOp op;
   LR_TRY(build_conv_op(&op, s));
   return launch_conv_op(op, static_cast<cudaStream_t>(stream));

@@ -14,6 +14,10 @@
 // Structure (one CTA per SM, persistent over output tiles of 128 x block_n):
 //   warp 0 (1 lane)  TMA producer      -> smem ring of {A 128x64, B block_n x 64} fp16 stages, 128B swizzle
 //   warp 1 (1 lane)  tcgen05.mma issue -> fp32 accumulator in TMEM, double buffered (2 x 256 columns)
+// CG = 2 (large problems): the two CTAs of a cluster form a CTA pair. Each loads its own 128 pixel rows of A and HALF
+// of the weight tile; the leader issues tcgen05.mma.cta_group::2 (M = 256), which reads B halves from both SMs, so
+// every SM ingests (128 + block_n/2) x 128 B per k-chunk instead of (128 + block_n) x 128 B — the per-SM L2->smem
+// ingest rate is what capped the 1-CTA kernel at ~55 % tensor-pipe utilisation.
 //   warps 2..9       epilogue          -> tcgen05.ld, bias (smem staged) / per-image bias (time embedding) /
 //                                         residual (prefetched one chunk ahead) / GEGLU, fp16 stores
 #pragma once
@@ -56,9 +60,12 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kMaxStages = 8;
 constexpr int kGemmAuxBytes = 256 /*barriers*/ + 2 * 256 * 4 /*bias staging, double buffered*/;
 
-__host__ __device__ inline int gemm_stage_bytes(int block_n) { return kATileBytes + block_n * kBlockK * 2; }
-__host__ inline int gemm_smem_bytes(int block_n, int stages) {
-  return 1024 /*align slack*/ + stages * gemm_stage_bytes(block_n) + kGemmAuxBytes;
+// bytes of one pipeline stage in ONE CTA (cg = CTAs cooperating on a tile: each holds block_n / cg weight rows)
+__host__ __device__ inline int gemm_stage_bytes(int block_n, int cg = 1) {
+  return kATileBytes + (block_n / cg) * kBlockK * 2;
+}
+__host__ inline int gemm_smem_bytes(int block_n, int stages, int cg = 1) {
+  return 1024 /*align slack*/ + stages * gemm_stage_bytes(block_n, cg) + kGemmAuxBytes;
 }
 
 // erf with |abs error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): one MUFU.RCP + one MUFU.EX2 + 8 FMA-pipe ops.
@@ -78,10 +85,14 @@ __device__ __forceinline__ float fast_erf(float x) {
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
 
+template <int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid_constant__ GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = gemm_stage_bytes(p.block_n);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // identical smem offsets in both CTAs of a pair are required (UMMA descriptors / multicast commits use offsets)
+  uint8_t* smem = smem_raw;
+  const int stage_bytes = gemm_stage_bytes(p.block_n, CG);
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* full = bars;                   // [kMaxStages]
   uint64_t* empty = bars + kMaxStages;     // [kMaxStages]
@@ -94,6 +105,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("lr_b200: gemm smem base not 1024-aligned\n");
+      __trap();
+    }
     tma_prefetch_desc(&p.tmA0);
     tma_prefetch_desc(&p.tmA1);
     tma_prefetch_desc(&p.tmB);
@@ -103,37 +118,47 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kEpiWarps);
+      mbar_init(&tempty[i], kEpiWarps * CG);  // the leader's MMA thread waits for the epilogues of BOTH CTAs
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_2sm(tmem_slot, 512);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Work unit = one 128*CG x block_n output tile per CTA (pair). CTA `rank` of a pair owns M-tile CG*pair + rank; when
+  // the number of M-tiles is odd the last pair's second CTA recomputes the last tile and simply does not store it.
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
-  const int num_tiles = tiles_m * p.tiles_n;
+  const int tiles_mp = (tiles_m + CG - 1) / CG;
+  const int num_tiles = tiles_mp * p.tiles_n;
   const int kiters = p.taps * (p.kc0 + p.kc1);
+  const int unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
+  const int b_rows = p.block_n / CG;
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
         const int tn = tile % p.tiles_n;
-        int tm = tile / p.tiles_n;
+        int tm = min((tile / p.tiles_n) * CG + static_cast<int>(rank), tiles_m - 1);
         const int tx = tm % p.tiles_x;
         tm /= p.tiles_x;
         const int ty = tm % p.tiles_y;
         const int tb = tm / p.tiles_y;
         const int x0 = tx * p.bw * p.stride, y0 = ty * p.bh * p.stride, n0 = tb * p.bn;
-        const int ncol0 = tn * p.block_n;
+        const int ncol0 = tn * p.block_n + static_cast<int>(rank) * b_rows;  // this CTA's share of the weight rows
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
           const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
@@ -141,16 +166,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* a_s = smem + s * stage_bytes;
             uint8_t* b_s = a_s + kATileBytes;
-            mbar_arrive_expect_tx(&full[s], stage_bytes);
-            int kb;
-            if (kc < p.kc0) {
-              tma_load_4d(a_s, &p.tmA0, &full[s], kc * kBlockK, x0 + dx, y0 + dy, n0);
-              kb = tap * p.ctot + kc * kBlockK;
+            const bool src0 = kc < p.kc0;
+            const int kch = (src0 ? kc : kc - p.kc0) * kBlockK;
+            const int kb = tap * p.ctot + (src0 ? 0 : p.c0) + kch;
+            const CUtensorMap* ta = src0 ? &p.tmA0 : &p.tmA1;
+            if (CG == 2) {
+              // the leader's barrier collects the bytes of both CTAs
+              if (leader) mbar_arrive_expect_tx(&full[s], 2 * stage_bytes);
+              tma_load_4d_2sm(a_s, ta, &full[s], kch, x0 + dx, y0 + dy, n0);
+              tma_load_2d_2sm(b_s, &p.tmB, &full[s], kb, ncol0);
             } else {
-              tma_load_4d(a_s, &p.tmA1, &full[s], (kc - p.kc0) * kBlockK, x0 + dx, y0 + dy, n0);
-              kb = tap * p.ctot + p.c0 + (kc - p.kc0) * kBlockK;
+              mbar_arrive_expect_tx(&full[s], stage_bytes);
+              tma_load_4d(a_s, ta, &full[s], kch, x0 + dx, y0 + dy, n0);
+              tma_load_2d(b_s, &p.tmB, &full[s], kb, ncol0);
             }
-            tma_load_2d(b_s, &p.tmB, &full[s], kb, ncol0);
             if (++s == p.stages) { s = 0; ph ^= 1; }
           }
         }
@@ -158,13 +187,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(kBlockM, p.block_n, 0);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc_f16(kBlockM * CG, p.block_n, 0);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * 256;
@@ -177,12 +206,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
           for (int k = 0; k < kBlockK / 16; ++k) {
             const uint64_t ad = umma_smem_desc_sw128(a_addr + k * 32, 1024, 16);
             const uint64_t bd = umma_smem_desc_sw128(b_addr + k * 32, 1024, 16);
-            umma_f16(d_tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+            if (CG == 2) umma_f16_2sm(d_tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[s]);
+          if (CG == 2) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[as]);
+        if (CG == 2) umma_commit_2sm(&tfull[as]); else umma_commit(&tfull[as]);
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
@@ -197,9 +227,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     int as = 0;
     uint32_t aph = 0;
     const bool vec_ok = (p.ld_out % 8 == 0) && (p.residual == nullptr || p.ld_res % 8 == 0);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit0; tile < num_tiles; tile += unit_step) {
       const int tn = tile % p.tiles_n;
-      int tm = tile / p.tiles_n;
+      int tm = (tile / p.tiles_n) * CG + static_cast<int>(rank);
+      const bool tile_ok = tm < tiles_m;
+      tm = min(tm, tiles_m - 1);
       const int tx = tm % p.tiles_x;
       tm /= p.tiles_x;
       const int ty = tm % p.tiles_y;
@@ -208,7 +240,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       const int yi = (r / p.bw) % p.bh;
       const int ni = r / (p.bw * p.bh);
       const int x = tx * p.bw + xi, y = ty * p.bh + yi, n = tb * p.bn + ni;
-      const bool row_ok = (x < p.W) && (y < p.H) && (n < p.n_img);
+      const bool row_ok = tile_ok && (x < p.W) && (y < p.H) && (n < p.n_img);
       const size_t grow = (static_cast<size_t>(n) * p.H + y) * p.W + x;
       const int ncol0 = tn * p.block_n;
 
@@ -316,14 +348,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]);
+      }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 }  // namespace lr

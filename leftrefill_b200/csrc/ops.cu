@@ -129,25 +129,42 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   p.ctot = s.c0 + s.c1;
   p.ncols = s.ncols;
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
-  // block_n: minimise waves * (block_n + fixed overhead)
-  int block_n = s.force_block_n;
-  if (block_n == 0) {
-    long long best = INT64_MAX;
-    for (int bnn = 256; bnn >= 32; bnn -= 32) {
-      const long long tiles = 1LL * tiles_m * cdiv(s.ncols, bnn);
-      const long long waves = (tiles + sm_count() - 1) / sm_count();
-      const long long cost = waves * (bnn + 40);
-      if (cost < best) {
-        best = cost;
-        block_n = bnn;
+  // (cg, block_n): minimise waves * per-tile cost. The per-tile cost models the measured behaviour of the kernel:
+  // tensor time ~ block_n, but the mainloop is bound by the bytes each SM pulls from L2 per k-chunk,
+  // (128 + block_n / cg) rows, when that exceeds what the SM can ingest while the MMAs run.
+  int block_n = s.force_block_n, cg = s.force_cg;
+  {
+    double best = 1e300;
+    int best_bn = 0, best_cg = 0;
+    for (int c = 1; c <= 2; ++c) {
+      if (s.force_cg && c != s.force_cg) continue;
+      if (c == 2 && tiles_m < 2) continue;
+      for (int bnn = 256; bnn >= 32; bnn -= 32) {
+        if (s.force_block_n && bnn != s.force_block_n) continue;
+        if (c == 2 && bnn % 32 != 0) continue;
+        const long long units = 1LL * cdiv(tiles_m, c) * cdiv(s.ncols, bnn);
+        const long long slots = sm_count() / c;
+        const long long waves = (units + slots - 1) / slots;
+        const double tensor = bnn;                               // ~ cycles / 0.5 per k16 step
+        const double ingest = 1.0 * (128.0 + bnn / c);           // bytes-bound mainloop (calibrated on B200, ncu r1)
+        const double per_tile = (tensor > ingest ? tensor : ingest) + 40.0;
+        const double cost = waves * per_tile;
+        if (cost < best) {
+          best = cost;
+          best_bn = bnn;
+          best_cg = c;
+        }
       }
     }
+    LR_CHECK(best_bn != 0, "conv: no feasible tile configuration");
+    block_n = best_bn;
+    cg = best_cg;
   }
   LR_CHECK(block_n % 32 == 0 && block_n >= 32 && block_n <= 256, "conv: bad block_n");
   LR_CHECK(!s.geglu || (s.ncols % 2 == 0), "conv: GEGLU needs an even column count");
   p.block_n = block_n;
   p.tiles_n = cdiv(s.ncols, block_n);
-  int stages = (232448 - 1024 - kGemmAuxBytes) / gemm_stage_bytes(block_n);
+  int stages = (232448 - 1024 - kGemmAuxBytes) / gemm_stage_bytes(block_n, cg);
   if (stages > kMaxStages) stages = kMaxStages;
   LR_CHECK(stages >= 2, "conv: not enough shared memory for 2 stages");
   p.stages = stages;
@@ -187,21 +204,24 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
     uint64_t dims[2] = {static_cast<uint64_t>(s.taps) * (s.c0 + s.c1), static_cast<uint64_t>(s.ncols)};
     LR_CHECK(dims[0] <= static_cast<uint64_t>(s.ldw), "conv: weight leading dim smaller than K");
     uint64_t str[1] = {static_cast<uint64_t>(s.ldw) * 2};
-    uint32_t box[2] = {kBlockK, static_cast<uint32_t>(block_n)};
+    uint32_t box[2] = {kBlockK, static_cast<uint32_t>(block_n / cg)};
     uint32_t es[2] = {1, 1};
     LR_TRY(make_tmap(&p.tmB, s.w, 2, dims, str, box, es));
   }
-  const int num_tiles = tiles_m * p.tiles_n;
-  op->grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  op->smem = gemm_smem_bytes(block_n, stages);
+  const int num_units = cdiv(tiles_m, cg) * p.tiles_n;
+  const int slots = sm_count() / cg;
+  op->grid = (num_units < slots ? num_units : slots) * cg;
+  op->smem = gemm_smem_bytes(block_n, stages, cg);
   op->block_n = block_n;
   op->stages = stages;
-  op->tiles = num_tiles;
+  op->tiles = num_units;
+  op->cg = cg;
   op->flops = 2.0 * s.n_img * Ho * Wo * static_cast<double>(s.ncols) * s.taps * (s.c0 + s.c1);
   memcpy(op->params, &p, sizeof(p));
   static bool attr_set = false;
   if (!attr_set) {
-    LR_CUDA(cudaFuncSetAttribute(gemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    LR_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    LR_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   return 0;
@@ -209,7 +229,24 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
 
 int launch_conv_op(const ConvOp& op, cudaStream_t st) {
   const GemmParams* p = reinterpret_cast<const GemmParams*>(op.params);
-  gemm_conv_kernel<<<op.grid, kGemmThreads, op.smem, st>>>(*p);
+  if (op.cg == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(op.grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = op.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LR_CUDA(cudaLaunchKernelEx(&cfg, gemm_conv_kernel<2>, *p));
+  } else {
+    gemm_conv_kernel<1><<<op.grid, kGemmThreads, op.smem, st>>>(*p);
+  }
   LR_LAUNCHED();
   return 0;
 }

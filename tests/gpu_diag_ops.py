@@ -174,6 +174,7 @@ def case_time(kind):
             a = torch.randn(M, K, device="cuda").half()
             w = torch.randn(Nn, K, device="cuda").half()
             timeit(lambda: ops.linear(a, w), 2.0 * M * K * Nn, f"linear {M}x{K}x{Nn}")
+            timeit(lambda: ops.linear(a, w, force_block_n=1000), 2.0 * M * K * Nn, f"linear {M}x{K}x{Nn} cg1")
         M, K, Nn = 65536, 320, 1280
         a = torch.randn(M, K, device="cuda").half()
         w = torch.randn(2 * Nn, K, device="cuda").half()
@@ -185,6 +186,9 @@ def case_time(kind):
             wt = torch.randn(co, 9 * c, device="cuda").half() * 0.01
             b = torch.zeros(co, device="cuda")
             timeit(lambda: ops.conv3x3(x, wt, bias=b), 2.0 * n * h * w_ * 9 * c * co, f"conv {n}x{h}x{w_} {c}->{co}")
+            for f in (1000, 2160, 2256):
+                timeit(lambda: ops.conv3x3(x, wt, bias=b, force_block_n=f), 2.0 * n * h * w_ * 9 * c * co,
+                       f"conv {n}x{h}x{w_} {c}->{co} force={f}")
     elif kind == "attn":
         for (b, hd, t, tk) in [(8, 5, 8192, 8192), (8, 10, 2048, 2048), (8, 20, 512, 512), (8, 5, 8192, 77),
                                (8, 20, 128, 128)]:
@@ -202,6 +206,11 @@ CASES = {
     "linear_bn64": lambda: case_linear(512, 320, 320, force=64),
     "linear_bn160": lambda: case_linear(512, 320, 320, force=160),
     "linear_bn256": lambda: case_linear(384, 640, 512, force=256),
+    "linear_2sm_256": lambda: case_linear(1024, 640, 512, bias=True, residual=True, force=2256),
+    "linear_2sm_160": lambda: case_linear(1000, 320, 320, bias=True, residual=True, force=2160),
+    "linear_2sm_odd": lambda: case_linear(384, 320, 96, bias=True, force=2096),
+    "linear_2sm_geglu": lambda: case_linear(512, 320, 1280, bias=True, geglu=True, force=2256),
+    "linear_2sm_big": lambda: case_linear(8192, 1280, 1280, bias=True, residual=True, force=2000),
     "linear_ragged": lambda: case_linear(1000, 320, 320, bias=True, residual=True),
     "linear_geglu": lambda: case_linear(512, 320, 1280, bias=True, geglu=True),
     "linear_n4": lambda: case_linear(300, 128, 4, bias=True),
@@ -212,6 +221,10 @@ CASES = {
     "conv_w128": lambda: case_conv(1, 8, 128, 64, 64),
     "conv_odd": lambda: case_conv(3, 24, 40, 64, 96),
     "conv_tiny": lambda: case_conv(4, 4, 8, 64, 64),
+    "conv_2sm": lambda: case_conv(2, 16, 32, 128, 192, bias_img=True, residual=True, force=2000),
+    "conv_2sm_concat": lambda: case_conv(2, 16, 32, 128, 128, c1=64, force=2128),
+    "conv_2sm_odd": lambda: case_conv(3, 24, 40, 64, 96, force=2096),
+    "conv_2sm_s2": lambda: case_conv(2, 64, 128, 64, 64, stride=2, force=2064),
     "conv_s2": lambda: case_conv(2, 16, 32, 64, 64, stride=2),
     "conv_s2_big": lambda: case_conv(2, 64, 128, 64, 64, stride=2),
     "conv_cout4": lambda: case_conv(2, 16, 32, 64, 4),

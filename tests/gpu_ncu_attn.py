@@ -1,0 +1,36 @@
+"""Single-kernel driver for ncu captures: python tests/gpu_ncu_attn.py [attn|conv|geglu|lin320]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from leftrefill_b200 import ops  # noqa: E402
+
+kind = sys.argv[1] if len(sys.argv) > 1 else "attn"
+torch.manual_seed(0)
+if kind == "attn":
+    qkv = torch.randn(8, 8192, 960, device="cuda").half()
+    q, k, v = qkv[:, :, :320], qkv[:, :, 320:640], qkv[:, :, 640:]
+    for _ in range(3):
+        ops.attention(q, k, v, 5)
+elif kind == "conv":
+    x = torch.randn(8, 64, 128, 320, device="cuda").half()
+    w = torch.randn(320, 2880, device="cuda").half() * 0.02
+    b = torch.zeros(320, device="cuda")
+    for _ in range(3):
+        ops.conv3x3(x, w, bias=b)
+elif kind == "conv1280":
+    x = torch.randn(8, 32, 64, 1280, device="cuda").half()
+    w = torch.randn(1280, 11520, device="cuda").half() * 0.01
+    b = torch.zeros(1280, device="cuda")
+    for _ in range(3):
+        ops.conv3x3(x, w, bias=b)
+elif kind == "lin320":
+    a = torch.randn(65536, 320, device="cuda").half()
+    w = torch.randn(320, 320, device="cuda").half() * 0.05
+    r = torch.randn(65536, 320, device="cuda").half()
+    b = torch.zeros(320, device="cuda")
+    for _ in range(3):
+        ops.linear(a, w, bias=b, residual=r)
+torch.cuda.synchronize()
