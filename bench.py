@@ -145,6 +145,7 @@ def run_native(args):
     from leftrefill_b200 import _native as N
     from leftrefill_b200 import parallel as P
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
     rank, world = P.init_distributed()
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -266,11 +267,13 @@ def run_native(args):
                                      "frac": (classes["attention_kernel"]["tflops"] or 0) / sustained},
                 "by_class": classes}
 
-    cb_times, cores = cpu_baseline(threads=os.cpu_count(), canvases=1, repeats=1, warmup=1)
-    cb_t = sum(cb_times) / len(cb_times)
-    cb = {"value": 1.0 / (S * cb_t), "unit": UNIT, "cores": cores, "kind": "port",
-          "sample": f"1 CFG DDIM step (UNet batch 2, 64x128 latent, fp32 oracle) of 1 canvas = {cb_t:.2f} s on {cores} "
-                    f"threads; images/s = 1/({S} x step)"}
+    cb = None
+    if world == 1:  # the CPU baseline is reported at N = 1 only
+        cb_times, cores = cpu_baseline(threads=os.cpu_count(), canvases=1, repeats=1, warmup=1)
+        cb_t = sum(cb_times) / len(cb_times)
+        cb = {"value": 1.0 / (S * cb_t), "unit": UNIT, "cores": cores, "kind": "port",
+              "sample": f"1 CFG DDIM step (UNet batch 2, 64x128 latent, fp32 oracle) of 1 canvas = {cb_t:.2f} s on "
+                        f"{cores} threads; images/s = 1/({S} x step)"}
 
     images = B * world * args.steps
     h2d = sum(t.numel() * t.element_size() for t in (xT_h, ccat_h, ctx_h, uc_h))
