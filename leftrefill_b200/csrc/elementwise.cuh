@@ -329,6 +329,53 @@ __global__ void upsample2x_nhwc_kernel(const __half* __restrict__ x, int n_img, 
   *reinterpret_cast<uint4*>(out + m * C + v * 8) = val;
 }
 
+// Multiview re-arranged self-attention (ldm/modules/multiview_attention.py:436-462, concat_target=True): every UNet
+// batch row is a stitched [ref_i | target] canvas of hh x (2*side) tokens. The attention sequence of sample b is
+// [target (taken from row 0), ref_1 .. ref_v], each block hh*side tokens. gather: dst[b, k, y, x] <- src; scatter:
+// the attended sequence is written back with the target block broadcast to all v rows (:456-460).
+__device__ __forceinline__ size_t mv_src_row(int bi, int k, int y, int x, int v, int hh, int side) {
+  const int row_img = (k == 0) ? bi * v : bi * v + (k - 1);
+  const int xx = (k == 0) ? side + x : x;
+  return (static_cast<size_t>(row_img) * hh + y) * (2 * side) + xx;
+}
+__global__ void mv_gather_kernel(const __half* __restrict__ src, int ld_src, int ncols, int b, int v, int hh, int side,
+                                 __half* __restrict__ dst) {
+  const int nvec = ncols / 8;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(b) * (v + 1) * hh * side * nvec;
+  if (idx >= total) return;
+  const int vec = static_cast<int>(idx % nvec);
+  size_t r = idx / nvec;
+  const int x = static_cast<int>(r % side);
+  r /= side;
+  const int y = static_cast<int>(r % hh);
+  r /= hh;
+  const int k = static_cast<int>(r % (v + 1));
+  const int bi = static_cast<int>(r / (v + 1));
+  const uint4 val = *reinterpret_cast<const uint4*>(src + mv_src_row(bi, k, y, x, v, hh, side) * ld_src + vec * 8);
+  *reinterpret_cast<uint4*>(dst + (idx / nvec) * ncols + vec * 8) = val;
+}
+__global__ void mv_scatter_kernel(const __half* __restrict__ src, int ncols, int b, int v, int hh, int side,
+                                  __half* __restrict__ dst) {
+  const int nvec = ncols / 8;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(b) * v * hh * 2 * side * nvec;
+  if (idx >= total) return;
+  const int vec = static_cast<int>(idx % nvec);
+  size_t r = idx / nvec;
+  const int xx = static_cast<int>(r % (2 * side));
+  r /= 2 * side;
+  const int y = static_cast<int>(r % hh);
+  r /= hh;
+  const int i = static_cast<int>(r % v);
+  const int bi = static_cast<int>(r / v);
+  const int k = (xx < side) ? i + 1 : 0;
+  const int x = (xx < side) ? xx : xx - side;
+  const size_t srow = ((static_cast<size_t>(bi) * (v + 1) + k) * hh + y) * side + x;
+  *reinterpret_cast<uint4*>(dst + (idx / nvec) * ncols + vec * 8) =
+      *reinterpret_cast<const uint4*>(src + srow * ncols + vec * 8);
+}
+
 // fp32 -> fp16 cast (context tokens)
 __global__ void cast_f32_f16_kernel(const float* __restrict__ x, size_t n, __half* __restrict__ out) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;

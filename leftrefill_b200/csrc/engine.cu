@@ -568,7 +568,46 @@ struct lr_unet {
       LR_TRY(add_ln(h, M, C, F(b.ln1_g), F(b.ln1_b), t));
       LR_TRY(acquire_h(static_cast<size_t>(M) * 3 * C, &qkv));
       LR_TRY(add_linear(t, M, C, H(b.qkv_w), 3 * C, nullptr, nullptr, 0, qkv, 3 * C, 0));
-      {
+      if (cfg.view_num > 1 && cfg.concat_target) {
+        // multiview_attention.py:436-462: rows are stitched [ref_i | target] canvases; attend over
+        // [target(row 0), ref_1..ref_v] and write the target block back to every row.
+        const int v = cfg.view_num - 1;
+        LR_CHECK(n % v == 0, "multiview: UNet batch not divisible by view_num - 1");
+        const int side = x.W / 2, hh = x.H;
+        LR_CHECK(x.W == 2 * x.H, "multiview concat_target expects stitched canvases with W == 2*H (as the reference)");
+        const int bs = n / v;
+        const int Tp = (v + 1) * hh * side;
+        const int Mp = bs * Tp;
+        __half *qkv_r, *a_r, *h_r, *o_r;
+        LR_TRY(acquire_h(static_cast<size_t>(Mp) * 3 * C, &qkv_r));
+        LR_TRY(acquire_h(static_cast<size_t>(Mp) * C, &a_r));
+        LR_TRY(acquire_h(static_cast<size_t>(Mp) * C, &h_r));
+        LR_TRY(acquire_h(static_cast<size_t>(Mp) * C, &o_r));
+        {
+          const __half* src = qkv;
+          push([=](cudaStream_t st) { return launch_mv_gather(src, 3 * C, 3 * C, bs, v, hh, side, qkv_r, st); });
+          const __half* hsrc = h;
+          push([=](cudaStream_t st) { return launch_mv_gather(hsrc, C, C, bs, v, hh, side, h_r, st); });
+        }
+        AttnSpec as;
+        as.q = qkv_r; as.ldq = 3 * C; as.q_col0 = 0;
+        as.k = qkv_r; as.ldk = 3 * C; as.k_col0 = C;
+        as.v = qkv_r; as.ldv = 3 * C; as.v_col0 = 2 * C;
+        as.out = a_r; as.ld_out = C;
+        as.batch = bs; as.heads = s.heads; as.tq = Tp; as.tk = Tp;
+        as.scale = 0.125f;
+        LR_TRY(add_attn(as));
+        LR_TRY(add_linear(a_r, Mp, C, H(b.out1_w), C, F(b.out1_b), h_r, C, o_r, C, 0));
+        {
+          __half* hdst = h;
+          push([=](cudaStream_t st) { return launch_mv_scatter(o_r, C, bs, v, hh, side, hdst, st); });
+        }
+        pool.release(qkv_r);
+        pool.release(a_r);
+        pool.release(h_r);
+        pool.release(o_r);
+        pool.release(qkv);
+      } else {
         // multiview (multiview_attention.py:448,462, concat_target=False): '(b v) hw c -> b (v hw) c' is a pure
         // reshape of the token matrix, so only batch / sequence length change.
         const int v = cfg.view_num > 1 ? cfg.view_num : 1;
@@ -581,9 +620,9 @@ struct lr_unet {
         as.batch = n / v; as.heads = s.heads; as.tq = P * v; as.tk = P * v;
         as.scale = 0.125f;
         LR_TRY(add_attn(as));
+        pool.release(qkv);
+        LR_TRY(add_linear(a, M, C, H(b.out1_w), C, F(b.out1_b), h, C, h, C, 0));
       }
-      pool.release(qkv);
-      LR_TRY(add_linear(a, M, C, H(b.out1_w), C, F(b.out1_b), h, C, h, C, 0));
       // cross-attention against the cached context K/V
       LR_TRY(add_ln(h, M, C, F(b.ln2_g), F(b.ln2_b), t));
       __half* q2;
@@ -865,8 +904,6 @@ int lr_unet_create(const lr_unet_cfg* cfg, lr_unet** out) {
   h->cfg = *cfg;
   if (h->cfg.view_num < 1) h->cfg.view_num = 1;
   LR_CHECK(h->cfg.transformer_depth >= 1, "transformer_depth must be >= 1");
-  LR_CHECK(!(h->cfg.view_num > 1 && h->cfg.concat_target),
-           "multiview concat_target=True re-arranged attention is not implemented yet");
   LR_TRY(h->build_graph());
   *out = h.release();
   return 0;

@@ -361,6 +361,21 @@ int launch_upsample2x(const __half* x, int n_img, int H, int W, int C, __half* o
   LR_LAUNCHED();
   return 0;
 }
+int launch_mv_gather(const __half* src, int ld_src, int ncols, int b, int v, int hh, int side, __half* dst,
+                     cudaStream_t st) {
+  LR_CHECK(ncols % 8 == 0 && ld_src % 8 == 0, "mv_gather: columns must be multiples of 8");
+  const size_t total = static_cast<size_t>(b) * (v + 1) * hh * side * (ncols / 8);
+  mv_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, ld_src, ncols, b, v, hh, side, dst);
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_mv_scatter(const __half* src, int ncols, int b, int v, int hh, int side, __half* dst, cudaStream_t st) {
+  LR_CHECK(ncols % 8 == 0, "mv_scatter: columns must be multiples of 8");
+  const size_t total = static_cast<size_t>(b) * v * hh * 2 * side * (ncols / 8);
+  mv_scatter_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, ncols, b, v, hh, side, dst);
+  LR_LAUNCHED();
+  return 0;
+}
 int launch_cast_f32_f16(const float* x, size_t n, __half* out, cudaStream_t st) {
   cast_f32_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, n, out);
   LR_LAUNCHED();

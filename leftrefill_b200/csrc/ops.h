@@ -94,6 +94,9 @@ int launch_layernorm(const __half* x, int M, int C, const float* gamma, const fl
                      cudaStream_t st);
 int launch_im2col_nchw_f32(const float* x, int n_img, int cin, int H, int W, int kpad, __half* out, cudaStream_t st);
 int launch_upsample2x(const __half* x, int n_img, int H, int W, int C, __half* out, cudaStream_t st);
+int launch_mv_gather(const __half* src, int ld_src, int ncols, int b, int v, int hh, int side, __half* dst,
+                     cudaStream_t st);
+int launch_mv_scatter(const __half* src, int ncols, int b, int v, int hh, int side, __half* dst, cudaStream_t st);
 int launch_cast_f32_f16(const float* x, size_t n, __half* out, cudaStream_t st);
 int launch_nhwc_to_nchw_f32(const __half* x, int ld, int n_img, int cout, int H, int W, float* out, cudaStream_t st);
 int launch_nchw_f32_to_nhwc(const float* x, int n_img, int C, int H, int W, __half* out, cudaStream_t st);

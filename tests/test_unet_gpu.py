@@ -108,8 +108,11 @@ def test_autocast_and_no_grad_context(small):
     _assert_parity(y.float(), g["out"])
 
 
-def test_multiview_v2_vs_reference_golden():
-    g = load_golden("multiview_v2.npz")
+@pytest.mark.parametrize("name", ["multiview_v2.npz", "multiview_v3ct.npz"])
+def test_multiview_vs_reference_golden(name):
+    """MultiViewUnetModel: view_num=2 / concat_target=False (pure re-batching) and view_num=3 / concat_target=True
+    (re-arranged [target, ref_1, ref_2] self-attention with the target block broadcast back to every row)."""
+    g = load_golden(name)
     mv = (int(g["view_num"]), bool(g["concat_target"]))
     m, sd = _build(O.SMALL_CFG, 1, multiview=mv)
     x, t, ctx = torch.tensor(g["x"]), torch.tensor(g["t"]), torch.tensor(g["context"])
