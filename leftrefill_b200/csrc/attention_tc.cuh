@@ -49,6 +49,10 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Measured dead ends (B200, round 1, 8x5 heads x 8192^2): ex2.approx.f16x2 is split by ptxas into two MUFU ops + PRMT;
+// moving 25 % of the exponentials to an FMA-pipe degree-3 polynomial made the kernel 8 % SLOWER (the softmax warps are
+// bound by issue/latency with 2 warps per scheduler, not by MUFU throughput alone); a ones-column in V to get the row
+// sum from the MMA was correct but not faster either.
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
