@@ -19,7 +19,9 @@
 // every SM ingests (128 + block_n/2) x 128 B per k-chunk instead of (128 + block_n) x 128 B — the per-SM L2->smem
 // ingest rate is what capped the 1-CTA kernel at ~55 % tensor-pipe utilisation.
 //   warps 2..9       epilogue          -> tcgen05.ld, bias (smem staged) / per-image bias (time embedding) /
-//                                         residual (prefetched one chunk ahead) / GEGLU, fp16 stores
+//                                         residual (prefetched one chunk ahead) / GEGLU -> fp16 tile staged in
+//                                         swizzled smem -> TMA store (full 128 B lines; per-thread 16 B row-strided
+//                                         global stores made the kernel epilogue-bound for K <= ~3000)
 #pragma once
 #include "ptx.cuh"
 
@@ -29,6 +31,10 @@ struct GemmParams {
   CUtensorMap tmA0;  // source 0 activations [C0, W, H, N] (conv) or [K, M, 1, 1] (linear)
   CUtensorMap tmA1;  // source 1 (skip connection) or a copy of tmA0
   CUtensorMap tmB;   // weights [Ktot, Ncols], K contiguous
+  CUtensorMap tmC;   // output [n_valid, W, H, N], box (64 cols, bw, bh, bn), 128B swizzle   (TMA-store epilogue)
+  CUtensorMap tmC2;  // same tensor, box (32 cols, ...), no swizzle: the 32-column remainder slab of a tile
+  int tma_store;     // 1: epilogue stages the fp16 tile in smem and writes it with TMA (needs ld_out % 8 == 0)
+  int cstage_off;    // byte offset of the staging buffer inside dynamic smem
   int n_img, H, W;   // OUTPUT pixel grid
   int bw, bh, bn;    // tile box: bw*bh*bn == 128 output pixels
   int tiles_x, tiles_y, tiles_b, tiles_n;
@@ -49,6 +55,7 @@ struct GemmParams {
   int geglu;               // accumulator columns are (value, gate) pairs -> out[:, j] = v * gelu(g) (attention.py:51-58)
   int n_valid;             // valid output columns (after GEGLU halving)
   float out_scale;         // multiplies the final value (1.0 normally)
+  int dbg;                 // bring-up experiments only (LR_GEMM_DEBUG): 1 = no A loads, 2 = no B loads, 4 = no MMAs
 };
 
 constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
@@ -170,15 +177,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
             const int kch = (src0 ? kc : kc - p.kc0) * kBlockK;
             const int kb = tap * p.ctot + (src0 ? 0 : p.c0) + kch;
             const CUtensorMap* ta = src0 ? &p.tmA0 : &p.tmA1;
+            const int tx_bytes = ((p.dbg & 1) ? 0 : kATileBytes) + ((p.dbg & 2) ? 0 : stage_bytes - kATileBytes);
             if (CG == 2) {
               // the leader's barrier collects the bytes of both CTAs
-              if (leader) mbar_arrive_expect_tx(&full[s], 2 * stage_bytes);
-              tma_load_4d_2sm(a_s, ta, &full[s], kch, x0 + dx, y0 + dy, n0);
-              tma_load_2d_2sm(b_s, &p.tmB, &full[s], kb, ncol0);
+              if (leader) mbar_arrive_expect_tx(&full[s], 2 * tx_bytes);
+              if (!(p.dbg & 1)) tma_load_4d_2sm(a_s, ta, &full[s], kch, x0 + dx, y0 + dy, n0);
+              if (!(p.dbg & 2)) tma_load_2d_2sm(b_s, &p.tmB, &full[s], kb, ncol0);
             } else {
-              mbar_arrive_expect_tx(&full[s], stage_bytes);
-              tma_load_4d(a_s, ta, &full[s], kch, x0 + dx, y0 + dy, n0);
-              tma_load_2d(b_s, &p.tmB, &full[s], kb, ncol0);
+              mbar_arrive_expect_tx(&full[s], tx_bytes);
+              if (!(p.dbg & 1)) tma_load_4d(a_s, ta, &full[s], kch, x0 + dx, y0 + dy, n0);
+              if (!(p.dbg & 2)) tma_load_2d(b_s, &p.tmB, &full[s], kb, ncol0);
             }
             if (++s == p.stages) { s = 0; ph ^= 1; }
           }
@@ -204,6 +212,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
           const uint32_t b_addr = a_addr + kATileBytes;
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
+            if (p.dbg & 4) break;
             const uint64_t ad = umma_smem_desc_sw128(a_addr + k * 32, 1024, 16);
             const uint64_t bd = umma_smem_desc_sw128(b_addr + k * 32, 1024, 16);
             if (CG == 2) umma_f16_2sm(d_tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
@@ -227,6 +236,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     int as = 0;
     uint32_t aph = 0;
     const bool vec_ok = (p.ld_out % 8 == 0) && (p.residual == nullptr || p.ld_res % 8 == 0);
+    uint8_t* cstage = smem + p.cstage_off;
+    const int ocols_tile = p.geglu ? p.block_n / 2 : p.block_n;  // output columns of one tile
+    const int full_slabs = ocols_tile >> 6;                      // 64-column slabs [128 rows][128 B], swizzled
+    bool stores_pending = false;
     for (int tile = unit0; tile < num_tiles; tile += unit_step) {
       const int tn = tile % p.tiles_n;
       int tm = (tile / p.tiles_n) * CG + static_cast<int>(rank);
@@ -244,6 +257,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       const size_t grow = (static_cast<size_t>(n) * p.H + y) * p.W + x;
       const int ncol0 = tn * p.block_n;
 
+      // the previous tile's TMA stores must have drained the staging buffer before anyone overwrites it
+      if (p.tma_store && etid == 0 && stores_pending) tma_store_wait_read();
       // stage this tile's bias slice (double buffered by accumulator stage; the named barrier orders reuse)
       float* sb = sbias + as * 256;
       for (int i = etid; i < p.block_n; i += kEpiThreads)
@@ -300,7 +315,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
             float g[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) g[j] = f[2 * j] * gelu_erf(f[2 * j + 1]) * p.out_scale;
-            if (vec_ok && oc0 + 16 <= p.n_valid) {
+            if (p.tma_store) {
+              const uint4 w0 = make_uint4(pack_half2(g[0], g[1]), pack_half2(g[2], g[3]), pack_half2(g[4], g[5]),
+                                          pack_half2(g[6], g[7]));
+              const uint4 w1 = make_uint4(pack_half2(g[8], g[9]), pack_half2(g[10], g[11]), pack_half2(g[12], g[13]),
+                                          pack_half2(g[14], g[15]));
+              const int oc = c >> 1;  // output column inside the tile (multiple of 16)
+              const int slab = oc >> 6, cp0 = (oc & 63) >> 3;
+              if (slab < full_slabs) {
+                uint8_t* rowp = cstage + slab * (kBlockM * 128) + r * 128;
+                *reinterpret_cast<uint4*>(rowp + ((cp0 ^ (r & 7)) << 4)) = w0;
+                *reinterpret_cast<uint4*>(rowp + (((cp0 + 1) ^ (r & 7)) << 4)) = w1;
+              } else {
+                uint8_t* rowp = cstage + full_slabs * (kBlockM * 128) + r * 64 + (cp0 << 4);
+                *reinterpret_cast<uint4*>(rowp) = w0;
+                *reinterpret_cast<uint4*>(rowp + 16) = w1;
+              }
+            } else if (vec_ok && oc0 + 16 <= p.n_valid) {
               uint4 w0 = make_uint4(pack_half2(g[0], g[1]), pack_half2(g[2], g[3]), pack_half2(g[4], g[5]),
                                     pack_half2(g[6], g[7]));
               uint4 w1 = make_uint4(pack_half2(g[8], g[9]), pack_half2(g[10], g[11]), pack_half2(g[12], g[13]),
@@ -313,7 +344,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
             }
           } else {
             __half* o = p.out + grow * p.ld_out + col0;
-            if (vec_ok && col0 + 32 <= p.n_valid) {
+            if (p.tma_store || (vec_ok && col0 + 32 <= p.n_valid)) {
               if (res_row != nullptr) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -326,13 +357,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
                   }
                 }
               }
+              const int slab = c >> 6, cp0 = (c & 63) >> 3;
+              uint8_t* rowp = (slab < full_slabs) ? cstage + slab * (kBlockM * 128) + r * 128
+                                                  : cstage + full_slabs * (kBlockM * 128) + r * 64;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 uint4 w = make_uint4(pack_half2(f[k * 8 + 0] * p.out_scale, f[k * 8 + 1] * p.out_scale),
                                      pack_half2(f[k * 8 + 2] * p.out_scale, f[k * 8 + 3] * p.out_scale),
                                      pack_half2(f[k * 8 + 4] * p.out_scale, f[k * 8 + 5] * p.out_scale),
                                      pack_half2(f[k * 8 + 6] * p.out_scale, f[k * 8 + 7] * p.out_scale));
-                reinterpret_cast<uint4*>(o)[k] = w;
+                if (!p.tma_store) reinterpret_cast<uint4*>(o)[k] = w;
+                else if (slab < full_slabs) *reinterpret_cast<uint4*>(rowp + (((cp0 + k) ^ (r & 7)) << 4)) = w;
+                else *reinterpret_cast<uint4*>(rowp + ((cp0 + k) << 4)) = w;
               }
             } else {
               for (int j = 0; j < 32; ++j) {
@@ -351,8 +387,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       if (lane == 0) {
         if (CG == 2) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]);
       }
+      if (p.tma_store) {
+        // the fp16 tile is complete in smem: one thread writes it out with TMA (rows / columns outside the tensor are
+        // clipped by the tensor map, so partial tiles need no masking)
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
+        if (etid == 0 && tile_ok) {
+          const int oc_tile0 = p.geglu ? (ncol0 >> 1) : ncol0;
+          const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tb * p.bn;
+          for (int sl = 0; sl < full_slabs; ++sl)
+            if (oc_tile0 + sl * 64 < p.n_valid)
+              tma_store_4d(&p.tmC, cstage + sl * (kBlockM * 128), oc_tile0 + sl * 64, x0, y0, n0);
+          if ((ocols_tile & 63) != 0 && oc_tile0 + full_slabs * 64 < p.n_valid)
+            tma_store_4d(&p.tmC2, cstage + full_slabs * (kBlockM * 128), oc_tile0 + full_slabs * 64, x0, y0, n0);
+          tma_store_commit();
+          stores_pending = true;
+        }
+      }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
+    if (p.tma_store && etid == 0 && stores_pending) tma_store_wait_read();
   }
 
   tc_fence_before();

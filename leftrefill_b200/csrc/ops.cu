@@ -2,6 +2,7 @@
 #include "ops.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -48,7 +49,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // fp16 tensor map, 128B swizzle; dims innermost first; strides (bytes) for dims 1..rank-1.
 static int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
-                     const uint32_t* box, const uint32_t* estr) {
+                     const uint32_t* box, const uint32_t* estr, bool swizzle128 = true) {
   EncodeTiledFn fn = get_encode_fn();
   LR_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   LR_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA: global address must be 16-byte aligned");
@@ -56,7 +57,8 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* 
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr),
                   reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides),
                   reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(estr),
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) + " (rank " +
@@ -164,10 +166,20 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   LR_CHECK(!s.geglu || (s.ncols % 2 == 0), "conv: GEGLU needs an even column count");
   p.block_n = block_n;
   p.tiles_n = cdiv(s.ncols, block_n);
-  int stages = (232448 - 1024 - kGemmAuxBytes) / gemm_stage_bytes(block_n, cg);
+  // TMA-store epilogue: needs 16-byte aligned output rows, output-tile widths made of 64-column slabs plus at most
+  // one 32-column remainder, and (with a residual) whole 32-column chunks
+  const int n_valid = s.geglu ? s.ncols / 2 : s.ncols;
+  const int ocols_tile = s.geglu ? block_n / 2 : block_n;
+  const bool tma_store = (s.ld_out % 8 == 0) && ((ocols_tile % 64) == 0 || (ocols_tile % 64) == 32) &&
+                         (s.residual == nullptr || (n_valid % 32 == 0 && s.ld_res % 8 == 0)) &&
+                         getenv("LR_NO_TMA_STORE") == nullptr;
+  const int cstage_bytes = tma_store ? kBlockM * ocols_tile * 2 : 0;
+  int stages = (232448 - 2048 - kGemmAuxBytes - cstage_bytes) / gemm_stage_bytes(block_n, cg);
   if (stages > kMaxStages) stages = kMaxStages;
   LR_CHECK(stages >= 2, "conv: not enough shared memory for 2 stages");
   p.stages = stages;
+  p.tma_store = tma_store ? 1 : 0;
+  p.cstage_off = (stages * gemm_stage_bytes(block_n, cg) + kGemmAuxBytes + 1023) & ~1023;  // swizzle needs 1024 B
   p.bias = s.bias;
   p.bias_img = s.bias_img;
   p.ld_bias_img = s.ld_bias_img > 0 ? s.ld_bias_img : s.ncols;
@@ -178,6 +190,10 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   p.geglu = s.geglu;
   p.n_valid = s.geglu ? s.ncols / 2 : s.ncols;
   p.out_scale = 1.0f;
+  {
+    const char* e = getenv("LR_GEMM_DEBUG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   LR_CHECK(!(s.geglu && s.residual), "conv: GEGLU + residual not supported");
 
   // activations: [C, W, H, N]
@@ -208,10 +224,22 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
     uint32_t es[2] = {1, 1};
     LR_TRY(make_tmap(&p.tmB, s.w, 2, dims, str, box, es));
   }
+  if (tma_store) {
+    // output tensor as the kernel tiles it: [cols, W, H, N] over the OUTPUT pixel grid
+    uint64_t dims[4] = {static_cast<uint64_t>(n_valid), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
+                        static_cast<uint64_t>(s.n_img)};
+    uint64_t str[3] = {static_cast<uint64_t>(s.ld_out) * 2, static_cast<uint64_t>(s.ld_out) * 2 * Wo,
+                       static_cast<uint64_t>(s.ld_out) * 2 * Wo * Ho};
+    uint32_t box[4] = {64, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
+    uint32_t es[4] = {1, 1, 1, 1};
+    LR_TRY(make_tmap(&p.tmC, s.out, 4, dims, str, box, es, true));
+    box[0] = 32;
+    LR_TRY(make_tmap(&p.tmC2, s.out, 4, dims, str, box, es, false));
+  }
   const int num_units = cdiv(tiles_m, cg) * p.tiles_n;
   const int slots = sm_count() / cg;
   op->grid = (num_units < slots ? num_units : slots) * cg;
-  op->smem = gemm_smem_bytes(block_n, stages, cg);
+  op->smem = tma_store ? p.cstage_off + cstage_bytes : gemm_smem_bytes(block_n, stages, cg);
   op->block_n = block_n;
   op->stages = stages;
   op->tiles = num_units;
