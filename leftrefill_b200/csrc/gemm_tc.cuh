@@ -153,24 +153,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   const int b_rows = p.block_n / CG;
 
   if (warp == 0) {
-    // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
-        const int tn = tile % p.tiles_n;
-        int tm = min((tile / p.tiles_n) * CG + static_cast<int>(rank), tiles_m - 1);
-        const int tx = tm % p.tiles_x;
-        tm /= p.tiles_x;
-        const int ty = tm % p.tiles_y;
-        const int tb = tm / p.tiles_y;
-        const int x0 = tx * p.bw * p.stride, y0 = ty * p.bh * p.stride, n0 = tb * p.bn;
-        const int ncol0 = tn * p.block_n + static_cast<int>(rank) * b_rows;  // this CTA's share of the weight rows
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
-          const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
-          for (int kc = 0; kc < p.kc0 + p.kc1; ++kc) {
-            mbar_wait(&empty[s], ph ^ 1);
+    // ------------------------------- TMA producer (whole warp loops, one elected lane issues) ---------------
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+      const int tn = tile % p.tiles_n;
+      int tm = min((tile / p.tiles_n) * CG + static_cast<int>(rank), tiles_m - 1);
+      const int tx = tm % p.tiles_x;
+      tm /= p.tiles_x;
+      const int ty = tm % p.tiles_y;
+      const int tb = tm / p.tiles_y;
+      const int x0 = tx * p.bw * p.stride, y0 = ty * p.bh * p.stride, n0 = tb * p.bn;
+      const int ncol0 = tn * p.block_n + static_cast<int>(rank) * b_rows;  // this CTA's share of the weight rows
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+        const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+        for (int kc = 0; kc < p.kc0 + p.kc1; ++kc) {
+          mbar_wait(&empty[s], ph ^ 1);
+          if (elect_one()) {
             uint8_t* a_s = smem + s * stage_bytes;
             uint8_t* b_s = a_s + kATileBytes;
             const bool src0 = kc < p.kc0;
@@ -188,15 +188,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
               if (!(p.dbg & 1)) tma_load_4d(a_s, ta, &full[s], kch, x0 + dx, y0 + dy, n0);
               if (!(p.dbg & 2)) tma_load_2d(b_s, &p.tmB, &full[s], kb, ncol0);
             }
-            if (++s == p.stages) { s = 0; ph ^= 1; }
           }
+          __syncwarp();
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0 && leader) {
+    // ------------------------------- MMA issuer (whole warp loops, one elected lane issues) ----------------
+    if (leader) {
       const uint32_t idesc = umma_idesc_f16(kBlockM * CG, p.block_n, 0);
+      const uint32_t desc_hi = umma_desc_hi_sw128(1024);
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem), 16);
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(smem) + kATileBytes, 16);
+      const uint32_t stage_units = static_cast<uint32_t>(stage_bytes) >> 4;
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -208,20 +213,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint32_t b_addr = a_addr + kATileBytes;
+          if (elect_one()) {
+            const uint32_t a_lo = a_lo0 + s * stage_units;
+            const uint32_t b_lo = b_lo0 + s * stage_units;
+            if (!(p.dbg & 4)) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            if (p.dbg & 4) break;
-            const uint64_t ad = umma_smem_desc_sw128(a_addr + k * 32, 1024, 16);
-            const uint64_t bd = umma_smem_desc_sw128(b_addr + k * 32, 1024, 16);
-            if (CG == 2) umma_f16_2sm(d_tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
-            else umma_f16(d_tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kBlockK / 16; ++k) {  // +32 bytes (= 2 descriptor units) per 16-element K step
+                const uint64_t ad = umma_desc_make(desc_hi, a_lo + 2 * k);
+                const uint64_t bd = umma_desc_make(desc_hi, b_lo + 2 * k);
+                if (CG == 2) umma_f16_2sm(d_tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+                else umma_f16(d_tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+              }
+            }
+            if (CG == 2) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);
           }
-          if (CG == 2) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);
+          __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        if (CG == 2) umma_commit_2sm(&tfull[as]); else umma_commit(&tfull[as]);
+        if (elect_one()) {
+          if (CG == 2) umma_commit_2sm(&tfull[as]); else umma_commit(&tfull[as]);
+        }
+        __syncwarp();
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }

@@ -65,6 +65,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a converged warp. Issue loops are executed by the WHOLE warp with warp-uniform operands and only the
+// tcgen05 / TMA instruction itself is predicated on this: operands then stay in uniform registers. (Running the loop
+// inside `if (lane == 0)` made ptxas emit ELECT + 5 x R2UR.BROADCAST + descriptor re-computation per MMA, ~130 issue
+// cycles each, which capped both the GEMM and the attention kernel — ncu source view, round 1.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / UMMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -267,6 +281,17 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
+}
+// Same descriptor split into a constant high word and an address-dependent low word, so that advancing along K or to
+// the next pipeline stage is a single 32-bit add on the low word (addresses are in 16-byte units).
+__device__ __forceinline__ uint32_t umma_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_make(uint32_t hi, uint32_t lo) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 // Instruction descriptor for kind::f16: fp16 A/B, fp32 D.
 //   [4,6) D format (1 = f32)  [7,10) A format (0 = f16)  [10,13) B format (0 = f16)
