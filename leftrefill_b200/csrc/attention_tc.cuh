@@ -112,42 +112,52 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp < 4) {
-    if (warp == 0 && lane == 0) {
-      // ------------------------------- TMA producer -------------------------------
-      mbar_arrive_expect_tx(q_full, ntq * kAttnTileBytes);
-      tma_load_3d(q_s, &p.tmQ, q_full, p.q_col0 + head * kAttnD, qb * kAttnQBlock, b);
-      if (ntq == 2)
-        tma_load_3d(q_s + kAttnTileBytes, &p.tmQ, q_full, p.q_col0 + head * kAttnD, qb * kAttnQBlock + kAttnTile, b);
+    if (warp == 0) {
+      // ------------------------------- TMA producer (whole warp loops, one elected lane issues) ---------------
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, ntq * kAttnTileBytes);
+        tma_load_3d(q_s, &p.tmQ, q_full, p.q_col0 + head * kAttnD, qb * kAttnQBlock, b);
+        if (ntq == 2)
+          tma_load_3d(q_s + kAttnTileBytes, &p.tmQ, q_full, p.q_col0 + head * kAttnD, qb * kAttnQBlock + kAttnTile, b);
+      }
+      __syncwarp();
       for (int j = 0; j < ntiles; ++j) {
         const int s = j % kAttnStages;
         const uint32_t ph = (j / kAttnStages) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * kAttnTileBytes);
-        tma_load_3d(k_s + s * kAttnTileBytes, &p.tmK, &kv_full[s], p.k_col0 + head * kAttnD, j * kAttnTile, b);
-        tma_load_3d(v_s + s * kAttnTileBytes, &p.tmV, &kv_full[s], p.v_col0 + head * kAttnD, j * kAttnTile, b);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&kv_full[s], 2 * kAttnTileBytes);
+          tma_load_3d(k_s + s * kAttnTileBytes, &p.tmK, &kv_full[s], p.k_col0 + head * kAttnD, j * kAttnTile, b);
+          tma_load_3d(v_s + s * kAttnTileBytes, &p.tmV, &kv_full[s], p.v_col0 + head * kAttnD, j * kAttnTile, b);
+        }
+        __syncwarp();
       }
-    } else if (warp == 1 && lane == 0) {
-      // ------------------------------- MMA issuer ---------------------------------
+    } else if (warp == 1) {
+      // ------------------------------- MMA issuer (whole warp loops, one elected lane issues) ----------------
+      // Descriptors are a constant high word plus a 32-bit low word (address >> 4) kept in uniform registers: advancing
+      // along K is one add. (Building each descriptor from scratch inside `if (lane == 0)` cost ~130 issue cycles per
+      // MMA — 24 MMAs per KV tile pair = the 3000-cycle period every earlier version of this kernel was stuck at.)
       const uint32_t idesc_s = umma_idesc_f16(128, kAttnTile, 0);  // S: N = 128 keys, K-major B
       const uint32_t idesc_o = umma_idesc_f16(128, kAttnD, 1);     // O: N = 64 channels, MN-major B (V)
-      const uint32_t q_addr = smem_u32(q_s);
-      auto issue_s = [&](int t, int stage) {
-        const uint32_t k_addr = smem_u32(k_s + stage * kAttnTileBytes);
-        const uint32_t qa = q_addr + t * kAttnTileBytes;
+      const uint32_t desc_hi = umma_desc_hi_sw128(1024);
+      const uint32_t q_lo = umma_desc_lo(smem_u32(q_s), 16);
+      const uint32_t k_lo = umma_desc_lo(smem_u32(k_s), 16);
+      const uint32_t v_lo = umma_desc_lo(smem_u32(v_s), 16);
+      constexpr uint32_t kTileUnits = kAttnTileBytes >> 4;
+      auto issue_s = [&](int t, int stage) {  // S_t = Q_t K^T : 4 k-steps of 16 channels (32 B = 2 units each)
 #pragma unroll
         for (int k = 0; k < kAttnD / 16; ++k) {
-          umma_f16(tmem_base + kTmemS + t * 128, umma_smem_desc_sw128(qa + k * 32, 1024, 16),
-                   umma_smem_desc_sw128(k_addr + k * 32, 1024, 16), idesc_s, k != 0 ? 1u : 0u);
+          umma_f16(tmem_base + kTmemS + t * 128, umma_desc_make(desc_hi, q_lo + t * kTileUnits + 2 * k),
+                   umma_desc_make(desc_hi, k_lo + stage * kTileUnits + 2 * k), idesc_s, k != 0 ? 1u : 0u);
         }
         umma_commit(&s_full[t]);
       };
-      auto issue_pv = [&](int t, int stage, bool accumulate) {
-        const uint32_t v_addr = smem_u32(v_s + stage * kAttnTileBytes);
+      auto issue_pv = [&](int t, int stage, uint32_t accumulate) {
+        // A = P_t from TMEM (8 columns = 16 fp16 per k step); B = 16 token rows of V (16 x 128 B = 128 units), MN-major
 #pragma unroll
         for (int k = 0; k < kAttnTile / 16; ++k) {
-          // A = P_t from TMEM (8 columns = 16 fp16 per k step); B = 16 token rows of V (128 B each), MN-major
           umma_f16_ts(tmem_base + kTmemO + t * 64, tmem_base + kTmemP + t * 64 + k * 8,
-                      umma_smem_desc_sw128(v_addr + k * 16 * 128, 1024, 16), idesc_o, (accumulate || k != 0) ? 1u : 0u);
+                      umma_desc_make(desc_hi, v_lo + stage * kTileUnits + k * 128), idesc_o, (accumulate | k) != 0 ? 1u : 0u);
         }
         umma_commit(&pv_done[t]);
       };
@@ -164,32 +174,41 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         for (int t = 0; t < 2; ++t) {
           if (t >= ntq) continue;
           const int j = ns[t];
-          if (j < ntiles && j - npv[t] < 1 + 1 &&  // S_t(j) may run ahead of PV_t by one tile (S is single-buffered)
-              mbar_test(&kv_full[j % kAttnStages], (j / kAttnStages) & 1) &&
-              (j == 0 || mbar_test(&s_empty[t], (j - 1) & 1))) {
+          bool go_s = false;
+          if (j < ntiles && j - npv[t] < 2)  // S_t(j) may run one tile ahead of PV_t (S is single-buffered)
+            go_s = mbar_test(&kv_full[j % kAttnStages], (j / kAttnStages) & 1) &&
+                   (j == 0 || mbar_test(&s_empty[t], (j - 1) & 1));
+          go_s = __shfl_sync(0xffffffffu, go_s ? 1 : 0, 0) != 0;  // warp-uniform decision
+          if (go_s) {
             tc_fence_after();
-            issue_s(t, j % kAttnStages);
+            if (elect_one()) issue_s(t, j % kAttnStages);
+            __syncwarp();
             ns[t] = j + 1;
             progress = true;
           }
           const int i = npv[t];
-          if (i < ns[t] && mbar_test(&p_full[t], i & 1)) {
+          bool go_pv = (i < ns[t]) && mbar_test(&p_full[t], i & 1);
+          go_pv = __shfl_sync(0xffffffffu, go_pv ? 1 : 0, 0) != 0;
+          if (go_pv) {
             tc_fence_after();
-            issue_pv(t, i % kAttnStages, i > 0);
+            if (elect_one()) issue_pv(t, i % kAttnStages, i > 0 ? 1u : 0u);
+            __syncwarp();
             npv[t] = i + 1;
             progress = true;
           }
         }
         const int done = (ntq == 2) ? min(npv[0], npv[1]) : npv[0];
         while (freed < done) {
-          umma_commit(&kv_empty[freed % kAttnStages]);
+          if (elect_one()) umma_commit(&kv_empty[freed % kAttnStages]);
+          __syncwarp();
           ++freed;
         }
         if (progress) {
           t0 = clock64();
         } else if (clock64() - t0 > 4000000000LL) {
-          printf("lr_b200: attention MMA issue loop stalled block=(%d,%d,%d) ns=%d,%d npv=%d,%d\n", blockIdx.x, blockIdx.y,
-                 blockIdx.z, ns[0], ns[1], npv[0], npv[1]);
+          if (lane == 0)
+            printf("lr_b200: attention MMA issue loop stalled block=(%d,%d,%d) ns=%d,%d npv=%d,%d\n", blockIdx.x,
+                   blockIdx.y, blockIdx.z, ns[0], ns[1], npv[0], npv[1]);
           __trap();
         }
       }
