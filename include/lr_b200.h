@@ -69,6 +69,14 @@ int lr_unet_set_context(lr_unet* h, const float* context, int n, int L, void* st
  * out [n, out_channels, H, W] fp32 NCHW. */
 int lr_unet_forward(lr_unet* h, const float* x, const int64_t* timesteps, const float* context, int L, float* out,
                     int n, int H, int W, void* stream);
+/* Classifier-free-guidance pair (p_sample_ddim, ldm/models/diffusion/ddim.py:317-343): the UNet batch is
+ * [uncond | cond] with IDENTICAL x, timesteps and c_concat in both halves; only the cross-attention context differs.
+ * x [n_canvas, in_channels, H, W], timesteps [n_canvas]; the 2*n_canvas contexts (uncond first) must have been cached
+ * with lr_unet_set_context; out [2*n_canvas, out_channels, H, W]. Everything before the first cross-attention (input
+ * conv, first ResBlock, first self-attention) is computed once and replicated; the result is bit-identical to
+ * lr_unet_forward on the doubled batch. */
+int lr_unet_forward_cfg_pair(lr_unet* h, const float* x, const int64_t* timesteps, float* out, int n_canvas, int H,
+                             int W, void* stream);
 /* Per-op CUDA-event timing of forward (bench.py's roofline): when enabled, every forward records an event between
  * plan steps on `stream`. lr_unet_read_profile waits for the last profiled forward and sums by kernel class:
  * 0 = gemm_conv_kernel (all convs + linears), 1 = attention_kernel, 2 = GroupNorm kernels, 3 = LayerNorm, 4 = other. */

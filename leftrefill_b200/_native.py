@@ -49,6 +49,7 @@ SIGNATURES = {
     "lr_unet_set_context": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "lr_unet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                 c_void_p]),
+    "lr_unet_forward_cfg_pair": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lr_unet_set_profiling": (c_int, [c_void_p, c_int]),
     "lr_unet_read_profile": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int)]),
     "lr_unet_num_steps": (c_int, [c_void_p]),

@@ -476,13 +476,15 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
 }
 
 // timestep_embedding (util.py:154-174): [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(1e4) i / half), fp32.
-__global__ void timestep_embedding_kernel(const long long* __restrict__ t, int n, int dim, float* __restrict__ out) {
+// `t` holds t_count entries; row b uses t[b % t_count] (the CFG-pair forward passes one timestep per canvas).
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, int t_count, int n, int dim,
+                                          float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (i >= n * half) return;
   const int b = i / half, j = i % half;
   const float freq = expf(-logf(10000.0f) * static_cast<float>(j) / static_cast<float>(half));
-  const float arg = static_cast<float>(t[b]) * freq;
+  const float arg = static_cast<float>(t[b % t_count]) * freq;
   out[static_cast<size_t>(b) * dim + j] = cosf(arg);
   out[static_cast<size_t>(b) * dim + half + j] = sinf(arg);
   if ((dim & 1) && j == 0) out[static_cast<size_t>(b) * dim + dim - 1] = 0.f;

@@ -124,6 +124,8 @@ struct lr_unet {
 
   // ---- plan state ----
   int pn = 0, ph = 0, pw = 0;  // planned shape
+  int pshared = 0;             // planned with the CFG-pair shared prefix
+  int shared_ns = 0;           // > 0 while planning the shared prefix: number of images actually computed
   Pool pool;
   struct Step {
     std::function<int(cudaStream_t)> fn;
@@ -463,10 +465,25 @@ struct lr_unet {
 
   float* emb_all = nullptr;  // [n, emb_total]: every ResBlock's emb_layers output
 
+  // CFG pair: the first half of a [n, ...] buffer was computed once for both halves; replicate it
+  void add_dup_half(__half* p, size_t half_elems) {
+    push([=](cudaStream_t st) {
+      cudaError_t e = cudaMemcpyAsync(p + half_elems, p, half_elems * sizeof(__half), cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) {
+        set_error(std::string("cudaMemcpyAsync(dup half): ") + cudaGetErrorString(e));
+        return 1;
+      }
+      return 0;
+    });
+  }
+
   // ResBlock._forward (openaimodel.py:254-274), x = concat(x0, x1) when x1.p != nullptr
-  int plan_res(const ResW& r, Act x0, Act x1, int n, Act* out) {
+  int plan_res(const ResW& r, Act x0, Act x1, int n_full, Act* out) {
     const int Hh = x0.H, Ww = x0.W, P = Hh * Ww;
+    // inside the shared CFG prefix only the first shared_ns images are computed (buffers stay full size)
+    const int n = shared_ns > 0 ? shared_ns : n_full;
     const size_t M = static_cast<size_t>(n) * P;
+    const size_t Mfull = static_cast<size_t>(n_full) * P;
     LR_CHECK(x0.C + x1.C == r.cin, "resblock: channel mismatch");
     __half *xn, *h, *hn, *o, *skip = nullptr;
     LR_TRY(acquire_h(M * r.cin, &xn));
@@ -521,7 +538,7 @@ struct lr_unet {
       LR_CHECK(x1.p == nullptr, "resblock: identity skip with concat input");
       resid = x0.p;
     }
-    LR_TRY(acquire_h(M * r.cout, &o));
+    LR_TRY(acquire_h(Mfull * r.cout, &o));
     {
       ConvSpec s;
       s.a0 = hn;
@@ -551,23 +568,36 @@ struct lr_unet {
   }
 
   // SpatialTransformer.forward + BasicTransformerBlock._forward (attention.py:393-419, 279-283)
-  int plan_st(const STW& s, Act x, int n, Act* out) {
+  int plan_st(const STW& s, Act x, int n_full, Act* out) {
     const int C = s.C, P = x.H * x.W;
-    const int M = n * P;
+    const int Mfull = n_full * P;
     LR_CHECK(x.C == C, "spatial transformer: channel mismatch");
+    // CFG pair: everything up to and including the FIRST self-attention is independent of the context, so inside the
+    // shared prefix it is computed for the first shared_ns images only and then replicated (ddim.py:317-326 feeds both
+    // halves the same x / t / c_concat; only c_crossattn differs). Buffers are full size throughout.
+    int n = shared_ns > 0 ? shared_ns : n_full;
+    int M = n * P;
     __half *xn, *h, *t, *qkv, *a, *g, *o;
-    LR_TRY(acquire_h(static_cast<size_t>(M) * C, &xn));
+    LR_TRY(acquire_h(static_cast<size_t>(Mfull) * C, &xn));
     LR_TRY(add_gn(x.p, C, nullptr, 0, n, P, 1e-6f, F(s.gn_g), F(s.gn_b), 0, xn));
-    LR_TRY(acquire_h(static_cast<size_t>(M) * C, &h));
+    LR_TRY(acquire_h(static_cast<size_t>(Mfull) * C, &h));
     LR_TRY(add_linear(xn, M, C, H(s.pin_w), C, F(s.pin_b), nullptr, 0, h, C, 0));
     pool.release(xn);
-    LR_TRY(acquire_h(static_cast<size_t>(M) * C, &t));
-    LR_TRY(acquire_h(static_cast<size_t>(M) * C, &a));
+    LR_TRY(acquire_h(static_cast<size_t>(Mfull) * C, &t));
+    LR_TRY(acquire_h(static_cast<size_t>(Mfull) * C, &a));
+    bool first_block = true;
     for (const TBlockW& b : s.blocks) {
+      if (!first_block && n != n_full) {  // depth > 1: only block 0's self-attention is shared
+        add_dup_half(h, static_cast<size_t>(M) * C);
+        add_dup_half(x.p, static_cast<size_t>(M) * C);
+        n = n_full;
+        M = Mfull;
+      }
       // self-attention: x = attn1(norm1(x)) + x
       LR_TRY(add_ln(h, M, C, F(b.ln1_g), F(b.ln1_b), t));
       LR_TRY(acquire_h(static_cast<size_t>(M) * 3 * C, &qkv));
       LR_TRY(add_linear(t, M, C, H(b.qkv_w), 3 * C, nullptr, nullptr, 0, qkv, 3 * C, 0));
+      LR_CHECK(!(shared_ns > 0 && cfg.view_num > 1), "CFG-pair sharing is not implemented for the multiview UNet");
       if (cfg.view_num > 1 && cfg.concat_target) {
         // multiview_attention.py:436-462: rows are stitched [ref_i | target] canvases; attend over
         // [target(row 0), ref_1..ref_v] and write the target block back to every row.
@@ -623,6 +653,13 @@ struct lr_unet {
         pool.release(qkv);
         LR_TRY(add_linear(a, M, C, H(b.out1_w), C, F(b.out1_b), h, C, h, C, 0));
       }
+      if (first_block && n != n_full) {  // end of the shared prefix: replicate the residual stream and the ST input
+        add_dup_half(h, static_cast<size_t>(M) * C);
+        add_dup_half(x.p, static_cast<size_t>(M) * C);
+        n = n_full;
+        M = Mfull;
+      }
+      first_block = false;
       // cross-attention against the cached context K/V
       LR_TRY(add_ln(h, M, C, F(b.ln2_g), F(b.ln2_b), t));
       __half* q2;
@@ -767,8 +804,10 @@ struct lr_unet {
     return 0;
   }
 
-  int build_plan(int n, int Hh, int Ww) {
-    if (pn == n && ph == Hh && pw == Ww) return 0;
+  int build_plan(int n, int Hh, int Ww, int shared = 0) {
+    if (pn == n && ph == Hh && pw == Ww && pshared == shared) return 0;
+    LR_CHECK(!shared || n % 2 == 0, "CFG-pair forward needs an even UNet batch");
+    const int ns = shared ? n / 2 : n;  // images whose x / t are distinct
     steps.clear();
     conv_ops.clear();
     attn_ops.clear();
@@ -801,7 +840,7 @@ struct lr_unet {
     LR_TRY(acquire_f(static_cast<size_t>(n) * temb, &emb));
     LR_TRY(acquire_f(static_cast<size_t>(n) * emb_total, &emb_all));
     push([=](cudaStream_t st) {
-      return launch_timestep_embedding(reinterpret_cast<const long long*>(this->in_t), n, mc, tsin, st);
+      return launch_timestep_embedding(reinterpret_cast<const long long*>(this->in_t), ns, n, mc, tsin, st);
     });
     {
       const __half* w0 = H(te0_w);
@@ -818,26 +857,42 @@ struct lr_unet {
     }
     // --- input conv: im2col of the NCHW fp32 boundary tensor, then a GEMM ---
     const size_t M0 = static_cast<size_t>(n) * Hh * Ww;
+    const size_t M0s = static_cast<size_t>(ns) * Hh * Ww;  // rows computed by the input conv (x is [ns, ...])
     __half* col;
-    LR_TRY(acquire_h(M0 * kpad_in, &col));
+    LR_TRY(acquire_h(M0s * kpad_in, &col));
     {
       const int cin = cfg.in_channels, kp = kpad_in;
       push(
-          [=](cudaStream_t st) { return launch_im2col_nchw_f32(this->in_x, n, cin, Hh, Ww, kp, col, st); });
+          [=](cudaStream_t st) { return launch_im2col_nchw_f32(this->in_x, ns, cin, Hh, Ww, kp, col, st); });
     }
     Act h;
     {
       __half* o;
       LR_TRY(acquire_h(M0 * mc, &o));
       const ConvW& c = convs[conv_in_idx];
-      LR_TRY(add_linear(col, static_cast<int>(M0), kpad_in, H(c.w), mc, F(c.b), nullptr, 0, o, mc, 0));
+      LR_TRY(add_linear(col, static_cast<int>(M0s), kpad_in, H(c.w), mc, F(c.b), nullptr, 0, o, mc, 0));
       h = Act{o, mc, Hh, Ww};
     }
     pool.release(col);
     std::vector<Act> hs{h};
     for (size_t i = 1; i < input_blocks.size(); ++i) {
       Act o;
-      LR_TRY(plan_block(input_blocks[i], h, Act{}, n, &o, false));
+      if (shared && i == 1) {
+        // shared CFG prefix: ResBlock (+ the first self-attention) of input_blocks.1 on the first half only
+        const bool has_st = input_blocks[1].size() > 1 && input_blocks[1][1].kind == N_ST;
+        shared_ns = ns;
+        if (has_st) {
+          LR_TRY(plan_block(input_blocks[1], h, Act{}, n, &o, false));  // plan_st leaves the prefix after attn1
+          shared_ns = 0;
+        } else {
+          LR_TRY(plan_block(input_blocks[1], h, Act{}, n, &o, false));
+          shared_ns = 0;
+          add_dup_half(o.p, M0s * o.C);
+        }
+        add_dup_half(hs[0].p, M0s * mc);  // conv_in output: also a skip connection for both halves
+      } else {
+        LR_TRY(plan_block(input_blocks[i], h, Act{}, n, &o, false));
+      }
       hs.push_back(o);
       h = o;
     }
@@ -884,6 +939,7 @@ struct lr_unet {
     pn = n;
     ph = Hh;
     pw = Ww;
+    pshared = shared;
     return 0;
   }
 };
@@ -1047,6 +1103,25 @@ int lr_unet_step_info(lr_unet* h, int i, double* ms, double* flops, int* cls, ch
     strncpy(desc, h->steps[i].desc.c_str(), desc_len - 1);
     desc[desc_len - 1] = 0;
   }
+  return 0;
+}
+
+int lr_unet_forward_cfg_pair(lr_unet* h, const float* x, const int64_t* timesteps, float* out, int n_canvas, int H,
+                             int W, void* stream) {
+  LR_CHECK(h && x && timesteps && out, "lr_unet_forward_cfg_pair: null argument");
+  LR_CHECK(n_canvas > 0 && H > 0 && W > 0, "lr_unet_forward_cfg_pair: empty input");
+  const int missing = lr_unet_missing_weights(h);
+  LR_CHECK(missing == 0, "lr_unet_forward_cfg_pair: " + std::to_string(missing) + " weights not uploaded");
+  const int div = 1 << (h->cfg.num_levels - 1);
+  LR_CHECK(H % div == 0 && W % div == 0, "lr_unet_forward_cfg_pair: H and W must be divisible by 2^(levels-1)");
+  LR_CHECK(h->ctx_valid && h->ctx_n == 2 * n_canvas,
+           "lr_unet_forward_cfg_pair: lr_unet_set_context must have cached 2*n_canvas contexts (uncond first)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LR_TRY(h->build_plan(2 * n_canvas, H, W, 1));
+  h->in_x = x;
+  h->in_t = timesteps;
+  h->out_y = out;
+  for (auto& s : h->steps) LR_TRY(s.fn(st));
   return 0;
 }
 

@@ -270,12 +270,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       const int ncol0 = tn * p.block_n;
 
       // the previous tile's TMA stores must have drained the staging buffer before anyone overwrites it
-      if (p.tma_store && etid == 0 && stores_pending) tma_store_wait_read();
+      if (p.tma_store && etid == 0 && stores_pending && !(p.dbg & 8)) tma_store_wait_read();
       // stage this tile's bias slice (double buffered by accumulator stage; the named barrier orders reuse)
       float* sb = sbias + as * 256;
-      for (int i = etid; i < p.block_n; i += kEpiThreads)
-        sb[i] = (p.bias != nullptr && ncol0 + i < p.ncols) ? __ldg(p.bias + ncol0 + i) : 0.f;
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      if (!(p.dbg & 16)) {
+        for (int i = etid; i < p.block_n; i += kEpiThreads)
+          sb[i] = (p.bias != nullptr && ncol0 + i < p.ncols) ? __ldg(p.bias + ncol0 + i) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      }
 
       // residual of the first chunk is fetched before the accumulator is ready (it does not depend on the MMA)
       const bool fast = vec_ok && row_ok && !p.geglu;
@@ -293,7 +295,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
       for (; c < p.block_n; c += 64) {
         uint32_t v[32];
-        tmem_ld32(t_row + c, v);
+        if (p.dbg & 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0;
+        } else {
+          tmem_ld32(t_row + c, v);
+        }
         uint4 rcur[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) rcur[k] = rnext[k];
@@ -404,7 +411,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         // clipped by the tensor map, so partial tiles need no masking)
         fence_proxy_async_smem();
         asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
-        if (etid == 0 && tile_ok) {
+        if (etid == 0 && tile_ok && !(p.dbg & 8)) {
           const int oc_tile0 = p.geglu ? (ncol0 >> 1) : ncol0;
           const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tb * p.bn;
           for (int sl = 0; sl < full_slabs; ++sl)

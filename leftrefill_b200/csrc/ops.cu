@@ -340,9 +340,11 @@ int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_i
   LR_CHECK(C % groups == 0, "groupnorm: channels not divisible by groups");
   LR_CHECK(C / 8 <= kNormThreads, "groupnorm: too many channels");
   LR_CHECK(x1 != nullptr || c1 == 0, "groupnorm: c1 without x1");
-  int chunk = P / 64;
+  // ~256 CTAs per image batch of 8: each CTA streams a long pixel run so that its tail (smem reduction, fp64 atomics,
+  // ticket) is amortised
+  int chunk = (P * n_img) / 256;
   if (chunk < 16) chunk = 16;
-  if (chunk > 256) chunk = 256;
+  if (chunk > 512) chunk = 512;
   const dim3 grid(cdiv(P, chunk), n_img);
   if (!scratch_is_zero) LR_CUDA(cudaMemsetAsync(scratch, 0, gn_scratch_bytes(n_img, groups), st));
   const int rpi = kNormThreads / (C / 8);
@@ -433,9 +435,9 @@ int launch_small_linear(const float* in, int ld_in, int n_rows, int K, const __h
   LR_LAUNCHED();
   return 0;
 }
-int launch_timestep_embedding(const long long* t, int n, int dim, float* out, cudaStream_t st) {
+int launch_timestep_embedding(const long long* t, int t_count, int n, int dim, float* out, cudaStream_t st) {
   const int total = n * (dim / 2);
-  timestep_embedding_kernel<<<cdiv(total, 256), 256, 0, st>>>(t, n, dim, out);
+  timestep_embedding_kernel<<<cdiv(total, 256), 256, 0, st>>>(t, t_count, n, dim, out);
   LR_LAUNCHED();
   return 0;
 }

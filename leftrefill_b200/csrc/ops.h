@@ -102,7 +102,7 @@ int launch_nhwc_to_nchw_f32(const __half* x, int ld, int n_img, int cout, int H,
 int launch_nchw_f32_to_nhwc(const float* x, int n_img, int C, int H, int W, __half* out, cudaStream_t st);
 int launch_small_linear(const float* in, int ld_in, int n_rows, int K, const __half* w, const float* bias, int n_out,
                         int silu_in, int silu_out, float* out, int ld_out, cudaStream_t st);
-int launch_timestep_embedding(const long long* t, int n, int dim, float* out, cudaStream_t st);
+int launch_timestep_embedding(const long long* t, int t_count, int n, int dim, float* out, cudaStream_t st);
 int launch_ddim_update(const float* x, const float* e_u, const float* e_c, const float* noise, float cfg, float a_t,
                        float a_prev, float sigma, float sqrt_one_minus_at, float temperature, size_t n, float* x_prev,
                        float* pred_x0, cudaStream_t st);

@@ -164,11 +164,17 @@ class DDIMSampler(object):
             if use_cfg:
                 cc = torch.cat([unconditional_conditioning["c_crossattn"][0], cc])
                 c_cat = torch.cat([unconditional_conditioning["c_concat"][0].float(), c_cat])
+            # both CFG halves see the same x, t and (in every LeftRefill driver) the same c_concat: then everything
+            # before the first cross-attention is computed once (lr_unet_forward_cfg_pair)
+            pair = (use_cfg and unet.view_num == 1 and
+                    torch.equal(unconditional_conditioning["c_concat"][0], cond["c_concat"][0]))
+            if pair:
+                c_cat = cond["c_concat"][0].float()
             nb = c_cat.shape[0]
             unet.set_context(cc)
             xc = torch.empty(nb, img.shape[1] + c_cat.shape[1], shape[2], shape[3], dtype=torch.float32, device=device)
             xc[:, img.shape[1]:] = c_cat
-            staged = (xc, nb)
+            staged = (xc, nb, pair)
 
         x = img.float()
         for i, step in enumerate(time_range):
@@ -183,10 +189,14 @@ class DDIMSampler(object):
                 unconditional_guidance_scale = ucg_schedule[i]
                 use_cfg = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
             if staged is not None:
-                xc, nb = staged
-                xc[:, :x.shape[1]] = torch.cat([x, x]) if use_cfg else x
+                xc, nb, pair = staged
                 t_in = torch.full((nb,), int(step), device=device, dtype=torch.long)
-                e = unet.forward_native(xc, t_in, None)
+                if pair and use_cfg:
+                    xc[:, :x.shape[1]] = x
+                    e = unet.forward_native_cfg_pair(xc, t_in)
+                else:
+                    xc[:, :x.shape[1]] = torch.cat([x, x]) if use_cfg else x
+                    e = unet.forward_native(xc, t_in, None)
                 e_u, e_c = (e[:b], e[b:]) if use_cfg else (e, None)
             else:
                 e_u, e_c = self._apply_model(x, cond, int(step), unconditional_conditioning, use_cfg)

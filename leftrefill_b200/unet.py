@@ -308,6 +308,15 @@ class UNetModel(nn.Module):
                                         hh, ww, N.current_stream()), "lr_unet_forward")
         return out
 
+    def forward_native_cfg_pair(self, x, timesteps):
+        """CFG pair [uncond | cond] sharing x / timesteps: x [B, C, H, W] -> eps [2B, out, H, W]. The 2B contexts (uncond
+        first) must have been cached with set_context. Bit-identical to forward_native on the doubled batch."""
+        n, c, hh, ww = x.shape
+        out = torch.empty(2 * n, self.out_channels, hh, ww, dtype=torch.float32, device=x.device)
+        N.check(N.lib().lr_unet_forward_cfg_pair(self.engine(), N.ptr(x), N.ptr(timesteps), N.ptr(out), n, hh, ww,
+                                                 N.current_stream()), "lr_unet_forward_cfg_pair")
+        return out
+
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         assert y is None, "must specify y if and only if the model is class-conditional"
         assert timesteps is not None and context is not None

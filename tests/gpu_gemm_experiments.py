@@ -24,9 +24,26 @@ if len(sys.argv) > 1:
         e1.record()
         torch.cuda.synchronize()
         out.append(f"{f}: {e0.elapsed_time(e1) * 100:6.1f}us")
-    print(f"dbg={os.environ.get('LR_GEMM_DEBUG', '0')}  " + "  ".join(out), flush=True)
+    print(f"dbg={os.environ.get('LR_GEMM_DEBUG', '0')}  conv320: " + "  ".join(out), flush=True)
+    a = torch.randn(65536, 320, device="cuda").half()
+    w = torch.randn(320, 320, device="cuda").half() * 0.05
+    r = torch.randn(65536, 320, device="cuda").half()
+    out = []
+    for f, res in ((1160, None), (2160, None), (1160, r), (2160, r), (1064, None), (1256, None)):
+        fn = lambda: ops.linear(a, w, bias=b, residual=res, force_block_n=f)
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out.append(f"{f}{'+res' if res is not None else ''}: {e0.elapsed_time(e1) * 100:6.1f}us")
+    print(f"dbg={os.environ.get('LR_GEMM_DEBUG', '0')}  lin320: " + "  ".join(out), flush=True)
 else:
-    for dbg in (0, 1, 2, 3, 4, 5, 6, 7):
+    for dbg in (0, 7, 7 + 8, 7 + 16, 7 + 32, 7 + 8 + 16, 7 + 8 + 16 + 32):
         env = dict(os.environ, LR_GEMM_DEBUG=str(dbg))
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "run"], env=env, capture_output=True, text=True,
                            timeout=120)

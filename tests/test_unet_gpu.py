@@ -164,6 +164,25 @@ def test_sampler_generic_path_equals_fast_path(small):
     assert torch.equal(outs[0][1], outs[1][1])  # both routes consumed the same number of random draws
 
 
+def _cfg_pair_check(m, cfg, hw, nb):
+    dev = "cuda"
+    xT, c_cat, ctx, uc = synthetic_inputs(nb, h=hw[0], w=hw[1], ctx_dim=cfg["context_dim"], device=dev)
+    xh = torch.cat([xT, c_cat], dim=1).contiguous()                       # [B, 9, H, W]
+    t = torch.full((nb,), 741, dtype=torch.long, device=dev)
+    with torch.no_grad():
+        m.sync_weights()
+        m.set_context(torch.cat([uc, ctx]).contiguous())
+        pair = m.forward_native_cfg_pair(xh, t)
+        full = m.forward_native(torch.cat([xh, xh]).contiguous(), torch.cat([t, t]), None)
+    assert pair.shape == full.shape
+    assert torch.equal(pair, full), (pair - full).abs().max().item()     # bit-identical: the sharing is exact
+
+
+def test_cfg_pair_shared_prefix_is_bit_identical_small(small):
+    """lr_unet_forward_cfg_pair computes conv_in / first ResBlock / first self-attention once for both CFG halves."""
+    _cfg_pair_check(small[0], O.SMALL_CFG, (16, 32), 3)
+
+
 @pytest.fixture(scope="module")
 def full():
     return _build(O.DEFAULT_CFG, 0)
@@ -176,6 +195,10 @@ def test_unet_full_config_vs_reference_golden(full):
     with torch.no_grad():
         y = m(x.cuda(), t.cuda(), context=ctx.cuda())
     _assert_parity(y, g["out"], _floor(sd, O.DEFAULT_CFG, x, t, ctx))
+
+
+def test_cfg_pair_shared_prefix_is_bit_identical_full(full):
+    _cfg_pair_check(full[0], O.DEFAULT_CFG, (64, 128), 4)
 
 
 def test_unet_full_size_properties(full):
