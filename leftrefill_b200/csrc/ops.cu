@@ -340,9 +340,9 @@ int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_i
   LR_CHECK(C % groups == 0, "groupnorm: channels not divisible by groups");
   LR_CHECK(C / 8 <= kNormThreads, "groupnorm: too many channels");
   LR_CHECK(x1 != nullptr || c1 == 0, "groupnorm: c1 without x1");
-  // ~256 CTAs per image batch of 8: each CTA streams a long pixel run so that its tail (smem reduction, fp64 atomics,
-  // ticket) is amortised
-  int chunk = (P * n_img) / 256;
+  // long pixel runs per CTA amortise its tail (smem reduction, fp64 atomics, ticket). The chunking must NOT depend on
+  // the batch size: the reduction tree has to be identical for any n_img (bit-exact batch invariance).
+  int chunk = P / 32;
   if (chunk < 16) chunk = 16;
   if (chunk > 512) chunk = 512;
   const dim3 grid(cdiv(P, chunk), n_img);
