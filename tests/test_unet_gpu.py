@@ -233,3 +233,42 @@ def test_unet_full_size_properties(full):
         with torch.autocast("cuda"):
             floor = O.unet_forward(sdc, O.DEFAULT_CFG, xc[4:5], t[:1], cc[4:5]).float()
     _assert_parity(y[4:5], ref, floor)
+
+
+def test_nvs_config_shape_vs_oracle(full):
+    """BASELINE config C5 (novel_view_synthesis.yaml): same UNet hyper-parameters at a 32x64 latent, per-sample t."""
+    m, sd = full
+    g = torch.Generator().manual_seed(55)
+    x = torch.randn(2, 9, 32, 64, generator=g)
+    ctx = torch.randn(2, 77, 1024, generator=g)
+    t = torch.tensor([981, 401])
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = O.unet_forward(sdc, O.DEFAULT_CFG, x.cuda(), t.cuda(), ctx.cuda())
+        with torch.autocast("cuda"):
+            floor = O.unet_forward(sdc, O.DEFAULT_CFG, x.cuda(), t.cuda(), ctx.cuda()).float()
+        y = m(x.cuda(), t.cuda(), context=ctx.cuda())
+    _assert_parity(y, ref, floor)
+
+
+def test_multiview_four_reference_stitched_full_size():
+    """BASELINE config C4 ("4-reference stitched canvas"): view_num=5, concat_target=True -> every sample is 4 stitched
+    [ref_i | target] rows and self-attention runs over 5*32*32 = 5120 tokens at the top level of a 32x64 latent
+    (20480 at 64x128). Full 865.9 M-parameter model, one sample, vs the fp32 oracle (on the GPU, to finish in seconds)."""
+    cfg = O.DEFAULT_CFG
+    m, sd = _build(cfg, 2, multiview=(5, True))
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(4, 9, 32, 64, generator=g)
+    ctx = torch.randn(4, 77, 1024, generator=g)
+    t = torch.full((4,), 601, dtype=torch.long)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = O.unet_forward(sdc, cfg, x.cuda(), t.cuda(), ctx.cuda(), view_num=5, concat_target=True)
+        with torch.autocast("cuda"):
+            floor = O.unet_forward(sdc, cfg, x.cuda(), t.cuda(), ctx.cuda(), view_num=5, concat_target=True).float()
+        y = m(x.cuda(), t.cuda(), context=ctx.cuda())
+    _assert_parity(y, ref, floor)
