@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   // the second query tile may lie completely beyond tq (e.g. the 8x16 level has 128 tokens): it is then skipped
   // everywhere (no fully out-of-bounds TMA box, no MMA, no softmax work)
   const int ntq = (qb * kAttnQBlock + kAttnTile < p.tq) ? 2 : 1;
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // predecessors complete: from here on global memory may be read and written
   if (warp < 4) {
     if (warp == 0) {
       // ------------------------------- TMA producer (whole warp loops, one elected lane issues) ---------------

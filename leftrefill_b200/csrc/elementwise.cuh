@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __half* __
                                                                 const __half* __restrict__ x1, int c1, int P,
                                                                 int chunk, int groups, float eps,
                                                                 unsigned char* __restrict__ scratch) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];  // [rpi][2][C]
   const int C = c0 + c1;
   const int nvec = C / 8;
@@ -147,6 +149,8 @@ __global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __half* __
                                                                 const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, int groups,
                                                                 int do_silu, __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = c0 + c1;
   const int nvec = C / 8;
   const int n = blockIdx.y;
@@ -214,6 +218,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
                                                         __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -275,6 +281,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 // an fp16 [M, kpad] matrix, k = tap*cin + c, zero padded, consumed by the GEMM as a Linear.
 __global__ void im2col_nchw_f32_kernel(const float* __restrict__ x, int n_img, int cin, int H, int W, int kpad,
                                        __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(n_img) * H * W * kpad;
   if (idx >= total) return;
@@ -315,6 +323,8 @@ __global__ void im2col_nhwc_kernel(const __half* __restrict__ x, int n_img, int 
 // Upsample (openaimodel.py:108-116): F.interpolate(scale_factor=2, mode="nearest"), NHWC fp16, 8-channel vectors.
 __global__ void upsample2x_nhwc_kernel(const __half* __restrict__ x, int n_img, int H, int W, int C,
                                        __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nvec = C / 8;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(n_img) * (2 * H) * (2 * W) * nvec;
@@ -340,6 +350,8 @@ __device__ __forceinline__ size_t mv_src_row(int bi, int k, int y, int x, int v,
 }
 __global__ void mv_gather_kernel(const __half* __restrict__ src, int ld_src, int ncols, int b, int v, int hh, int side,
                                  __half* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nvec = ncols / 8;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(b) * (v + 1) * hh * side * nvec;
@@ -357,6 +369,8 @@ __global__ void mv_gather_kernel(const __half* __restrict__ src, int ld_src, int
 }
 __global__ void mv_scatter_kernel(const __half* __restrict__ src, int ncols, int b, int v, int hh, int side,
                                   __half* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nvec = ncols / 8;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(b) * v * hh * 2 * side * nvec;
@@ -385,6 +399,8 @@ __global__ void cast_f32_f16_kernel(const float* __restrict__ x, size_t n, __hal
 // UNet output: NHWC fp16 [M, ld] (first cout columns) -> NCHW fp32 [n, cout, H, W]
 __global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ x, int ld, int n_img, int cout, int H, int W,
                                             float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(n_img) * cout * H * W;
   if (idx >= total) return;
@@ -420,6 +436,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
                                                            const __half* __restrict__ w,
                                                            const float* __restrict__ bias, int n_out, int silu_in,
                                                            int silu_out, float* __restrict__ out, int ld_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float act[];  // [rows][K]
   const int lane = threadIdx.x & 31;
   const int o0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kSmallOutPerWarp;
@@ -500,6 +518,8 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __r
                                    const float* __restrict__ e_c, const float* __restrict__ noise, float cfg,
                                    float a_t, float a_prev, float sigma, float sqrt_one_minus_at, float temperature,
                                    size_t n, float* __restrict__ x_prev, float* __restrict__ pred_x0) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float e = e_u[i];

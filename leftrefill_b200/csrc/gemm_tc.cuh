@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // predecessors complete: from here on global memory may be read and written
 
   // Work unit = one 128*CG x block_n output tile per CTA (pair). CTA `rank` of a pair owns M-tile CG*pair + rank; when
   // the number of M-tiles is odd the last pair's second CTA recomputes the last tile and simply does not store it.

@@ -69,6 +69,36 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* 
   return 0;
 }
 
+// All hot kernels go through this launcher: programmatic dependent launch (+ optional 2-CTA cluster).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                              Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  static const bool use_pdl = getenv("LR_NO_PDL") == nullptr;
+  if (use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -258,22 +288,9 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
 int launch_conv_op(const ConvOp& op, cudaStream_t st) {
   const GemmParams* p = reinterpret_cast<const GemmParams*>(op.params);
   if (op.cg == 2) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(op.grid);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = op.smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    LR_CUDA(cudaLaunchKernelEx(&cfg, gemm_conv_kernel<2>, *p));
+    LR_CUDA(launch_pdl(gemm_conv_kernel<2>, dim3(op.grid), dim3(kGemmThreads), op.smem, st, 2, *p));
   } else {
-    gemm_conv_kernel<1><<<op.grid, kGemmThreads, op.smem, st>>>(*p);
+    LR_CUDA(launch_pdl(gemm_conv_kernel<1>, dim3(op.grid), dim3(kGemmThreads), op.smem, st, 1, *p));
   }
   LR_LAUNCHED();
   return 0;
@@ -322,7 +339,7 @@ int build_attn_op(AttnOp* op, const AttnSpec& s) {
 
 int launch_attn_op(const AttnOp& op, cudaStream_t st) {
   const AttnParams* p = reinterpret_cast<const AttnParams*>(op.params);
-  attention_kernel<<<op.grid, kAttnThreads, kAttnSmemBytes, st>>>(*p);
+  LR_CUDA(launch_pdl(attention_kernel, op.grid, dim3(kAttnThreads), kAttnSmemBytes, st, 1, *p));
   LR_LAUNCHED();
   return 0;
 }
@@ -349,11 +366,11 @@ int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_i
   if (!scratch_is_zero) LR_CUDA(cudaMemsetAsync(scratch, 0, gn_scratch_bytes(n_img, groups), st));
   const int rpi = kNormThreads / (C / 8);
   const size_t smem = static_cast<size_t>(rpi) * 2 * C * sizeof(float);
-  gn_stats_kernel<<<grid, kNormThreads, smem, st>>>(x0, c0, x1, c1, P, chunk, groups, eps,
-                                                    static_cast<unsigned char*>(scratch));
+  LR_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(kNormThreads), smem, st, 1, x0, c0, x1, c1, P, chunk, groups, eps,
+                     static_cast<unsigned char*>(scratch)));
   LR_LAUNCHED();
-  gn_apply_kernel<<<grid, kNormThreads, 0, st>>>(x0, c0, x1, c1, P, chunk, static_cast<const unsigned char*>(scratch),
-                                                 gamma, beta, groups, do_silu, out);
+  LR_CUDA(launch_pdl(gn_apply_kernel, grid, dim3(kNormThreads), 0, st, 1, x0, c0, x1, c1, P, chunk,
+                     static_cast<const unsigned char*>(scratch), gamma, beta, groups, do_silu, out));
   LR_LAUNCHED();
   return 0;
 }
@@ -366,12 +383,12 @@ int launch_layernorm(const __half* x, int M, int C, const float* gamma, const fl
   const int rows_per_block = 8;
   const dim3 grid(cdiv(M, rows_per_block));
   switch (vpl) {
-    case 1: layernorm_kernel<1><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, out); break;
-    case 2: layernorm_kernel<2><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, out); break;
-    case 3: layernorm_kernel<3><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, out); break;
-    case 4: layernorm_kernel<4><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, out); break;
-    case 5: layernorm_kernel<5><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, out); break;
-    case 6: case 7: case 8: layernorm_kernel<8><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, out); break;
+    case 1: LR_CUDA(launch_pdl(layernorm_kernel<1>, grid, dim3(256), 0, st, 1, x, M, C, gamma, beta, eps, out)); break;
+    case 2: LR_CUDA(launch_pdl(layernorm_kernel<2>, grid, dim3(256), 0, st, 1, x, M, C, gamma, beta, eps, out)); break;
+    case 3: LR_CUDA(launch_pdl(layernorm_kernel<3>, grid, dim3(256), 0, st, 1, x, M, C, gamma, beta, eps, out)); break;
+    case 4: LR_CUDA(launch_pdl(layernorm_kernel<4>, grid, dim3(256), 0, st, 1, x, M, C, gamma, beta, eps, out)); break;
+    case 5: LR_CUDA(launch_pdl(layernorm_kernel<5>, grid, dim3(256), 0, st, 1, x, M, C, gamma, beta, eps, out)); break;
+    case 6: case 7: case 8: LR_CUDA(launch_pdl(layernorm_kernel<8>, grid, dim3(256), 0, st, 1, x, M, C, gamma, beta, eps, out)); break;
     default: LR_CHECK(false, "layernorm: C > 2048 unsupported");
   }
   LR_LAUNCHED();
@@ -380,14 +397,16 @@ int launch_layernorm(const __half* x, int M, int C, const float* gamma, const fl
 
 int launch_im2col_nchw_f32(const float* x, int n_img, int cin, int H, int W, int kpad, __half* out, cudaStream_t st) {
   const size_t total = static_cast<size_t>(n_img) * H * W * kpad;
-  im2col_nchw_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, n_img, cin, H, W, kpad, out);
+  LR_CUDA(launch_pdl(im2col_nchw_f32_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, 1, x,
+                     n_img, cin, H, W, kpad, out));
   LR_LAUNCHED();
   return 0;
 }
 int launch_upsample2x(const __half* x, int n_img, int H, int W, int C, __half* out, cudaStream_t st) {
   LR_CHECK(C % 8 == 0, "upsample: C must be a multiple of 8");
   const size_t total = static_cast<size_t>(n_img) * 4 * H * W * (C / 8);
-  upsample2x_nhwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, n_img, H, W, C, out);
+  LR_CUDA(launch_pdl(upsample2x_nhwc_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, 1, x,
+                     n_img, H, W, C, out));
   LR_LAUNCHED();
   return 0;
 }
@@ -395,14 +414,16 @@ int launch_mv_gather(const __half* src, int ld_src, int ncols, int b, int v, int
                      cudaStream_t st) {
   LR_CHECK(ncols % 8 == 0 && ld_src % 8 == 0, "mv_gather: columns must be multiples of 8");
   const size_t total = static_cast<size_t>(b) * (v + 1) * hh * side * (ncols / 8);
-  mv_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, ld_src, ncols, b, v, hh, side, dst);
+  LR_CUDA(launch_pdl(mv_gather_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, 1, src, ld_src,
+                     ncols, b, v, hh, side, dst));
   LR_LAUNCHED();
   return 0;
 }
 int launch_mv_scatter(const __half* src, int ncols, int b, int v, int hh, int side, __half* dst, cudaStream_t st) {
   LR_CHECK(ncols % 8 == 0, "mv_scatter: columns must be multiples of 8");
   const size_t total = static_cast<size_t>(b) * v * hh * 2 * side * (ncols / 8);
-  mv_scatter_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, ncols, b, v, hh, side, dst);
+  LR_CUDA(launch_pdl(mv_scatter_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, 1, src, ncols,
+                     b, v, hh, side, dst));
   LR_LAUNCHED();
   return 0;
 }
@@ -413,8 +434,8 @@ int launch_cast_f32_f16(const float* x, size_t n, __half* out, cudaStream_t st) 
 }
 int launch_nhwc_to_nchw_f32(const __half* x, int ld, int n_img, int cout, int H, int W, float* out, cudaStream_t st) {
   const size_t total = static_cast<size_t>(n_img) * cout * H * W;
-  nhwc_f16_to_nchw_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, ld, n_img, cout, H, W,
-                                                                                          out);
+  LR_CUDA(launch_pdl(nhwc_f16_to_nchw_f32_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, 1,
+                     x, ld, n_img, cout, H, W, out));
   LR_LAUNCHED();
   return 0;
 }
@@ -430,8 +451,8 @@ int launch_small_linear(const float* in, int ld_in, int n_rows, int K, const __h
   const int rows = n_rows < kMaxSmallBatch ? n_rows : kMaxSmallBatch;
   const size_t smem = static_cast<size_t>(rows) * K * sizeof(float);
   LR_CHECK(smem <= 48 * 1024, "small_linear: K too large for the activation staging buffer");
-  small_linear_kernel<<<cdiv(n_out, 8 * kSmallOutPerWarp), 256, smem, st>>>(in, ld_in, n_rows, K, w, bias, n_out,
-                                                                             silu_in, silu_out, out, ld_out);
+  LR_CUDA(launch_pdl(small_linear_kernel, dim3(cdiv(n_out, 8 * kSmallOutPerWarp)), dim3(256), smem, st, 1, in, ld_in,
+                     n_rows, K, w, bias, n_out, silu_in, silu_out, out, ld_out));
   LR_LAUNCHED();
   return 0;
 }
@@ -444,8 +465,8 @@ int launch_timestep_embedding(const long long* t, int t_count, int n, int dim, f
 int launch_ddim_update(const float* x, const float* e_u, const float* e_c, const float* noise, float cfg, float a_t,
                        float a_prev, float sigma, float sqrt_one_minus_at, float temperature, size_t n, float* x_prev,
                        float* pred_x0, cudaStream_t st) {
-  ddim_update_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
-      x, e_u, e_c, noise, cfg, a_t, a_prev, sigma, sqrt_one_minus_at, temperature, n, x_prev, pred_x0);
+  LR_CUDA(launch_pdl(ddim_update_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, 1, x, e_u, e_c,
+                     noise, cfg, a_t, a_prev, sigma, sqrt_one_minus_at, temperature, n, x_prev, pred_x0));
   LR_LAUNCHED();
   return 0;
 }

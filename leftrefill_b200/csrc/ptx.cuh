@@ -79,6 +79,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch: every hot kernel is launched with programmaticStreamSerialization, releases its
+// dependents at entry and waits for its predecessors only after its own prologue (barrier init, TMEM allocation,
+// descriptor prefetch), so launch latency + prologue overlap the tail of the previous kernel. No global memory is
+// touched before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / UMMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
