@@ -22,6 +22,10 @@ const char* lr_last_error(void);
 /* number of CUDA kernels launched by this library since the last reset (bench.py's gpu_launches) */
 long long lr_launch_count(void);
 void lr_launch_count_reset(void);
+/* Bring-up aid (no reference counterpart): when LR_GEMM_TRACE / LR_ATTN_TRACE is set in the environment before the first
+ * op, CTA 0 of the GEMM / attention kernels records clock64() samples per warp role and phase; this copies them to HOST
+ * memory `dst` (synchronises the device) and optionally clears the buffer. Fails when tracing is not enabled. */
+int lr_debug_read_trace(void* dst, long long bytes, int clear);
 
 /* ---- UNet engine: replaces UNetModel.forward (ldm/modules/diffusionmodules/openaimodel.py:755-787) ------------ */
 typedef struct lr_unet lr_unet;

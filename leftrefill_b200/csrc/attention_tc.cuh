@@ -26,6 +26,7 @@ struct AttnParams {
   __half* out;                 // [batch*tq, ld_out], head h -> columns [h*64, h*64+64)
   int ld_out;
   float scale_log2;            // softmax scale * log2(e)
+  unsigned long long* trace;   // LR_ATTN_TRACE: block (0,0,0) accumulates clock64() per softmax phase; else null
 };
 
 constexpr int kAttnThreads = 384;
@@ -59,6 +60,11 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
+// kTrace = true (debug builds of the launch only): one lane per softmax warpgroup of block (0,0,0) accumulates the
+// cycles of each phase of tile_body into p.trace[t*8 + phase]:
+//   0 wait S ready | 1 tcgen05.ld S | 2 row max / rescale decision | 3 exp2 + pack | 4 wait PV(j-1) (+ O rescale)
+//   5 tcgen05.st P + arrive | 6 total | 7 tiles
+template <bool kTrace>
 __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* q_s = smem;                                       // [2] query tiles
@@ -228,10 +234,22 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     float l = 0.f;
     const int my_tiles = (t < ntq) ? ntiles : 0;
 
+    unsigned long long tr[6] = {0, 0, 0, 0, 0, 0};
+    long long tr_t = 0, tr_begin = 0;
+    const bool tracing = kTrace && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    if (kTrace) tr_begin = tr_t = clock64();
+    auto mark = [&](int phase) {
+      if (kTrace) {
+        const long long now = clock64();
+        tr[phase] += static_cast<unsigned long long>(now - tr_t);
+        tr_t = now;
+      }
+    };
     auto tile_body = [&](int j, auto mask_tag) {
       constexpr bool kMask = decltype(mask_tag)::value;
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
+      mark(0);
       uint32_t s[128];
       {
         uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
@@ -246,6 +264,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       }
       tc_fence_before();
       mbar_arrive(&s_empty[t]);  // S_t may be overwritten by the next QK^T right away
+      mark(1);
       if (kMask) {               // only the last KV tile can be partial (keys beyond tk were zero-filled by TMA)
         const int kv_valid = p.tk - j * kAttnTile;
 #pragma unroll
@@ -271,6 +290,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         m_used = m_new;
         l *= alpha;
       }
+      mark(2);
       // P = exp2((s - m_used) * scale_log2) as fp16 pairs, kept in registers until the previous PV has released P_t
       const float moff = m_used * p.scale_log2;
       uint32_t h[64];
@@ -289,6 +309,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         h[i + 1] = pack_half2(e2, e3);
       }
       l += (l0 + l1) + (l2 + l3);
+      mark(3);
       if (j > 0) {
         mbar_wait(&pv_done[t], (j - 1) & 1);  // PV(j-1) finished reading P_t and updating O_t
         tc_fence_after();
@@ -305,6 +326,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
           }
         }
       }
+      mark(4);
       {
         uint32_t(&h0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&h[0]);
         uint32_t(&h1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&h[32]);
@@ -314,10 +336,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
+      mark(5);
     };
 
     for (int j = 0; j < my_tiles - 1; ++j) tile_body(j, BoolTag<false>{});
     if (my_tiles > 0) tile_body(my_tiles - 1, BoolTag<true>{});
+    if (kTrace && tracing && q == 0 && lane == 0) {
+      for (int i = 0; i < 6; ++i) p.trace[t * 8 + i] = tr[i];
+      p.trace[t * 8 + 6] = static_cast<unsigned long long>(clock64() - tr_begin);
+      p.trace[t * 8 + 7] = static_cast<unsigned long long>(my_tiles);
+    }
 
     // epilogue: O / rowsum -> fp16
     if (t < ntq) {

@@ -23,23 +23,138 @@ __device__ __forceinline__ void store8(__half* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) =
       make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with MUFU.EX2 + MUFU.RCP (no IEEE division: the slow path of `/` made GroupNorm+SiLU issue bound)
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // ------------------------------------------------------------------------------------------------------------
 // GroupNorm (reference: GroupNorm32, ldm/modules/diffusionmodules/util.py:217-219, fp32 math; Normalize,
 // ldm/modules/attention.py:90-91). Sources x0 [n, P, c0] and x1 [n, P, c1] form the channel concat.
 //
-// Statistics: each thread owns one 8-channel vector column and walks pixels (4 loads in flight); the CTA reduces its
-// partials in a FIXED order in shared memory (bit-reproducible), folds channels to groups in fp64 and adds one
-// (sum, sum of squares) pair per group to the per-site scratch with fp64 atomics. The last CTA of an image (ticket
-// counter) turns the sums into (mean, rstd) floats, so the apply kernel needs no fp64 and no extra launch.
+// Thread mapping (all GroupNorm kernels): thread -> (8-channel vector column `vec`, pixel slice `rsub`), rpi = 512 / nvec
+// slices sweep the pixel range rpi rows at a time, kGnBatch independent 16-byte loads in flight per thread (the loads
+// of a batch are predicated, never serialised by a tail loop). Every reduction runs in a FIXED order (thread-local
+// order, shared-memory slice order, cluster rank order), so statistics are bit-reproducible and independent of the
+// batch size.
+//
+// Two execution schemes, chosen per call site by launch_groupnorm:
+//   * fused (gn_fused_cluster_kernel): one cluster of CS CTAs per image. Pass 1 reads the image once and reduces to
+//     per-group (sum, sum of squares) in fp64; the CS partials are exchanged through distributed shared memory and
+//     every CTA finalises (mean, rstd) itself; pass 2 re-reads its own pixels (L2 / L1 resident: the whole image is
+//     a few MB at most) and writes y = [silu]((x - mean) * rstd * gamma + beta). One launch, no atomics, no scratch.
+//   * two-pass (gn_stats_kernel + gn_apply_kernel) for images too large for one cluster: fp64 atomics into a per-site
+//     scratch, the last CTA of an image (ticket) finalises (mean, rstd).
 // Scratch layout per call site (zeroed by the caller): double sums[n][G][2]; float2 mr[n][G]; unsigned ticket[n].
-// grid = (pixel chunks, n); block = kNormThreads; dynamic smem = rpi * 2 * C floats.
 // ------------------------------------------------------------------------------------------------------------
+constexpr int kGnBatch = 8;
+
 __host__ __device__ inline size_t gn_scratch_bytes(int n, int groups) {
   return static_cast<size_t>(n) * groups * (2 * sizeof(double) + sizeof(float2)) + static_cast<size_t>(n) * 8;
 }
 
+__device__ __forceinline__ uint4 ldg16(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack_half2(w[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+// Compiler barrier on a packed vector: stops ptxas/nvcc from keeping the UNPACKED fp32 copy of a register-resident row
+// live across passes (which doubles the register footprint); re-unpacking costs 4 cheap converts.
+__device__ __forceinline__ void keep_packed(uint4& v) { asm volatile("" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)); }
+
+// per-thread partial (sum, sum of squares) of 8 channels over pixels p0, p0 + rpi, ... < p_end
+__device__ __forceinline__ void gn_accumulate(const __half* __restrict__ base, int ld, int p0, int p_end, int rpi,
+                                              float (&s)[8], float (&ss)[8]) {
+  for (int p = p0; p < p_end; p += kGnBatch * rpi) {
+    uint4 v[kGnBatch];
+#pragma unroll
+    for (int u = 0; u < kGnBatch; ++u) {
+      const int pp = p + u * rpi;
+      v[u] = (pp < p_end) ? ldg16(base + static_cast<size_t>(pp) * ld) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < kGnBatch; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        ss[j] = fmaf(f[j], f[j], ss[j]);
+      }
+    }
+  }
+}
+
+// CTA-wide fixed-order reduction of the per-thread partials to per-group fp64 (sum, sum of squares).
+// sm: [rpi][2][C] floats. On return threads g < groups hold their group's sums in (a, b).
+__device__ __forceinline__ void gn_cta_group_sums(float* sm, int C, int rpi, int rsub, int ch, int groups,
+                                                  const float (&s)[8], const float (&ss)[8], double& a, double& b) {
+  if (rsub < rpi) {
+    float* dst = sm + static_cast<size_t>(rsub) * 2 * C + ch;
+    *reinterpret_cast<float4*>(dst) = make_float4(s[0], s[1], s[2], s[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(s[4], s[5], s[6], s[7]);
+    *reinterpret_cast<float4*>(dst + C) = make_float4(ss[0], ss[1], ss[2], ss[3]);
+    *reinterpret_cast<float4*>(dst + C + 4) = make_float4(ss[4], ss[5], ss[6], ss[7]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float acc = sm[i];
+    for (int rr = 1; rr < rpi; ++rr) acc += sm[static_cast<size_t>(rr) * 2 * C + i];
+    sm[i] = acc;
+  }
+  __syncthreads();
+  a = 0.0;
+  b = 0.0;
+  const int cpg = C / groups;
+  if (static_cast<int>(threadIdx.x) < groups) {
+    const int g = threadIdx.x;
+    for (int j = 0; j < cpg; ++j) {
+      a += static_cast<double>(sm[g * cpg + j]);
+      b += static_cast<double>(sm[C + g * cpg + j]);
+    }
+  }
+}
+
+__device__ __forceinline__ float2 gn_finalize(double sum, double sq, double cnt, float eps) {
+  const double mean = sum / cnt;
+  double var = sq / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  return make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+}
+
+// y = [silu](x * sc + sh) for pixels p0, p0 + rpi, ... < p_end of one 8-channel column
+__device__ __forceinline__ void gn_apply_rows(const __half* __restrict__ base, int ld, __half* __restrict__ o, int C,
+                                              int p0, int p_end, int rpi, const float (&sc)[8], const float (&sh)[8],
+                                              int do_silu) {
+  for (int p = p0; p < p_end; p += kGnBatch * rpi) {
+    uint4 v[kGnBatch];
+#pragma unroll
+    for (int u = 0; u < kGnBatch; ++u) {
+      const int pp = p + u * rpi;
+      v[u] = (pp < p_end) ? ldg16(base + static_cast<size_t>(pp) * ld) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < kGnBatch; ++u) {
+      const int pp = p + u * rpi;
+      if (pp < p_end) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float y = fmaf(f[j], sc[j], sh[j]);
+          f[j] = do_silu ? silu_f(y) : y;
+        }
+        store8(o + static_cast<size_t>(pp) * C, f);
+      }
+    }
+  }
+}
+
+// grid = (pixel chunks, n); block = kNormThreads; dynamic smem = rpi * 2 * C floats.
 __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __half* __restrict__ x0, int c0,
                                                                 const __half* __restrict__ x1, int c1, int P,
                                                                 int chunk, int groups, float eps,
@@ -59,64 +174,20 @@ __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __half* __
   const int rpi = blockDim.x / nvec;  // pixel rows handled per sweep
   const int vec = threadIdx.x % nvec;
   const int rsub = threadIdx.x / nvec;
+  const int ch = vec * 8;
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
   if (rsub < rpi) {
-    float s[8], ss[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
-    const int ch = vec * 8;
-    const __half* base;
-    int ld;
-    if (ch < c0) {
-      base = x0 + ch;
-      ld = c0;
-    } else {
-      base = x1 + (ch - c0);
-      ld = c1;
-    }
+    const __half* base = (ch < c0) ? x0 + ch : x1 + (ch - c0);
+    const int ld = (ch < c0) ? c0 : c1;
     base += static_cast<size_t>(n) * P * ld;
-    int p = p_begin + rsub;
-    for (; p + 3 * rpi < p_end; p += 4 * rpi) {  // 4 independent 16-byte loads in flight per thread
-      float f0[8], f1[8], f2[8], f3[8];
-      load8(base + static_cast<size_t>(p) * ld, f0);
-      load8(base + static_cast<size_t>(p + rpi) * ld, f1);
-      load8(base + static_cast<size_t>(p + 2 * rpi) * ld, f2);
-      load8(base + static_cast<size_t>(p + 3 * rpi) * ld, f3);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
-        ss[j] += (f0[j] * f0[j] + f1[j] * f1[j]) + (f2[j] * f2[j] + f3[j] * f3[j]);
-      }
-    }
-    for (; p < p_end; p += rpi) {
-      float f[8];
-      load8(base + static_cast<size_t>(p) * ld, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += f[j];
-        ss[j] += f[j] * f[j];
-      }
-    }
-    float* dst = sm + static_cast<size_t>(rsub) * 2 * C + ch;
-    *reinterpret_cast<float4*>(dst) = make_float4(s[0], s[1], s[2], s[3]);
-    *reinterpret_cast<float4*>(dst + 4) = make_float4(s[4], s[5], s[6], s[7]);
-    *reinterpret_cast<float4*>(dst + C) = make_float4(ss[0], ss[1], ss[2], ss[3]);
-    *reinterpret_cast<float4*>(dst + C + 4) = make_float4(ss[4], ss[5], ss[6], ss[7]);
+    gn_accumulate(base, ld, p_begin + rsub, p_end, rpi, s, ss);
   }
-  __syncthreads();
-  // fixed-order reduction over the rpi row-slices, in place into slice 0
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-    float a = sm[i];
-    for (int rr = 1; rr < rpi; ++rr) a += sm[static_cast<size_t>(rr) * 2 * C + i];
-    sm[i] = a;
-  }
-  __syncthreads();
-  const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    double a = 0.0, b = 0.0;
-    for (int j = 0; j < cpg; ++j) {
-      a += static_cast<double>(sm[g * cpg + j]);
-      b += static_cast<double>(sm[C + g * cpg + j]);
-    }
+  double a, b;
+  gn_cta_group_sums(sm, C, rpi, rsub, ch, groups, s, ss, a, b);
+  if (static_cast<int>(threadIdx.x) < groups) {
+    const int g = threadIdx.x;
     atomicAdd(&sums[(static_cast<size_t>(n) * groups + g) * 2 + 0], a);
     atomicAdd(&sums[(static_cast<size_t>(n) * groups + g) * 2 + 1], b);
   }
@@ -128,15 +199,11 @@ __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __half* __
   __syncthreads();
   if (s_ticket == gridDim.x - 1) {
     __threadfence();
-    const double cnt = static_cast<double>(P) * cpg;
+    const double cnt = static_cast<double>(P) * (C / groups);
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
       const double sum = __ldcg(&sums[(static_cast<size_t>(n) * groups + g) * 2 + 0]);
       const double sq = __ldcg(&sums[(static_cast<size_t>(n) * groups + g) * 2 + 1]);
-      const double mean = sum / cnt;
-      double var = sq / cnt - mean * mean;
-      if (var < 0.0) var = 0.0;
-      mr[static_cast<size_t>(n) * groups + g] =
-          make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+      mr[static_cast<size_t>(n) * groups + g] = gn_finalize(sum, sq, cnt, eps);
     }
   }
 }
@@ -172,104 +239,240 @@ __global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __half* __
     sc[j] = m.y * gamma[ch + j];
     sh[j] = beta[ch + j] - m.x * sc[j];
   }
-  const __half* base;
-  int ld;
-  if (ch < c0) {
-    base = x0 + ch;
-    ld = c0;
-  } else {
-    base = x1 + (ch - c0);
-    ld = c1;
-  }
+  const __half* base = (ch < c0) ? x0 + ch : x1 + (ch - c0);
+  const int ld = (ch < c0) ? c0 : c1;
   base += static_cast<size_t>(n) * P * ld;
   __half* o = out + static_cast<size_t>(n) * P * C + ch;
-  int p = p_begin + rsub;
-  for (; p + 3 * rpi < p_end; p += 4 * rpi) {
-    float f[4][8];
+  gn_apply_rows(base, ld, o, C, p_begin + rsub, p_end, rpi, sc, sh, do_silu);
+}
+
+// Fused single-launch GroupNorm: grid = (CS, n) with cluster dims (CS, 1, 1); block = kNormThreads;
+// dynamic smem = rpi * 2 * C floats.
+__device__ __forceinline__ double ld_dsmem_f64(const double* p, uint32_t rank) {
+  uint32_t ra;
+  double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+// split cluster barrier (non-.aligned forms: callers may arrive right after thread-divergent code)
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kNormThreads) gn_fused_cluster_kernel(const __half* __restrict__ x0, int c0,
+                                                                        const __half* __restrict__ x1, int c1, int P,
+                                                                        int groups, float eps,
+                                                                        const float* __restrict__ gamma,
+                                                                        const float* __restrict__ beta, int do_silu,
+                                                                        __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float sm[];        // [rpi][2][C]
+  __shared__ double s_part[2 * 64];    // this CTA's per-group (sum, sum of squares), read by the whole cluster
+  __shared__ float2 s_mr[64];
+  const int C = c0 + c1;
+  const int nvec = C / 8;
+  const int n = blockIdx.y;
+  const int cs = gridDim.x;  // == cluster size
+  const uint32_t rank = cluster_ctarank();
+  const int per = (P + cs - 1) / cs;
+  const int p_begin = static_cast<int>(rank) * per;
+  const int p_end = min(P, p_begin + per);
+  const int rpi = blockDim.x / nvec;
+  const int vec = threadIdx.x % nvec;
+  const int rsub = threadIdx.x / nvec;
+  const int ch = vec * 8;
+  const __half* base = (ch < c0) ? x0 + ch : x1 + (ch - c0);
+  const int ld = (ch < c0) ? c0 : c1;
+  base += static_cast<size_t>(n) * P * ld;
+  float s[8], ss[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) load8(base + static_cast<size_t>(p + u * rpi) * ld, f[u]);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float y = f[u][j] * sc[j] + sh[j];
-        f[u][j] = do_silu ? silu_f(y) : y;
-      }
-      store8(o + static_cast<size_t>(p + u * rpi) * C, f[u]);
-    }
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  if (rsub < rpi) gn_accumulate(base, ld, p_begin + rsub, p_end, rpi, s, ss);
+  double a, b;
+  gn_cta_group_sums(sm, C, rpi, rsub, ch, groups, s, ss, a, b);
+  if (static_cast<int>(threadIdx.x) < groups) {
+    s_part[2 * threadIdx.x] = a;
+    s_part[2 * threadIdx.x + 1] = b;
   }
-  for (; p < p_end; p += rpi) {
-    float f[8];
-    load8(base + static_cast<size_t>(p) * ld, f);
+  cluster_arrive();
+  cluster_wait();
+  if (static_cast<int>(threadIdx.x) < groups) {
+    double sum = 0.0, sq = 0.0;
+    for (int r = 0; r < cs; ++r) {  // rank order: identical in every CTA
+      sum += ld_dsmem_f64(&s_part[2 * threadIdx.x], r);
+      sq += ld_dsmem_f64(&s_part[2 * threadIdx.x + 1], r);
+    }
+    s_mr[threadIdx.x] = gn_finalize(sum, sq, static_cast<double>(P) * (C / groups), eps);
+  }
+  cluster_arrive();  // our remote reads are done; matched by the wait at the end (keeps every CTA's smem alive)
+  __syncthreads();
+  if (rsub < rpi) {
+    const int cpg = C / groups;
+    float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float y = f[j] * sc[j] + sh[j];
-      f[j] = do_silu ? silu_f(y) : y;
+      const float2 m = s_mr[(ch + j) / cpg];
+      sc[j] = m.y * gamma[ch + j];
+      sh[j] = beta[ch + j] - m.x * sc[j];
     }
-    store8(o + static_cast<size_t>(p) * C, f);
+    __half* o = out + static_cast<size_t>(n) * P * C + ch;
+    gn_apply_rows(base, ld, o, C, p_begin + rsub, p_end, rpi, sc, sh, do_silu);
   }
+  cluster_wait();
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// LayerNorm over the channel dim (nn.LayerNorm eps 1e-5, attention.py:266-268), one warp per token row.
+// LayerNorm over the channel dim (nn.LayerNorm eps 1e-5, attention.py:266-268).
+// HBM-streaming structure: the token matrix is contiguous, so a tile of kLnTileRows rows is ONE 1-D bulk copy
+// (cp.async.bulk global -> shared, completion on an mbarrier). A producer warp keeps `stages` tiles in flight per CTA
+// (bytes in flight are bounded by shared memory, not by registers); 8 consumer warps each normalise two rows of the
+// tile (two-pass statistics on register-resident rows, interleaved for ILP) and store fp16 rows straight to global.
+// Persistent: grid-stride over tiles. gamma / beta are staged once per CTA.
+// Dynamic smem: stages * kLnTileRows * C * 2 (tiles) + 2 * C * 4 (gamma, beta) + 2 * stages * 8 (barriers).
 // ------------------------------------------------------------------------------------------------------------
-template <int VPL>  // 8-channel vectors per lane
-__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int M, int C,
-                                                        const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, float eps,
-                                                        __half* __restrict__ out) {
+constexpr int kLnConsumerWarps = 8;
+constexpr int kLnRowsPerWarp = 2;
+constexpr int kLnTileRows = kLnConsumerWarps * kLnRowsPerWarp;  // 16
+constexpr int kLnThreads = (kLnConsumerWarps + 1) * 32;
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int VPL>  // 8-channel vectors per lane: ceil(C / 256)
+__global__ void __launch_bounds__(kLnThreads) layernorm_kernel(const __half* __restrict__ x, int M, int C,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float eps,
+                                                               __half* __restrict__ out, int stages) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int tile_bytes = kLnTileRows * C * 2;
+  float* gb = reinterpret_cast<float*>(ln_smem + static_cast<size_t>(stages) * tile_bytes);  // [2][C]
+  uint64_t* full = reinterpret_cast<uint64_t*>(gb + 2 * C);
+  uint64_t* empty = full + stages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
-  pdl_wait();
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const int lane = threadIdx.x & 31;
-  const int nvec = C / 8;
-  float f[VPL][8];
-  float s = 0.f;
-#pragma unroll
-  for (int v = 0; v < VPL; ++v) {
-    const int vi = lane + v * 32;
-    if (vi < nvec) {
-      load8(x + static_cast<size_t>(row) * C + vi * 8, f[v]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s += f[v][j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[v][j] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kLnConsumerWarps);
     }
+    fence_barrier_init();
   }
+  // weights are never written inside a forward: safe to read before pdl_wait
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    gb[i] = gamma[i];
+    gb[C + i] = beta[i];
+  }
+  __syncthreads();
+  pdl_wait();
+  const int ntiles = (M + kLnTileRows - 1) / kLnTileRows;
+  if (warp == kLnConsumerWarps) {
+    // ------------------------------- producer warp ---------------------------------------------------------
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      mbar_wait(&empty[s], ph ^ 1);
+      if (lane == 0) {
+        const int rows = min(kLnTileRows, M - t * kLnTileRows);
+        const uint32_t bytes = static_cast<uint32_t>(rows) * C * 2;
+        mbar_arrive_expect_tx(&full[s], bytes);
+        bulk_load_1d(ln_smem + static_cast<size_t>(s) * tile_bytes,
+                     x + static_cast<size_t>(t) * kLnTileRows * C, bytes, &full[s]);
+      }
+      __syncwarp();
+      if (++s == stages) { s = 0; ph ^= 1; }
+    }
+    return;
+  }
+  // ------------------------------- consumer warps ------------------------------------------------------------
+  const int nvec = C / 8;
+  const float inv_c = 1.0f / static_cast<float>(C);
+  int s = 0;
+  uint32_t ph = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    mbar_wait(&full[s], ph);
+    const uint8_t* tile = ln_smem + static_cast<size_t>(s) * tile_bytes;
+    const int r0 = warp * kLnRowsPerWarp;
+    uint4 raw[kLnRowsPerWarp][VPL];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / C;
-  float q = 0.f;
+    for (int r = 0; r < kLnRowsPerWarp; ++r) {
 #pragma unroll
-  for (int v = 0; v < VPL; ++v) {
-    const int vi = lane + v * 32;
-    if (vi < nvec) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = f[v][j] - mean;
-        q += d * d;
+      for (int v = 0; v < VPL; ++v) {
+        const int vi = lane + v * 32;
+        raw[r][v] = (vi < nvec) ? *reinterpret_cast<const uint4*>(tile + (static_cast<size_t>(r0 + r) * C + vi * 8) * 2)
+                                : make_uint4(0u, 0u, 0u, 0u);
       }
     }
-  }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);  // rows are in registers: the slot can be refilled
+    if (++s == stages) { s = 0; ph ^= 1; }
+    float mean[kLnRowsPerWarp], rstd[kLnRowsPerWarp];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / C + eps);
+    for (int r = 0; r < kLnRowsPerWarp; ++r) {
+      float acc = 0.f;
 #pragma unroll
-  for (int v = 0; v < VPL; ++v) {
-    const int vi = lane + v * 32;
-    if (vi < nvec) {
-      float y[8];
-      const float4 g0 = *reinterpret_cast<const float4*>(gamma + vi * 8);
-      const float4 g1 = *reinterpret_cast<const float4*>(gamma + vi * 8 + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(beta + vi * 8);
-      const float4 b1 = *reinterpret_cast<const float4*>(beta + vi * 8 + 4);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      for (int v = 0; v < VPL; ++v) {
+        float f[8];
+        unpack8(raw[r][v], f);
+        acc += ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
+      }
+      mean[r] = acc;
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = (f[v][j] - mean) * rstd * gg[j] + bb[j];
-      store8(out + static_cast<size_t>(row) * C + vi * 8, y);
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < kLnRowsPerWarp; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+    }
+#pragma unroll
+    for (int r = 0; r < kLnRowsPerWarp; ++r) {
+      mean[r] *= inv_c;
+      float q = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        if (lane + v * 32 < nvec) {
+          float f[8];
+          unpack8(raw[r][v], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = f[j] - mean[r];
+            q = fmaf(d, d, q);
+          }
+        }
+      }
+      rstd[r] = q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < kLnRowsPerWarp; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+    }
+#pragma unroll
+    for (int r = 0; r < kLnRowsPerWarp; ++r) rstd[r] = rsqrtf(rstd[r] * inv_c + eps);
+    const long long row_base = static_cast<long long>(t) * kLnTileRows + r0;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int vi = lane + v * 32;
+      if (vi < nvec) {
+        const float4 g0 = *reinterpret_cast<const float4*>(gb + vi * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(gb + vi * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(gb + C + vi * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(gb + C + vi * 8 + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int r = 0; r < kLnRowsPerWarp; ++r) {
+          if (row_base + r < M) {
+            float f[8], y[8];
+            unpack8(raw[r][v], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = (f[j] - mean[r]) * rstd[r] * gg[j] + bb[j];
+            store8(out + static_cast<size_t>(row_base + r) * C + vi * 8, y);
+          }
+        }
+      }
     }
   }
 }

@@ -953,6 +953,10 @@ int lr_abi_version(void) { return LR_B200_ABI_VERSION; }
 const char* lr_last_error(void) { return lr::last_error(); }
 long long lr_launch_count(void) { return lr::launches_since_reset(); }
 void lr_launch_count_reset(void) { lr::reset_launch_counter(); }
+int lr_debug_read_trace(void* dst, long long bytes, int clear) {
+  LR_CHECK(dst != nullptr && bytes > 0, "lr_debug_read_trace: bad argument");
+  return lr::debug_read_trace(dst, static_cast<size_t>(bytes), clear);
+}
 
 int lr_unet_create(const lr_unet_cfg* cfg, lr_unet** out) {
   LR_CHECK(cfg != nullptr && out != nullptr, "lr_unet_create: null argument");

@@ -56,7 +56,15 @@ struct GemmParams {
   int n_valid;             // valid output columns (after GEGLU halving)
   float out_scale;         // multiplies the final value (1.0 normally)
   int dbg;                 // bring-up experiments only (LR_GEMM_DEBUG): 1 = no A loads, 2 = no B loads, 4 = no MMAs
+  unsigned long long* trace;  // LR_GEMM_TRACE: CTA 0 records clock64() per role / tile / phase ([3][16][8]); else null
 };
+
+// role: 0 producer, 1 MMA issuer, 2 epilogue (warp 2). One lane of CTA 0 writes; first 16 tiles only.
+#define LR_GEMM_TR(role, tcount, slot)                                                                       \
+  do {                                                                                                       \
+    if (p.trace != nullptr && blockIdx.x == 0 && (tcount) < 16 && lane == 0)                                 \
+      p.trace[((role) * 16 + (tcount)) * 8 + (slot)] = static_cast<unsigned long long>(clock64());           \
+  } while (0)
 
 constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kEpiWarps = 8;
@@ -158,7 +166,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     // ------------------------------- TMA producer (whole warp loops, one elected lane issues) ---------------
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+    int tcount = 0;
+    for (int tile = unit0; tile < num_tiles; tile += unit_step, ++tcount) {
+      LR_GEMM_TR(0, tcount, 0);
       const int tn = tile % p.tiles_n;
       int tm = min((tile / p.tiles_n) * CG + static_cast<int>(rank), tiles_m - 1);
       const int tx = tm % p.tiles_x;
@@ -195,6 +205,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
+      LR_GEMM_TR(0, tcount, 1);
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer (whole warp loops, one elected lane issues) ----------------
@@ -208,13 +219,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+      int tcount = 0;
+      for (int tile = unit0; tile < num_tiles; tile += unit_step, ++tcount) {
+        LR_GEMM_TR(1, tcount, 0);
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
+        LR_GEMM_TR(1, tcount, 1);
         const uint32_t d_tmem = tmem_base + as * 256;
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          if (it == 0) LR_GEMM_TR(1, tcount, 2);
           if (elect_one()) {
             const uint32_t a_lo = a_lo0 + s * stage_units;
             const uint32_t b_lo = b_lo0 + s * stage_units;
@@ -236,6 +251,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
           if (CG == 2) umma_commit_2sm(&tfull[as]); else umma_commit(&tfull[as]);
         }
         __syncwarp();
+        LR_GEMM_TR(1, tcount, 3);
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
@@ -254,7 +270,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     const int ocols_tile = p.geglu ? p.block_n / 2 : p.block_n;  // output columns of one tile
     const int full_slabs = ocols_tile >> 6;                      // 64-column slabs [128 rows][128 B], swizzled
     bool stores_pending = false;
-    for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+    int tcount = 0;
+    for (int tile = unit0; tile < num_tiles; tile += unit_step, ++tcount) {
+      if (ew == 0) LR_GEMM_TR(2, tcount, 0);
       const int tn = tile % p.tiles_n;
       int tm = (tile / p.tiles_n) * CG + static_cast<int>(rank);
       const bool tile_ok = tm < tiles_m;
@@ -292,8 +310,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         for (int k = 0; k < 4; ++k) rnext[k] = __ldg(rp + k);
       }
 
+      if (ew == 0) LR_GEMM_TR(2, tcount, 1);
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
+      if (ew == 0) LR_GEMM_TR(2, tcount, 2);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
       for (; c < p.block_n; c += 64) {
         uint32_t v[32];
@@ -405,6 +425,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       }
       tc_fence_before();
       __syncwarp();
+      if (ew == 0) LR_GEMM_TR(2, tcount, 3);
       if (lane == 0) {
         if (CG == 2) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]);
       }
@@ -413,6 +434,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         // clipped by the tensor map, so partial tiles need no masking)
         fence_proxy_async_smem();
         asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
+        if (ew == 0) LR_GEMM_TR(2, tcount, 4);
         if (etid == 0 && tile_ok && !(p.dbg & 8)) {
           const int oc_tile0 = p.geglu ? (ncol0 >> 1) : ncol0;
           const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tb * p.bn;
@@ -424,6 +446,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
           tma_store_commit();
           stores_pending = true;
         }
+        if (ew == 0) LR_GEMM_TR(2, tcount, 5);
       }
       if (++as == 2) { as = 0; aph ^= 1; }
     }

@@ -99,6 +99,29 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Debug trace buffer (LR_GEMM_TRACE / LR_ATTN_TRACE set): kernels of CTA 0 drop clock64() samples here; read back with
+// lr_debug_read_trace. Null (no instrumentation executed) otherwise.
+constexpr size_t kTraceBytes = 16384;
+unsigned long long* debug_trace_buffer() {
+  static unsigned long long* buf = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    if (getenv("LR_GEMM_TRACE") == nullptr && getenv("LR_ATTN_TRACE") == nullptr) return;
+    if (cudaMalloc(&buf, kTraceBytes) != cudaSuccess) { buf = nullptr; return; }
+    cudaMemset(buf, 0, kTraceBytes);
+  });
+  return buf;
+}
+int debug_read_trace(void* dst, size_t bytes, int clear) {
+  unsigned long long* b = debug_trace_buffer();
+  LR_CHECK(b != nullptr, "trace buffer not enabled (set LR_GEMM_TRACE or LR_ATTN_TRACE before the first op)");
+  if (bytes > kTraceBytes) bytes = kTraceBytes;
+  LR_CUDA(cudaDeviceSynchronize());
+  LR_CUDA(cudaMemcpy(dst, b, bytes, cudaMemcpyDeviceToHost));
+  if (clear) LR_CUDA(cudaMemset(b, 0, kTraceBytes));
+  return 0;
+}
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -224,6 +247,7 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
     const char* e = getenv("LR_GEMM_DEBUG");
     p.dbg = e ? atoi(e) : 0;
   }
+  p.trace = debug_trace_buffer();
   LR_CHECK(!(s.geglu && s.residual), "conv: GEGLU + residual not supported");
 
   // activations: [C, W, H, N]
@@ -326,12 +350,14 @@ int build_attn_op(AttnOp* op, const AttnSpec& s) {
   p.out = s.out;
   p.ld_out = s.ld_out;
   p.scale_log2 = s.scale * 1.4426950408889634f;
+  p.trace = getenv("LR_ATTN_TRACE") ? debug_trace_buffer() : nullptr;
   op->grid = dim3(cdiv(s.tq, kAttnQBlock), s.heads, s.batch);
   op->flops = 4.0 * s.batch * s.heads * static_cast<double>(s.tq) * s.tk * kAttnD;
   memcpy(op->params, &p, sizeof(p));
   static bool attr_set = false;
   if (!attr_set) {
-    LR_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    LR_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    LR_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
     attr_set = true;
   }
   return 0;
@@ -339,7 +365,11 @@ int build_attn_op(AttnOp* op, const AttnSpec& s) {
 
 int launch_attn_op(const AttnOp& op, cudaStream_t st) {
   const AttnParams* p = reinterpret_cast<const AttnParams*>(op.params);
-  LR_CUDA(launch_pdl(attention_kernel, op.grid, dim3(kAttnThreads), kAttnSmemBytes, st, 1, *p));
+  if (p->trace != nullptr) {
+    LR_CUDA(launch_pdl(attention_kernel<true>, op.grid, dim3(kAttnThreads), kAttnSmemBytes, st, 1, *p));
+  } else {
+    LR_CUDA(launch_pdl(attention_kernel<false>, op.grid, dim3(kAttnThreads), kAttnSmemBytes, st, 1, *p));
+  }
   LR_LAUNCHED();
   return 0;
 }
@@ -349,6 +379,11 @@ int launch_attn_op(const AttnOp& op, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------------------
 size_t groupnorm_scratch_bytes(int n_img, int groups) { return (gn_scratch_bytes(n_img, groups) + 255) & ~size_t(255); }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_img, int P, int groups, float eps,
                      const float* gamma, const float* beta, int do_silu, void* scratch, int scratch_is_zero,
                      __half* out, cudaStream_t st) {
@@ -356,16 +391,29 @@ int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_i
   LR_CHECK(c0 % 8 == 0 && c1 % 8 == 0, "groupnorm: channels must be multiples of 8");
   LR_CHECK(C % groups == 0, "groupnorm: channels not divisible by groups");
   LR_CHECK(C / 8 <= kNormThreads, "groupnorm: too many channels");
+  LR_CHECK(groups <= kNormThreads, "groupnorm: too many groups");
   LR_CHECK(x1 != nullptr || c1 == 0, "groupnorm: c1 without x1");
-  // long pixel runs per CTA amortise its tail (smem reduction, fp64 atomics, ticket). The chunking must NOT depend on
-  // the batch size: the reduction tree has to be identical for any n_img (bit-exact batch invariance).
-  int chunk = P / 32;
+  const int rpi = kNormThreads / (C / 8);
+  const size_t smem = static_cast<size_t>(rpi) * 2 * C * sizeof(float);
+  // Images of up to kGnFusedKB KB per CTA of an 8-CTA cluster take the single-launch fused kernel (second pass hits
+  // L2); larger ones the two-pass scheme. Neither choice depends on the batch size (bit-exact batch invariance).
+  static const int fused_kb = env_int("LR_GN_FUSED_KB", 448);
+  static const int chunk_div = env_int("LR_GN_CHUNK_DIV", 64);
+  constexpr int kCS = 8;
+  const size_t img_bytes = static_cast<size_t>(P) * C * sizeof(__half);
+  if (fused_kb > 0 && groups <= 64 && img_bytes <= static_cast<size_t>(kCS) * fused_kb * 1024) {
+    LR_CUDA(launch_pdl(gn_fused_cluster_kernel, dim3(kCS, n_img), dim3(kNormThreads), smem, st, kCS, x0, c0, x1, c1, P,
+                       groups, eps, gamma, beta, do_silu, out));
+    LR_LAUNCHED();
+    return 0;
+  }
+  LR_CHECK(scratch != nullptr, "groupnorm: scratch buffer required");
+  // The chunking must NOT depend on the batch size: the reduction tree has to be identical for any n_img.
+  int chunk = P / chunk_div;
   if (chunk < 16) chunk = 16;
   if (chunk > 512) chunk = 512;
   const dim3 grid(cdiv(P, chunk), n_img);
   if (!scratch_is_zero) LR_CUDA(cudaMemsetAsync(scratch, 0, gn_scratch_bytes(n_img, groups), st));
-  const int rpi = kNormThreads / (C / 8);
-  const size_t smem = static_cast<size_t>(rpi) * 2 * C * sizeof(float);
   LR_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(kNormThreads), smem, st, 1, x0, c0, x1, c1, P, chunk, groups, eps,
                      static_cast<unsigned char*>(scratch)));
   LR_LAUNCHED();
@@ -375,23 +423,47 @@ int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_i
   return 0;
 }
 
+template <int VPL>
+static int launch_ln_t(const __half* x, int M, int C, const float* gamma, const float* beta, float eps, __half* out,
+                       cudaStream_t st) {
+  const int tile_bytes = kLnTileRows * C * 2;
+  int stages = (96 * 1024) / tile_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  const size_t smem = static_cast<size_t>(stages) * tile_bytes + static_cast<size_t>(2) * C * sizeof(float) +
+                      static_cast<size_t>(2) * stages * sizeof(uint64_t);
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    LR_CUDA(cudaFuncSetAttribute(layernorm_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const int ntiles = cdiv(M, kLnTileRows);
+  int ctas_per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
+  if (ctas_per_sm > 4) ctas_per_sm = 4;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  int blocks = sm_count() * ctas_per_sm;
+  if (blocks > ntiles) blocks = ntiles;
+  LR_CUDA(launch_pdl(layernorm_kernel<VPL>, dim3(blocks), dim3(kLnThreads), smem, st, 1, x, M, C, gamma, beta, eps, out,
+                     stages));
+  LR_LAUNCHED();
+  return 0;
+}
+
 int launch_layernorm(const __half* x, int M, int C, const float* gamma, const float* beta, float eps, __half* out,
                      cudaStream_t st) {
   LR_CHECK(C % 8 == 0, "layernorm: C must be a multiple of 8");
+  LR_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0, "layernorm: input must be 16-byte aligned");
   const int nvec = C / 8;
   const int vpl = cdiv(nvec, 32);
-  const int rows_per_block = 8;
-  const dim3 grid(cdiv(M, rows_per_block));
   switch (vpl) {
-    case 1: LR_CUDA(launch_pdl(layernorm_kernel<1>, grid, dim3(256), 0, st, 1, x, M, C, gamma, beta, eps, out)); break;
-    case 2: LR_CUDA(launch_pdl(layernorm_kernel<2>, grid, dim3(256), 0, st, 1, x, M, C, gamma, beta, eps, out)); break;
-    case 3: LR_CUDA(launch_pdl(layernorm_kernel<3>, grid, dim3(256), 0, st, 1, x, M, C, gamma, beta, eps, out)); break;
-    case 4: LR_CUDA(launch_pdl(layernorm_kernel<4>, grid, dim3(256), 0, st, 1, x, M, C, gamma, beta, eps, out)); break;
-    case 5: LR_CUDA(launch_pdl(layernorm_kernel<5>, grid, dim3(256), 0, st, 1, x, M, C, gamma, beta, eps, out)); break;
-    case 6: case 7: case 8: LR_CUDA(launch_pdl(layernorm_kernel<8>, grid, dim3(256), 0, st, 1, x, M, C, gamma, beta, eps, out)); break;
+    case 1: return launch_ln_t<1>(x, M, C, gamma, beta, eps, out, st);
+    case 2: return launch_ln_t<2>(x, M, C, gamma, beta, eps, out, st);
+    case 3: return launch_ln_t<3>(x, M, C, gamma, beta, eps, out, st);
+    case 4: return launch_ln_t<4>(x, M, C, gamma, beta, eps, out, st);
+    case 5: return launch_ln_t<5>(x, M, C, gamma, beta, eps, out, st);
+    case 6: case 7: case 8: return launch_ln_t<8>(x, M, C, gamma, beta, eps, out, st);
     default: LR_CHECK(false, "layernorm: C > 2048 unsupported");
   }
-  LR_LAUNCHED();
   return 0;
 }
 

@@ -110,6 +110,9 @@ int launch_repack_conv(const float* w, int O, int I, int ldk, __half* out, cudaS
 int launch_repack_linear(const float* w, int O, int I, int geglu, int dst_row0, __half* out, cudaStream_t st);
 int launch_repack_bias(const float* b, int O, int geglu, float* out, cudaStream_t st);
 
+unsigned long long* debug_trace_buffer();
+int debug_read_trace(void* dst, size_t bytes, int clear);
+
 long long launches_since_reset();
 void reset_launch_counter();
 
