@@ -89,6 +89,9 @@ int lr_unet_read_profile(lr_unet* h, double ms_by_class[5], double flops_by_clas
 /* Per plan step: duration of the last profiled forward (ms, -1 if none), algorithmic FLOPs, class, description. */
 int lr_unet_num_steps(const lr_unet* h);
 int lr_unet_step_info(lr_unet* h, int index, double* ms, double* flops, int* cls, char* desc, int desc_len);
+/* Incremented whenever the engine rebuilds its static plan (new batch / latent shape / context length): device
+ * pointers baked into a captured CUDA graph of lr_unet_forward* are valid only while this value is unchanged. */
+long long lr_unet_plan_generation(const lr_unet* h);
 /* Algorithmic FLOPs (2*M*N*K convs/linears + 4*Tq*Tk*d attention) of the last planned forward. */
 double lr_unet_last_flops(const lr_unet* h);
 /* Bytes of device memory held by the engine (weights + activation plan). */
@@ -100,6 +103,12 @@ long long lr_unet_device_bytes(const lr_unet* h);
 int lr_ddim_update(const float* x, const float* eps_uncond, const float* eps_cond, const float* noise, float cfg_scale,
                    float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at, float temperature, int64_t numel,
                    float* x_prev, float* pred_x0, void* stream);
+/* Same update with the per-step scalars in DEVICE memory, coef = {cfg_scale, a_t, a_prev, sigma_t, sqrt(1 - a_t)}
+ * (fp32): the launch is identical for every DDIM step, which lets the drop-in DDIMSampler capture ONE CUDA graph of
+ * (UNet forward + update) and replay it for all steps of ddim_sampling (ddim.py:253-296). x_prev may alias x. */
+int lr_ddim_update_dev(const float* x, const float* eps_uncond, const float* eps_cond, const float* noise,
+                       const float* coef, float temperature, int64_t numel, float* x_prev, float* pred_x0,
+                       void* stream);
 
 /* ---- op-level entry points (what CrossAttention / ResBlock / SpatialTransformer mirrors call stand-alone) ------
  * Activations are NHWC fp16: row = (n*H + y)*W + x, channels contiguous. */

@@ -56,6 +56,9 @@ SIGNATURES = {
     "lr_unet_num_steps": (c_int, [c_void_p]),
     "lr_unet_step_info": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_double), POINTER(c_int), c_char_p,
                                   c_int]),
+    "lr_unet_plan_generation": (c_longlong, [c_void_p]),
+    "lr_ddim_update_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int64, c_void_p,
+                                   c_void_p, c_void_p]),
     "lr_unet_last_flops": (c_double, [c_void_p]),
     "lr_unet_device_bytes": (c_longlong, [c_void_p]),
     "lr_ddim_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float,

@@ -734,6 +734,26 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __r
   x_prev[i] = sqrtf(a_prev) * p0 + dir + nz;
 }
 
+// Same update with the per-step scalars read from DEVICE memory, coef = {cfg, a_t, a_prev, sigma, sqrt(1 - a_t)}:
+// the launch arguments do not change from step to step, so one captured CUDA graph serves all DDIM steps.
+__global__ void ddim_update_dev_kernel(const float* x /* may alias x_prev */, const float* __restrict__ e_u,
+                                       const float* __restrict__ e_c, const float* __restrict__ noise,
+                                       const float* __restrict__ coef, float temperature, size_t n,
+                                       float* x_prev, float* __restrict__ pred_x0) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float cfg = coef[0], a_t = coef[1], a_prev = coef[2], sigma = coef[3], sqrt_one_minus_at = coef[4];
+  float e = e_u[i];
+  if (e_c != nullptr) e = e + cfg * (e_c[i] - e);
+  const float p0 = (x[i] - sqrt_one_minus_at * e) / sqrtf(a_t);
+  const float dir = sqrtf(1.0f - a_prev - sigma * sigma) * e;
+  const float nz = noise != nullptr ? sigma * noise[i] * temperature : 0.f;
+  pred_x0[i] = p0;
+  x_prev[i] = sqrtf(a_prev) * p0 + dir + nz;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Weight repacking (fp32 PyTorch layouts -> fp16 GEMM layouts), run once per weight update.
 // ------------------------------------------------------------------------------------------------------------

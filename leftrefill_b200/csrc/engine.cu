@@ -124,6 +124,7 @@ struct lr_unet {
 
   // ---- plan state ----
   int pn = 0, ph = 0, pw = 0;  // planned shape
+  long long plan_generation = 0;  // bumped whenever the plan (and with it every activation pointer) is rebuilt
   int pshared = 0;             // planned with the CFG-pair shared prefix
   int shared_ns = 0;           // > 0 while planning the shared prefix: number of images actually computed
   Pool pool;
@@ -940,6 +941,7 @@ struct lr_unet {
     ph = Hh;
     pw = Ww;
     pshared = shared;
+    ++plan_generation;
     return 0;
   }
 };
@@ -1127,6 +1129,17 @@ int lr_unet_forward_cfg_pair(lr_unet* h, const float* x, const int64_t* timestep
   h->out_y = out;
   for (auto& s : h->steps) LR_TRY(s.fn(st));
   return 0;
+}
+
+long long lr_unet_plan_generation(const lr_unet* h) { return h ? h->plan_generation : -1; }
+
+int lr_ddim_update_dev(const float* x, const float* eps_uncond, const float* eps_cond, const float* noise,
+                       const float* coef, float temperature, int64_t numel, float* x_prev, float* pred_x0,
+                       void* stream) {
+  LR_CHECK(x && eps_uncond && coef && x_prev && pred_x0 && numel >= 0, "lr_ddim_update_dev: bad argument");
+  if (numel == 0) return 0;
+  return launch_ddim_update_dev(x, eps_uncond, eps_cond, noise, coef, temperature, static_cast<size_t>(numel), x_prev,
+                                pred_x0, static_cast<cudaStream_t>(stream));
 }
 
 double lr_unet_last_flops(const lr_unet* h) { return h ? h->flops : 0.0; }

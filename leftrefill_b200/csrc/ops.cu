@@ -542,6 +542,13 @@ int launch_ddim_update(const float* x, const float* e_u, const float* e_c, const
   LR_LAUNCHED();
   return 0;
 }
+int launch_ddim_update_dev(const float* x, const float* e_u, const float* e_c, const float* noise, const float* coef,
+                           float temperature, size_t n, float* x_prev, float* pred_x0, cudaStream_t st) {
+  LR_CUDA(launch_pdl(ddim_update_dev_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, 1, x, e_u,
+                     e_c, noise, coef, temperature, n, x_prev, pred_x0));
+  LR_LAUNCHED();
+  return 0;
+}
 int launch_repack_conv(const float* w, int O, int I, int ldk, __half* out, cudaStream_t st) {
   const size_t total = static_cast<size_t>(O) * ldk;
   repack_conv_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(w, O, I, ldk, out);

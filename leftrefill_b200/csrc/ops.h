@@ -106,6 +106,8 @@ int launch_timestep_embedding(const long long* t, int t_count, int n, int dim, f
 int launch_ddim_update(const float* x, const float* e_u, const float* e_c, const float* noise, float cfg, float a_t,
                        float a_prev, float sigma, float sqrt_one_minus_at, float temperature, size_t n, float* x_prev,
                        float* pred_x0, cudaStream_t st);
+int launch_ddim_update_dev(const float* x, const float* e_u, const float* e_c, const float* noise, const float* coef,
+                           float temperature, size_t n, float* x_prev, float* pred_x0, cudaStream_t st);
 int launch_repack_conv(const float* w, int O, int I, int ldk, __half* out, cudaStream_t st);
 int launch_repack_linear(const float* w, int O, int I, int geglu, int dst_row0, __half* out, cudaStream_t st);
 int launch_repack_bias(const float* b, int O, int geglu, float* out, cudaStream_t st);

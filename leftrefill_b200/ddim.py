@@ -10,8 +10,15 @@ What changes is where the work happens:
   * when the wrapped model is a `leftrefill_b200.UNetModel` under 'hybrid' conditioning, the step-invariant work is
     hoisted out of the loop: cat(uncond, cond) context is built once and its cross-attention K/V cached in the
     engine, c_concat is staged once, and the UNet runs the CFG pair as one batched native forward per step.
+  * on that fast path the per-step work (stage x_t into the 9-channel input, UNet CFG forward, fused update) is
+    captured ONCE as a CUDA graph whose step-dependent scalars (timestep, a_t, a_prev, sigma_t, ...) live in device
+    memory, and replayed for every step: ~410 kernel launches per step cost the host one graph launch. The graph is
+    cached on the UNet module (keyed by shapes and the engine's plan generation), so later `sample` calls reuse it.
+    `LR_NO_CUDA_GRAPH=1` keeps the eager loop (bit-identical results; the kernels and their order are the same).
 Anything else (other models / conditioning layouts) goes through `model.apply_model` exactly like the reference.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -45,6 +52,55 @@ def make_ddim_sampling_parameters(alphacums, ddim_timesteps, eta, verbose=True):
         print(f"For the chosen value of eta, which is {eta}, this results in the following sigma_t schedule for ddim "
               f"sampler {sigmas}")
     return sigmas, alphas, alphas_prev
+
+
+class _StepGraph:
+    """One captured CUDA graph of a whole DDIM step on the native fast path, replayed for every step.
+
+    Static device buffers (graph inputs / outputs): x (the fp32 latent state, updated in place), xc (the UNet input
+    with c_concat pre-staged), t (int64 timesteps), coef (cfg, a_t, a_prev, sigma_t, sqrt(1 - a_t)), noise, pred_x0.
+    """
+
+    def __init__(self, unet, nb, b, cx, c_total, H, W, pair, use_cfg, temperature, device):
+        from . import _native as N
+        self.unet, self.nb, self.b, self.pair, self.use_cfg = unet, nb, b, pair, use_cfg
+        self.temperature = float(temperature)
+        self.x = torch.zeros(b, cx, H, W, dtype=torch.float32, device=device)
+        self.xc = torch.zeros(nb, c_total, H, W, dtype=torch.float32, device=device)
+        self.t = torch.full((nb,), 1, dtype=torch.long, device=device)
+        self.coef = torch.tensor([1.0, 0.5, 0.6, 0.1, 0.5 ** 0.5], dtype=torch.float32, device=device)
+        self.noise = torch.zeros_like(self.x)
+        self.pred_x0 = torch.zeros_like(self.x)
+        self.graph = None
+        # eager warm-up on a side stream: builds the engine's plan (device allocations are illegal during capture)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            self._body()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.generation = N.lib().lr_unet_plan_generation(unet.engine())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._body()
+        self.graph = graph
+
+    def _body(self):
+        cx = self.x.shape[1]
+        if self.pair and self.use_cfg:
+            self.xc[:, :cx] = self.x
+            e = self.unet.forward_native_cfg_pair(self.xc, self.t)
+        else:
+            self.xc[:self.b, :cx] = self.x
+            if self.use_cfg:
+                self.xc[self.b:, :cx] = self.x
+            e = self.unet.forward_native(self.xc, self.t, None)
+        e_u, e_c = (e[:self.b], e[self.b:]) if self.use_cfg else (e, None)
+        ops.ddim_update_dev(self.x, e_u, e_c, self.noise, self.coef, self.temperature, self.x, self.pred_x0)
+
+    def valid(self):
+        from . import _native as N
+        return self.graph is not None and N.lib().lr_unet_plan_generation(self.unet.engine()) == self.generation
 
 
 class DDIMSampler(object):
@@ -175,6 +231,12 @@ class DDIMSampler(object):
             xc = torch.empty(nb, img.shape[1] + c_cat.shape[1], shape[2], shape[3], dtype=torch.float32, device=device)
             xc[:, img.shape[1]:] = c_cat
             staged = (xc, nb, pair)
+            if noise_dropout == 0. and os.environ.get("LR_NO_CUDA_GRAPH") is None and torch.cuda.is_available():
+                sg = self._step_graph(unet, nb, b, img.shape[1], xc.shape[1], shape[2], shape[3], pair, use_cfg,
+                                      temperature, device)
+                if sg is not None:
+                    return self._graphed_loop(sg, img, c_cat, time_range, total_steps, mask, x0, callback,
+                                              img_callback, log_every_t, unconditional_guidance_scale, intermediates)
 
         x = img.float()
         for i, step in enumerate(time_range):
@@ -209,6 +271,62 @@ class DDIMSampler(object):
                 intermediates["x_inter"].append(x)
                 intermediates["pred_x0"].append(pred_x0)
         return x, intermediates
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _step_graph(self, unet, nb, b, cx, c_total, H, W, pair, use_cfg, temperature, device):
+        """Returns the cached (or freshly captured) step graph for this configuration, None if capture is unavailable."""
+        key = (nb, b, cx, c_total, H, W, bool(pair), bool(use_cfg), float(temperature), str(device))
+        cache = unet.__dict__.setdefault("_step_graphs", {})
+        sg = cache.get(key)
+        if sg is not None and sg is not False and sg.valid():
+            return sg
+        if sg is False:
+            return None
+        try:
+            sg = _StepGraph(unet, nb, b, cx, c_total, H, W, pair, use_cfg, temperature, device)
+        except Exception as e:  # noqa: BLE001 - capture is an optimisation: fall back to the eager loop, say so once
+            print(f"leftrefill_b200: CUDA graph capture of the DDIM step failed ({str(e)[:200]}); using the eager loop")
+            torch.cuda.synchronize(device)
+            cache[key] = False
+            return None
+        cache[key] = sg
+        return sg
+
+    def _graphed_loop(self, sg, img, c_cat, time_range, total_steps, mask, x0, callback, img_callback, log_every_t,
+                      cfg_scale, intermediates):
+        """ddim_sampling's loop (ddim.py:253-296) with the whole step as one graph replay. RNG consumption is the
+        reference's: one normal draw of x's shape per step, after the model call of that step."""
+        device = sg.x.device
+        cx = sg.x.shape[1]
+        sg.xc[:, cx:] = c_cat
+        sg.x.copy_(img.float())
+        idx = [total_steps - i - 1 for i in range(total_steps)]
+        table = np.stack([np.full(total_steps, cfg_scale, dtype=np.float64), self.ddim_alphas[idx],
+                          self.ddim_alphas_prev[idx], self.ddim_sigmas[idx], self.ddim_sqrt_one_minus_alphas[idx]],
+                         axis=1).astype(np.float32)
+        coef_table = torch.from_numpy(table).to(device)
+        for i, step in enumerate(time_range):
+            index = total_steps - i - 1
+            if mask is not None:
+                assert x0 is not None
+                ts = torch.full((sg.b,), int(step), device=device, dtype=torch.long)
+                img_orig = self.model.q_sample(x0, ts)
+                sg.x.copy_(img_orig * mask + (1. - mask) * sg.x)
+            sg.t.fill_(int(step))
+            sg.coef.copy_(coef_table[i])
+            if self.noise_source is not None:
+                sg.noise.copy_(self.noise_source(sg.x.shape, device, i))
+            else:
+                sg.noise.normal_()
+            sg.graph.replay()
+            if callback:
+                callback(i)
+            if img_callback:
+                img_callback(sg.pred_x0.clone(), i)
+            if index % log_every_t == 0 or index == total_steps - 1:
+                intermediates["x_inter"].append(sg.x.clone())
+                intermediates["pred_x0"].append(sg.pred_x0.clone())
+        return sg.x.clone(), intermediates
 
     def _apply_model(self, x, c, step, uc, use_cfg):
         """Generic path: the reference's CFG batching around model.apply_model (ddim.py:311-343)."""

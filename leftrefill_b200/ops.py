@@ -135,3 +135,15 @@ def ddim_update(x, eps_uncond, eps_cond, noise, cfg_scale, a_t, a_prev, sigma_t,
                                    float(sigma_t), float(sqrt_one_minus_at), float(temperature), x.numel(),
                                    N.ptr(x_prev), N.ptr(pred_x0), N.current_stream()), "ddim_update")
     return x_prev, pred_x0
+
+
+def ddim_update_dev(x, eps_uncond, eps_cond, noise, coef, temperature, x_prev, pred_x0):
+    """ddim_update with the step scalars in device memory: coef fp32 [5] = (cfg, a_t, a_prev, sigma_t, sqrt(1 - a_t)).
+    Writes into the given x_prev (may alias x) / pred_x0 buffers; CUDA-graph capturable (no allocation)."""
+    _chk(x, torch.float32)
+    _chk(coef, torch.float32)
+    assert coef.numel() >= 5
+    N.check(N.lib().lr_ddim_update_dev(N.ptr(x), N.ptr(_chk(eps_uncond, torch.float32)), N.ptr(eps_cond),
+                                       N.ptr(noise), N.ptr(coef), float(temperature), x.numel(), N.ptr(_chk(x_prev)),
+                                       N.ptr(_chk(pred_x0)), N.current_stream()), "ddim_update_dev")
+    return x_prev, pred_x0

@@ -164,6 +164,40 @@ def test_sampler_generic_path_equals_fast_path(small):
     assert torch.equal(outs[0][1], outs[1][1])  # both routes consumed the same number of random draws
 
 
+def test_sampler_cuda_graph_equals_eager_loop(small, monkeypatch):
+    """The captured step graph (one replay per DDIM step, scalars in device memory) must reproduce the eager loop bit
+    for bit, consume the same random draws, and be reusable by a later sample() call with other conditioning."""
+    import leftrefill_b200 as lr
+    m, _ = small
+    dev = torch.device("cuda")
+    m.__dict__.pop("_step_graphs", None)
+    results = {}
+    for seed_inputs in (1234, 77):
+        x_T, c_cat, ctx, uc = synthetic_inputs(2, h=16, w=32, ctx_dim=256, seed=seed_inputs, device=dev)
+        cond = {"c_concat": [c_cat], "c_crossattn": [ctx]}
+        ucond = {"c_concat": [c_cat], "c_crossattn": [uc]}
+        for mode in ("graph", "eager"):
+            if mode == "eager":
+                monkeypatch.setenv("LR_NO_CUDA_GRAPH", "1")
+            else:
+                monkeypatch.delenv("LR_NO_CUDA_GRAPH", raising=False)
+            torch.manual_seed(321)
+            s = lr.DDIMSampler(FakeLDM(m, dev))
+            y, inter = s.sample(5, 2, (4, 16, 32), cond, eta=1.0, verbose=False, unconditional_guidance_scale=2.5,
+                                unconditional_conditioning=ucond, log_every_t=2)
+            results[(seed_inputs, mode)] = (y, inter, torch.rand(1, device=dev))
+        yg, ig, rg = results[(seed_inputs, "graph")]
+        ye, ie, re = results[(seed_inputs, "eager")]
+        assert torch.equal(yg, ye), (yg - ye).abs().max().item()
+        assert len(ig["x_inter"]) == len(ie["x_inter"]) and len(ig["pred_x0"]) == len(ie["pred_x0"])
+        for a, b in zip(ig["pred_x0"][1:], ie["pred_x0"][1:]):
+            assert torch.equal(a, b)
+        assert torch.equal(rg, re)
+    graphs = m.__dict__.get("_step_graphs", {})
+    assert len(graphs) == 1 and all(g is not False for g in graphs.values()), "one graph, captured once, reused"
+    assert not torch.equal(results[(1234, "graph")][0], results[(77, "graph")][0])
+
+
 def _cfg_pair_check(m, cfg, hw, nb):
     dev = "cuda"
     xT, c_cat, ctx, uc = synthetic_inputs(nb, h=hw[0], w=hw[1], ctx_dim=cfg["context_dim"], device=dev)
