@@ -7,7 +7,8 @@ import os
 from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblr_b200.so")
+# LR_B200_LIB: A/B experiments against another build of the same ABI (tests/gpu_time_gemm.py); normal use never sets it
+LIB_PATH = os.environ.get("LR_B200_LIB") or os.path.join(_HERE, "liblr_b200.so")
 
 
 class LRError(RuntimeError):

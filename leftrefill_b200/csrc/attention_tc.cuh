@@ -4,11 +4,11 @@
 // fp16 operands, fp32 QK^T accumulation (the reference's _ATTN_PRECISION="fp32" path), fp32 softmax statistics.
 //
 // One CTA = one (batch, head, 256-query block) = two 128-row query tiles that ping-pong on the tensor core. d_head = 64.
-//   warp 0 (1 lane)   : TMA — Q0/Q1 once, then a 3-stage ring of {K_j, V_j} 128-token tiles shared by both query tiles
-//   warp 1 (1 lane)   : tcgen05.mma — S_t = Q_t K_j^T (128x128 fp32 in TMEM), O_t += P_t V_j (128x64 fp32 in TMEM) with
-//                       P_t read from TENSOR MEMORY (fp16 pairs, 64 columns): the softmax result never touches shared
-//                       memory. S_t(j+1) is issued as soon as warpgroup t has pulled S_t(j) into registers, so in
-//                       steady state a warpgroup never waits for the tensor pipe.
+//   warp 0 (1 lane)   : TMA — Q0/Q1 once, then a 4-stage ring of {K_j, V_j} 128-token tiles shared by both query tiles
+//   warps 1, 2 (1 lane): tcgen05.mma for query tile 0 / 1 — S_t = Q_t K_j^T (128x128 fp32 in TMEM), O_t += P_t V_j
+//                       (128x64 fp32 in TMEM) with P_t read from TENSOR MEMORY (fp16 pairs, 64 columns): the softmax
+//                       result never touches shared memory. S_t(j+1) is issued as soon as warpgroup t has pulled
+//                       S_t(j) into registers, so in steady state a warpgroup never waits for the tensor pipe.
 //   warps 4..7, 8..11 : softmax warpgroup for tile 0 / tile 1 — thread <-> query row (tcgen05.ld 32x32b), the whole
 //                       128-wide logits row lives in registers, online max with lazy rescaling of the TMEM-resident O
 //                       (threshold 2^8), P_t = exp2(.) packed to fp16 pairs and stored with tcgen05.st.
@@ -34,10 +34,19 @@ constexpr int kAttnTile = 128;                          // rows of one query til
 constexpr int kAttnQBlock = 2 * kAttnTile;              // queries per CTA
 constexpr int kAttnD = 64;
 constexpr int kAttnTileBytes = kAttnTile * kAttnD * 2;  // 16 KB
-constexpr int kAttnStages = 3;
+constexpr int kAttnStages = 4;
 constexpr int kAttnSmemBytes = 2 * kAttnTileBytes /*Q0,Q1*/ + kAttnStages * 2 * kAttnTileBytes /*K,V ring*/ +
                                256 /*barriers*/;
 constexpr int kTmemS = 0, kTmemP = 256, kTmemO = 384;  // column bases (S: 128 per tile, P: 64, O: 64)
+// Softmax ping-pong (A/B: -DLR_ATTN_PINGPONG=0): the two warpgroups take turns in the exp2 phase (named barriers 2/3),
+// so one warpgroup owns the MUFU unit (16 ex2/clk/SM) while the other loads S, finds the row max and stores P. Without
+// it both drift into lock step, share the MUFU at half rate each and leave it idle during their common non-exp phases.
+#ifndef LR_HI_WARP_ISSUE
+#define LR_HI_WARP_ISSUE 0
+#endif
+#ifndef LR_ATTN_PINGPONG
+#define LR_ATTN_PINGPONG 1
+#endif
 constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P stays <= 256, exact in fp16/fp32 accumulators
 
 template <bool B>
@@ -71,16 +80,24 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   uint8_t* k_s = q_s + 2 * kAttnTileBytes;                   // [stages]
   uint8_t* v_s = k_s + kAttnStages * kAttnTileBytes;         // [stages]
   uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + kAttnStages * kAttnTileBytes);
-  uint64_t* q_full = bars;          // 1
-  uint64_t* kv_full = bars + 1;     // [3]
-  uint64_t* kv_empty = bars + 4;    // [3]
-  uint64_t* s_full = bars + 7;      // [2] S_t(j) is in TMEM
-  uint64_t* s_empty = bars + 9;     // [2] warpgroup t holds S_t(j) in registers
-  uint64_t* p_full = bars + 11;     // [2] P_t(j) is in TMEM
-  uint64_t* pv_done = bars + 13;    // [2] O_t += P_t(j) V_j has completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* q_full = bars;                         // 1
+  uint64_t* kv_full = bars + 1;                    // [stages]
+  uint64_t* kv_empty = kv_full + kAttnStages;      // [stages]
+  uint64_t* s_full = kv_empty + kAttnStages;       // [2] S_t(j) is in TMEM
+  uint64_t* s_empty = s_full + 2;                  // [2] warpgroup t holds S_t(j) in registers
+  uint64_t* p_full = s_empty + 2;                  // [2] P_t(j) is in TMEM
+  uint64_t* pv_done = p_full + 2;                  // [2] O_t += P_t(j) V_j has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // roles: 0 = TMA, 1 / 2 = MMA issuer of query tile 0 / 1, 3 = idle, 4..7 / 8..11 = softmax warpgroup 0 / 1.
+  // -DLR_HI_WARP_ISSUE=1 moves the issuing roles to the highest hardware warp ids (8..10); measured on B200 (round 1,
+  // r1h): 893 us instead of 854 us at 8 x 5 heads x 8192^2, so the issuers stay on the lowest ids.
+  const int hw_warp = threadIdx.x >> 5;
+#if LR_HI_WARP_ISSUE
+  const int warp = (hw_warp + 4) % 12;
+#else
+  const int warp = hw_warp;
+#endif
   const int lane = threadIdx.x & 31;
   const int qb = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int ntiles = (p.tk + kAttnTile - 1) / kAttnTile;
@@ -100,7 +117,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     mbar_init(q_full, 1);
     for (int i = 0; i < kAttnStages; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], ntq);  // one tcgen05.commit per query tile's issuing warp
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
@@ -140,11 +157,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         }
         __syncwarp();
       }
-    } else if (warp == 1) {
-      // ------------------------------- MMA issuer (whole warp loops, one elected lane issues) ----------------
-      // Descriptors are a constant high word plus a 32-bit low word (address >> 4) kept in uniform registers: advancing
-      // along K is one add. (Building each descriptor from scratch inside `if (lane == 0)` cost ~130 issue cycles per
-      // MMA — 24 MMAs per KV tile pair = the 3000-cycle period every earlier version of this kernel was stuck at.)
+    } else if (warp - 1 < ntq) {
+      // ------------------------------- MMA issuers: warp 1 -> query tile 0, warp 2 -> query tile 1 -------------
+      // One issuing warp PER query tile, each following its own warpgroup with BLOCKING mbarrier waits in program
+      // order (a suspended try_wait wakes ~60 cycles after the arrive). The earlier single-warp event loop polled six
+      // barriers with mbarrier.test_wait (~150 cycles each): a warpgroup waited ~740 cycles per KV tile for an S tile
+      // whose inputs had been ready for a long time (in-kernel trace, profiles/r1b_trace.log).
+      // Whole warp loops, one elected lane issues. Descriptors are a constant high word plus a 32-bit low word
+      // (address >> 4) kept in uniform registers: advancing along K is one add.
+      const int t = warp - 1;
       const uint32_t idesc_s = umma_idesc_f16(128, kAttnTile, 0);  // S: N = 128 keys, K-major B
       const uint32_t idesc_o = umma_idesc_f16(128, kAttnD, 1);     // O: N = 64 channels, MN-major B (V)
       const uint32_t desc_hi = umma_desc_hi_sw128(1024);
@@ -152,7 +173,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       const uint32_t k_lo = umma_desc_lo(smem_u32(k_s), 16);
       const uint32_t v_lo = umma_desc_lo(smem_u32(v_s), 16);
       constexpr uint32_t kTileUnits = kAttnTileBytes >> 4;
-      auto issue_s = [&](int t, int stage) {  // S_t = Q_t K^T : 4 k-steps of 16 channels (32 B = 2 units each)
+      auto issue_s = [&](int stage) {  // S_t = Q_t K^T : 4 k-steps of 16 channels (32 B = 2 units each)
 #pragma unroll
         for (int k = 0; k < kAttnD / 16; ++k) {
           umma_f16(tmem_base + kTmemS + t * 128, umma_desc_make(desc_hi, q_lo + t * kTileUnits + 2 * k),
@@ -160,7 +181,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         }
         umma_commit(&s_full[t]);
       };
-      auto issue_pv = [&](int t, int stage, uint32_t accumulate) {
+      auto issue_pv = [&](int stage, uint32_t accumulate) {
         // A = P_t from TMEM (8 columns = 16 fp16 per k step); B = 16 token rows of V (16 x 128 B = 128 units), MN-major
 #pragma unroll
         for (int k = 0; k < kAttnTile / 16; ++k) {
@@ -168,63 +189,33 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                       umma_desc_make(desc_hi, v_lo + stage * kTileUnits + k * 128), idesc_o, (accumulate | k) != 0 ? 1u : 0u);
         }
         umma_commit(&pv_done[t]);
+        umma_commit(&kv_empty[stage]);  // the stage is free once BOTH tiles' PV MMAs have read it (count = ntq)
       };
       mbar_wait(q_full, 0);
-      // Event-driven issue: whichever of {S_t(next), PV_t(next)} has its inputs ready goes first, so a slow warpgroup
-      // never blocks the other tile's MMAs (no head-of-line blocking on a fixed t = 0, 1 order).
-      int ns[2] = {0, 0};   // next S index per tile
-      int npv[2] = {0, 0};  // next PV index per tile
-      int freed = 0;        // KV stages released so far
-      long long t0 = clock64();
-      while (npv[0] < ntiles || (ntq == 2 && npv[1] < ntiles)) {
-        bool progress = false;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (t >= ntq) continue;
-          const int j = ns[t];
-          bool go_s = false;
-          if (j < ntiles && j - npv[t] < 2)  // S_t(j) may run one tile ahead of PV_t (S is single-buffered)
-            go_s = mbar_test(&kv_full[j % kAttnStages], (j / kAttnStages) & 1) &&
-                   (j == 0 || mbar_test(&s_empty[t], (j - 1) & 1));
-          go_s = __shfl_sync(0xffffffffu, go_s ? 1 : 0, 0) != 0;  // warp-uniform decision
-          if (go_s) {
-            tc_fence_after();
-            if (elect_one()) issue_s(t, j % kAttnStages);
-            __syncwarp();
-            ns[t] = j + 1;
-            progress = true;
-          }
-          const int i = npv[t];
-          bool go_pv = (i < ns[t]) && mbar_test(&p_full[t], i & 1);
-          go_pv = __shfl_sync(0xffffffffu, go_pv ? 1 : 0, 0) != 0;
-          if (go_pv) {
-            tc_fence_after();
-            if (elect_one()) issue_pv(t, i % kAttnStages, i > 0 ? 1u : 0u);
-            __syncwarp();
-            npv[t] = i + 1;
-            progress = true;
-          }
-        }
-        const int done = (ntq == 2) ? min(npv[0], npv[1]) : npv[0];
-        while (freed < done) {
-          if (elect_one()) umma_commit(&kv_empty[freed % kAttnStages]);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      if (elect_one()) issue_s(0);
+      __syncwarp();
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) {
+          // S_t(j+1) runs one tile ahead: it needs K_{j+1} and the warpgroup to have pulled S_t(j) into registers
+          const int s1 = (j + 1) % kAttnStages;
+          mbar_wait(&kv_full[s1], ((j + 1) / kAttnStages) & 1);
+          mbar_wait(&s_empty[t], j & 1);
+          tc_fence_after();
+          if (elect_one()) issue_s(s1);
           __syncwarp();
-          ++freed;
         }
-        if (progress) {
-          t0 = clock64();
-        } else if (clock64() - t0 > 4000000000LL) {
-          if (lane == 0)
-            printf("lr_b200: attention MMA issue loop stalled block=(%d,%d,%d) ns=%d,%d npv=%d,%d\n", blockIdx.x,
-                   blockIdx.y, blockIdx.z, ns[0], ns[1], npv[0], npv[1]);
-          __trap();
-        }
+        mbar_wait(&p_full[t], j & 1);
+        tc_fence_after();
+        if (elect_one()) issue_pv(j % kAttnStages, j > 0 ? 1u : 0u);
+        __syncwarp();
       }
     }
   } else {
     // ------------------------------- softmax warpgroups ---------------------------
     const int t = (warp - 4) >> 2;  // query tile of this warpgroup
-    const int q = warp & 3;         // TMEM lane quarter
+    const int q = hw_warp & 3;      // TMEM lane quarter (hardware warp id % 4)
     const int r = q * 32 + lane;    // row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t tmem_S = tmem_base + kTmemS + t * 128 + lane_addr;
@@ -245,6 +236,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         tr_t = now;
       }
     };
+#if LR_ATTN_PINGPONG
+    if (ntq == 2 && t == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");  // warpgroup 0 goes first
+#endif
     auto tile_body = [&](int j, auto mask_tag) {
       constexpr bool kMask = decltype(mask_tag)::value;
       mbar_wait(&s_full[t], j & 1);
@@ -291,6 +285,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         l *= alpha;
       }
       mark(2);
+#if LR_ATTN_PINGPONG
+      if (ntq == 2) asm volatile("bar.sync %0, 256;" ::"r"(2 + t) : "memory");  // my turn on the MUFU
+#endif
       // P = exp2((s - m_used) * scale_log2) as fp16 pairs, kept in registers until the previous PV has released P_t
       const float moff = m_used * p.scale_log2;
       uint32_t h[64];
@@ -309,6 +306,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         h[i + 1] = pack_half2(e2, e3);
       }
       l += (l0 + l1) + (l2 + l3);
+#if LR_ATTN_PINGPONG
+      // hand the MUFU to the other warpgroup (its last turn needs no successor)
+      if (ntq == 2 && !(t == 1 && j == my_tiles - 1)) asm volatile("bar.arrive %0, 256;" ::"r"(3 - t) : "memory");
+#endif
       mark(3);
       if (j > 0) {
         mbar_wait(&pv_done[t], (j - 1) & 1);  // PV(j-1) finished reading P_t and updating O_t

@@ -66,7 +66,13 @@ struct GemmParams {
       p.trace[((role) * 16 + (tcount)) * 8 + (slot)] = static_cast<unsigned long long>(clock64());           \
   } while (0)
 
-constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+// Warp roles: role 0 = TMA producer, role 1 = MMA issuer, roles 2..9 = epilogue. -DLR_HI_WARP_ISSUE=1 moves the two
+// single-lane issuing roles to the highest hardware warp ids (8, 9); measured on B200 (round 1, r1h): no difference for
+// this kernel, so the natural order stays the default.
+#ifndef LR_HI_WARP_ISSUE
+#define LR_HI_WARP_ISSUE 0
+#endif
+constexpr int kGemmThreads = 320;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kBlockM = 128;
@@ -116,7 +122,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][256]
 
-  const int warp = threadIdx.x >> 5;
+  const int hw_warp = threadIdx.x >> 5;
+#if LR_HI_WARP_ISSUE
+  const int warp = (hw_warp + 2) % 10;  // role: hardware warps 0..7 -> epilogue (2..9), 8 -> producer (0), 9 -> MMA (1)
+#else
+  const int warp = hw_warp;
+#endif
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents();
 
@@ -259,10 +270,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     // ------------------------------- epilogue warps -----------------------------
     // 8 warps: warp (2+w) reads TMEM lane quarter (w & 3); the two warps of a quarter interleave 32-column chunks.
     const int ew = warp - 2;
-    const int q = warp & 3;  // TMEM lane quarter this warp may access (hardware: warp id % 4)
+    const int q = hw_warp & 3;  // TMEM lane quarter this warp may access (hardware: warp id % 4)
     const int half = ew >> 2;
     const int r = q * 32 + lane;
-    const int etid = threadIdx.x - 64;
+    const int etid = ew * 32 + lane;
     int as = 0;
     uint32_t aph = 0;
     const bool vec_ok = (p.ld_out % 8 == 0) && (p.residual == nullptr || p.ld_res % 8 == 0);

@@ -43,7 +43,7 @@ if len(sys.argv) > 1:
         out.append(f"{f}{'+res' if res is not None else ''}: {e0.elapsed_time(e1) * 100:6.1f}us")
     print(f"dbg={os.environ.get('LR_GEMM_DEBUG', '0')}  lin320: " + "  ".join(out), flush=True)
 else:
-    for dbg in (0, 7, 7 + 8, 7 + 16, 7 + 32, 7 + 8 + 16, 7 + 8 + 16 + 32):
+    for dbg in [int(v) for v in os.environ.get('LR_DBG_LIST', '0,3,4,7').split(',')]:
         env = dict(os.environ, LR_GEMM_DEBUG=str(dbg))
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "run"], env=env, capture_output=True, text=True,
                            timeout=120)
