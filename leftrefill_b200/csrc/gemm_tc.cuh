@@ -34,7 +34,10 @@ struct GemmParams {
   CUtensorMap tmC;   // output [n_valid, W, H, N], box (64 cols, bw, bh, bn), 128B swizzle   (TMA-store epilogue)
   CUtensorMap tmC2;  // same tensor, box (32 cols, ...), no swizzle: the 32-column remainder slab of a tile
   int tma_store;     // 1: epilogue stages the fp16 tile in smem and writes it with TMA (needs ld_out % 8 == 0)
-  int cstage_off;    // byte offset of the staging buffer inside dynamic smem
+  int cstage_off;    // byte offset of the staging buffer(s) inside dynamic smem
+  int cstage_bufs;   // 1 or 2 staging buffers (2: short main loops, where the epilogue sets the tile period: it then never
+                     // waits for a TMA store to drain its buffer)
+  int cstage_bytes;  // bytes of one staging buffer (multiple of 1024)
   int n_img, H, W;   // OUTPUT pixel grid
   int bw, bh, bn;    // tile box: bw*bh*bn == 128 output pixels
   int tiles_x, tiles_y, tiles_b, tiles_n;
@@ -277,13 +280,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     int as = 0;
     uint32_t aph = 0;
     const bool vec_ok = (p.ld_out % 8 == 0) && (p.residual == nullptr || p.ld_res % 8 == 0);
-    uint8_t* cstage = smem + p.cstage_off;
     const int ocols_tile = p.geglu ? p.block_n / 2 : p.block_n;  // output columns of one tile
     const int full_slabs = ocols_tile >> 6;                      // 64-column slabs [128 rows][128 B], swizzled
     bool stores_pending = false;
+    // bias: one column per epilogue thread (block_n <= 256 = kEpiThreads), fetched ONE TILE AHEAD into a register
+    auto fetch_bias = [&](int tile) -> float {
+      if (tile >= num_tiles || p.bias == nullptr || etid >= p.block_n || (p.dbg & 16)) return 0.f;
+      const int col = (tile % p.tiles_n) * p.block_n + etid;
+      return col < p.ncols ? __ldg(p.bias + col) : 0.f;
+    };
+    float bias_next = fetch_bias(unit0);
     int tcount = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_step, ++tcount) {
       if (ew == 0) LR_GEMM_TR(2, tcount, 0);
+      uint8_t* cstage = smem + p.cstage_off + ((p.cstage_bufs == 2) ? (tcount & 1) * p.cstage_bytes : 0);
       const int tn = tile % p.tiles_n;
       int tm = (tile / p.tiles_n) * CG + static_cast<int>(rank);
       const bool tile_ok = tm < tiles_m;
@@ -300,15 +310,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       const size_t grow = (static_cast<size_t>(n) * p.H + y) * p.W + x;
       const int ncol0 = tn * p.block_n;
 
-      // the previous tile's TMA stores must have drained the staging buffer before anyone overwrites it
-      if (p.tma_store && etid == 0 && stores_pending && !(p.dbg & 8)) tma_store_wait_read();
+      // single staging buffer: the previous tile's TMA stores must have drained it before anyone overwrites it
+      if (p.tma_store && p.cstage_bufs == 1 && etid == 0 && stores_pending && !(p.dbg & 8)) tma_store_wait_read();
       // stage this tile's bias slice (double buffered by accumulator stage; the named barrier orders reuse)
       float* sb = sbias + as * 256;
-      if (!(p.dbg & 16)) {
-        for (int i = etid; i < p.block_n; i += kEpiThreads)
-          sb[i] = (p.bias != nullptr && ncol0 + i < p.ncols) ? __ldg(p.bias + ncol0 + i) : 0.f;
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      }
+      if (etid < p.block_n) sb[etid] = bias_next;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      bias_next = fetch_bias(tile + unit_step);
 
       // residual of the first chunk is fetched before the accumulator is ready (it does not depend on the MMA)
       const bool fast = vec_ok && row_ok && !p.geglu;
@@ -443,6 +451,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       if (p.tma_store) {
         // the fp16 tile is complete in smem: one thread writes it out with TMA (rows / columns outside the tensor are
         // clipped by the tensor map, so partial tiles need no masking)
+        // two staging buffers: the store issued a whole tile ago has long finished reading its buffer; confirming it
+        // here (before the barrier) is free and makes that buffer safe for the next tile
+        if (p.cstage_bufs == 2 && etid == 0 && stores_pending && !(p.dbg & 8)) tma_store_wait_read();
         fence_proxy_async_smem();
         asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
         if (ew == 0) LR_GEMM_TR(2, tcount, 4);

@@ -137,6 +137,10 @@ static int sm_count() {
 // GEMM / conv op
 // ------------------------------------------------------------------------------------------------------------
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 int build_conv_op(ConvOp* op, const ConvSpec& s) {
   LR_CHECK(s.a0 && s.w && s.out, "conv: null pointer");
@@ -226,13 +230,24 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   const bool tma_store = (s.ld_out % 8 == 0) && ((ocols_tile % 64) == 0 || (ocols_tile % 64) == 32) &&
                          (s.residual == nullptr || (n_valid % 32 == 0 && s.ld_res % 8 == 0)) &&
                          getenv("LR_NO_TMA_STORE") == nullptr;
-  const int cstage_bytes = tma_store ? kBlockM * ocols_tile * 2 : 0;
-  int stages = (232448 - 2048 - kGemmAuxBytes - cstage_bytes) / gemm_stage_bytes(block_n, cg);
+  const int cstage_bytes = tma_store ? kBlockM * ocols_tile * 2 : 0;  // multiple of 8 KB: keeps 1024 B alignment
+  // Short main loops (small K): the epilogue sets the tile period, so it gets two staging buffers and never waits for
+  // a TMA store to drain; long main loops keep the shared memory for pipeline stages.
+  const int kiters = s.taps * (cdiv(s.c0, kBlockK) + cdiv(s.c1, kBlockK));
+  static const int two_below = env_int("LR_GEMM_TWO_CSTAGE_KITERS", 24);
+  int bufs = (tma_store && kiters <= two_below) ? 2 : 1;
+  int stages = (232448 - 2048 - kGemmAuxBytes - bufs * cstage_bytes) / gemm_stage_bytes(block_n, cg);
+  if (bufs == 2 && stages < 3) {
+    bufs = 1;
+    stages = (232448 - 2048 - kGemmAuxBytes - cstage_bytes) / gemm_stage_bytes(block_n, cg);
+  }
   if (stages > kMaxStages) stages = kMaxStages;
   LR_CHECK(stages >= 2, "conv: not enough shared memory for 2 stages");
   p.stages = stages;
   p.tma_store = tma_store ? 1 : 0;
   p.cstage_off = (stages * gemm_stage_bytes(block_n, cg) + kGemmAuxBytes + 1023) & ~1023;  // swizzle needs 1024 B
+  p.cstage_bufs = bufs;
+  p.cstage_bytes = cstage_bytes;
   p.bias = s.bias;
   p.bias_img = s.bias_img;
   p.ld_bias_img = s.ld_bias_img > 0 ? s.ld_bias_img : s.ncols;
@@ -293,7 +308,7 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   const int num_units = cdiv(tiles_m, cg) * p.tiles_n;
   const int slots = sm_count() / cg;
   op->grid = (num_units < slots ? num_units : slots) * cg;
-  op->smem = tma_store ? p.cstage_off + cstage_bytes : gemm_smem_bytes(block_n, stages, cg);
+  op->smem = tma_store ? p.cstage_off + bufs * cstage_bytes : gemm_smem_bytes(block_n, stages, cg);
   op->block_n = block_n;
   op->stages = stages;
   op->tiles = num_units;
@@ -378,11 +393,6 @@ int launch_attn_op(const AttnOp& op, cudaStream_t st) {
 // normalisation / elementwise
 // ------------------------------------------------------------------------------------------------------------
 size_t groupnorm_scratch_bytes(int n_img, int groups) { return (gn_scratch_bytes(n_img, groups) + 255) & ~size_t(255); }
-
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
 
 int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_img, int P, int groups, float eps,
                      const float* gamma, const float* beta, int do_silu, void* scratch, int scratch_is_zero,
