@@ -22,6 +22,9 @@ const char* lr_last_error(void);
 /* number of CUDA kernels launched by this library since the last reset (bench.py's gpu_launches) */
 long long lr_launch_count(void);
 void lr_launch_count_reset(void);
+/* Kernels replayed through a captured CUDA graph are launched by the driver, not by this library: the host side adds
+ * the number of kernel nodes of every replay here so that lr_launch_count() keeps counting executed kernels. */
+void lr_launch_count_add(long long n);
 /* Bring-up aid (no reference counterpart): when LR_GEMM_TRACE / LR_ATTN_TRACE is set in the environment before the first
  * op, CTA 0 of the GEMM / attention kernels records clock64() samples per warp role and phase; this copies them to HOST
  * memory `dst` (synchronises the device) and optionally clears the buffer. Fails when tracing is not enabled. */

@@ -40,6 +40,7 @@ SIGNATURES = {
     "lr_last_error": (c_char_p, []),
     "lr_launch_count": (c_longlong, []),
     "lr_launch_count_reset": (None, []),
+    "lr_launch_count_add": (None, [c_longlong]),
     "lr_debug_read_trace": (c_int, [c_void_p, c_longlong, c_int]),
     "lr_unet_create": (c_int, [POINTER(UNetCfg), POINTER(c_void_p)]),
     "lr_unet_destroy": (None, [c_void_p]),

@@ -59,10 +59,25 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// Measured dead ends (B200, round 1, 8x5 heads x 8192^2): ex2.approx.f16x2 is split by ptxas into two MUFU ops + PRMT;
-// moving 25 % of the exponentials to an FMA-pipe degree-3 polynomial made the kernel 8 % SLOWER (the softmax warps are
-// bound by issue/latency with 2 warps per scheduler, not by MUFU throughput alone); a ones-column in V to get the row
-// sum from the MMA was correct but not faster either.
+// exp2 on the FMA pipe (Cody-Waite range reduction + degree-3 minimax polynomial, max relative error 7.6e-5, i.e. below
+// half an fp16 ulp of the P value it feeds). -DLR_ATTN_POLY_GROUPS=G computes one exponential in every G groups of four
+// here instead of on the MUFU unit (16 ex2/clk/SM, 77 % busy in ncu, FMA pipe 22 %). Measured on B200 with the softmax
+// ping-pong in place (round 1, r1l, 8x5 heads x 8192^2): 875 us all-MUFU, 907 us with 25 %, 981 us with 12.5 % on the
+// polynomial - the softmax warps are bound by issue slots and latency as much as by MUFU throughput, so the default is 0.
+// Other measured dead ends: ex2.approx.f16x2 is split by ptxas into two MUFU ops + PRMT; a ones-column in V to get the
+// row sum from the MMA was correct but not faster.
+#ifndef LR_ATTN_POLY_GROUPS
+#define LR_ATTN_POLY_GROUPS 0
+#endif
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.0f);
+  const float xr = x + 12582912.0f;        // 1.5 * 2^23: the nearest integer to x lands in the low mantissa bits
+  const float f = x - (xr - 12582912.0f);  // [-0.5, 0.5]
+  float p = fmaf(0.05517028f, f, 0.2426077f);
+  p = fmaf(p, f, 0.6932609f);
+  p = fmaf(p, f, 0.9999283f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));  // p * 2^round(x)
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -297,7 +312,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         const float e0 = fast_exp2(fmaf(__uint_as_float(s[2 * i]), p.scale_log2, -moff));
         const float e1 = fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), p.scale_log2, -moff));
         const float e2 = fast_exp2(fmaf(__uint_as_float(s[2 * i + 2]), p.scale_log2, -moff));
-        const float e3 = fast_exp2(fmaf(__uint_as_float(s[2 * i + 3]), p.scale_log2, -moff));
+        const float x3 = fmaf(__uint_as_float(s[2 * i + 3]), p.scale_log2, -moff);
+        const float e3 = (LR_ATTN_POLY_GROUPS > 0 && ((i >> 1) % (LR_ATTN_POLY_GROUPS > 0 ? LR_ATTN_POLY_GROUPS : 1)) == 0)
+                             ? poly_exp2(x3) : fast_exp2(x3);
         l0 += e0;
         l1 += e1;
         l2 += e2;

@@ -955,6 +955,7 @@ int lr_abi_version(void) { return LR_B200_ABI_VERSION; }
 const char* lr_last_error(void) { return lr::last_error(); }
 long long lr_launch_count(void) { return lr::launches_since_reset(); }
 void lr_launch_count_reset(void) { lr::reset_launch_counter(); }
+void lr_launch_count_add(long long n) { lr::add_launches(n); }
 int lr_debug_read_trace(void* dst, long long bytes, int clear) {
   LR_CHECK(dst != nullptr && bytes > 0, "lr_debug_read_trace: bad argument");
   return lr::debug_read_trace(dst, static_cast<size_t>(bytes), clear);

@@ -19,6 +19,7 @@ const char* last_error() { return g_err.c_str(); }
 static std::atomic<long long> g_launches{0};
 long long launches_since_reset() { return g_launches.load(); }
 void reset_launch_counter() { g_launches.store(0); }
+void add_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 #define LR_LAUNCHED()                                        \
   do {                                                       \
     g_launches.fetch_add(1, std::memory_order_relaxed);      \

@@ -117,5 +117,6 @@ int debug_read_trace(void* dst, size_t bytes, int clear);
 
 long long launches_since_reset();
 void reset_launch_counter();
+void add_launches(long long n);
 
 }  // namespace lr

@@ -81,9 +81,17 @@ class _StepGraph:
         torch.cuda.synchronize(device)
         self.generation = N.lib().lr_unet_plan_generation(unet.engine())
         graph = torch.cuda.CUDAGraph()
+        before = N.lib().lr_launch_count()
         with torch.cuda.graph(graph):
             self._body()
+        self.kernels = N.lib().lr_launch_count() - before  # native kernel nodes of one replay
+        N.lib().lr_launch_count_add(-self.kernels)          # the capture itself executed nothing
         self.graph = graph
+
+    def replay(self):
+        from . import _native as N
+        self.graph.replay()
+        N.lib().lr_launch_count_add(self.kernels)
 
     def _body(self):
         cx = self.x.shape[1]
@@ -318,7 +326,7 @@ class DDIMSampler(object):
                 sg.noise.copy_(self.noise_source(sg.x.shape, device, i))
             else:
                 sg.noise.normal_()
-            sg.graph.replay()
+            sg.replay()
             if callback:
                 callback(i)
             if img_callback:
