@@ -269,6 +269,7 @@ def run_native(args):
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return
     sustained, burst, hbm, peak_src = _peaks()
     names = ["gemm_conv_kernel", "attention_kernel", "groupnorm", "layernorm", "other"]
@@ -315,6 +316,7 @@ def run_native(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

@@ -1,7 +1,7 @@
 """leftrefill_b200 — B200-native (sm_100a) implementation of LeftRefill's DDIM/UNet hot path.
 
 Public surface (mirrors the reference class surface):
-    UNetModel, MultiViewUnetModel, ResBlock, Upsample, Downsample, TimestepEmbedSequential   (openaimodel.py)
+    UNetModel, MultiViewUnetModel, NVSUnetModel, ResBlock, Upsample, Downsample, TimestepEmbedSequential   (openaimodel.py)
     CrossAttention, BasicTransformerBlock, SpatialTransformer, FeedForward, GEGLU            (attention.py)
     DDIMSampler                                                                              (ddim.py)
     install()  -> makes `ldm.modules.diffusionmodules.openaimodel.UNetModel`, `ldm.modules.attention.CrossAttention`
@@ -15,7 +15,7 @@ import types
 __version__ = "0.1.0"
 
 _LAZY = {
-    "UNetModel": "unet", "MultiViewUnetModel": "unet", "ResBlock": "unet", "Upsample": "unet", "Downsample": "unet",
+    "UNetModel": "unet", "MultiViewUnetModel": "unet", "NVSUnetModel": "unet", "ResBlock": "unet", "Upsample": "unet", "Downsample": "unet",
     "TimestepEmbedSequential": "unet", "TimestepBlock": "unet", "GroupNorm32": "unet",
     "CrossAttention": "attention", "MemoryEfficientCrossAttention": "attention", "BasicTransformerBlock": "attention",
     "SpatialTransformer": "attention", "FeedForward": "attention", "GEGLU": "attention",

@@ -406,10 +406,13 @@ int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_i
   LR_CHECK(x1 != nullptr || c1 == 0, "groupnorm: c1 without x1");
   const int rpi = kNormThreads / (C / 8);
   const size_t smem = static_cast<size_t>(rpi) * 2 * C * sizeof(float);
-  // Images of up to kGnFusedKB KB per CTA of an 8-CTA cluster take the single-launch fused kernel (second pass hits
-  // L2); larger ones the two-pass scheme. Neither choice depends on the batch size (bit-exact batch invariance).
-  static const int fused_kb = env_int("LR_GN_FUSED_KB", 448);
-  static const int chunk_div = env_int("LR_GN_CHUNK_DIV", 64);
+  // Images of up to 8 x LR_GN_FUSED_KB KB take the single-launch fused kernel (one 8-CTA cluster per image, second pass
+  // hits L2), larger ones the two-pass scheme. Measured on B200 at N = 8 (round 1, r1m): fused wins up to 1.3 MB per
+  // image (16x32x1280: 17.7 vs 18.8 us; 8x16x1280: 9.6 vs 12.6 us), two-pass from 2.6 MB (32x64x640: 24.5 vs 28.1 us);
+  // 16-CTA (non-portable) clusters were slower than both everywhere. No choice depends on the batch size (bit-exact
+  // batch invariance).
+  static const int fused_kb = env_int("LR_GN_FUSED_KB", 160);
+  static const int chunk_div = env_int("LR_GN_CHUNK_DIV", 32);
   constexpr int kCS = 8;
   const size_t img_bytes = static_cast<size_t>(P) * C * sizeof(__half);
   if (fused_kb > 0 && groups <= 64 && img_bytes <= static_cast<size_t>(kCS) * fused_kb * 1024) {

@@ -161,12 +161,19 @@ class DDIMSampler(object):
                 ctmp = ctmp[0]
             if ctmp.shape[0] != batch_size:
                 print(f"Warning: Got {ctmp.shape[0]} conditionings but batch-size is {batch_size}")
-        if isinstance(conditioning, list):
-            raise NotImplementedError("ddim_multi_sampling (list conditioning) is outside the accelerated path")
         if kwargs.get("return_attn", False):
             raise NotImplementedError("return_attn is a debugging feature of the reference and is not supported")
         self.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=verbose)
         C, H, W = shape
+        if type(conditioning) == list:  # noqa: E721 - same dispatch as the reference (ddim.py:104)
+            return self.ddim_multi_sampling(conditioning, (batch_size, C, H, W), callback=callback,
+                                            img_callback=img_callback, quantize_denoised=quantize_x0, mask=mask, x0=x0,
+                                            ddim_use_original_steps=False, noise_dropout=noise_dropout,
+                                            temperature=temperature, score_corrector=score_corrector,
+                                            corrector_kwargs=corrector_kwargs, x_T=x_T, log_every_t=log_every_t,
+                                            unconditional_guidance_scale=unconditional_guidance_scale,
+                                            unconditional_conditioning=unconditional_conditioning,
+                                            dynamic_threshold=dynamic_threshold, ucg_schedule=ucg_schedule)
         return self.ddim_sampling(conditioning, (batch_size, C, H, W), callback=callback, img_callback=img_callback,
                                   quantize_denoised=quantize_x0, mask=mask, x0=x0, ddim_use_original_steps=False,
                                   noise_dropout=noise_dropout, temperature=temperature,
@@ -194,6 +201,57 @@ class DDIMSampler(object):
         if ucond is not None and cfg_scale != 1. and not ok(ucond):
             return None
         return unet
+
+    @torch.no_grad()
+    def ddim_multi_sampling(self, cond, shape, x_T=None, ddim_use_original_steps=False, callback=None, timesteps=None,
+                            quantize_denoised=False, mask=None, x0=None, img_callback=None, log_every_t=100,
+                            temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
+                            unconditional_guidance_scale=1., unconditional_conditioning=None, dynamic_threshold=None,
+                            ucg_schedule=None, **kwargs):
+        """Conditionally-consistent multi-reference sampling (reference ddim.py:146-222): `cond` /
+        `unconditional_conditioning` / `x_T` are lists with one entry per reference view; every step denoises each
+        stitched [reference | target] canvas on its own, then ONE of the predicted right (target) halves - chosen with
+        `random.shuffle`, exactly like the reference - is written into all canvases. Returns (first canvas, {}).
+        Each per-view step is `p_sample_ddim`: the native UNet through `model.apply_model` + the fused update kernel."""
+        import random
+        if ddim_use_original_steps:
+            raise NotImplementedError("ddim_use_original_steps is never used by the LeftRefill drivers")
+        device = self._device()
+        b = shape[0]
+        img = [torch.randn(shape, device=device)] * len(cond) if x_T is None else list(x_T)
+        if unconditional_conditioning is None:
+            unconditional_conditioning = [None] * len(cond)
+        if timesteps is None:
+            timesteps = self.ddim_timesteps
+        else:
+            subset_end = int(min(timesteps / self.ddim_timesteps.shape[0], 1) * self.ddim_timesteps.shape[0]) - 1
+            timesteps = self.ddim_timesteps[:subset_end]
+        intermediates = {}
+        time_range = np.flip(timesteps)
+        total_steps = timesteps.shape[0]
+        for i, step in enumerate(time_range):
+            index = total_steps - i - 1
+            ts = torch.full((b,), int(step), device=device, dtype=torch.long)
+            if ucg_schedule is not None:
+                assert len(ucg_schedule) == len(time_range)
+                unconditional_guidance_scale = ucg_schedule[i]
+            pred_img_right, new_img = [], []
+            for img_, cond_, uc_ in zip(img, cond, unconditional_conditioning):
+                img_, _ = self.p_sample_ddim(img_, cond_, ts, index=index, quantize_denoised=quantize_denoised,
+                                             temperature=temperature, noise_dropout=noise_dropout,
+                                             score_corrector=score_corrector, corrector_kwargs=corrector_kwargs,
+                                             unconditional_guidance_scale=unconditional_guidance_scale,
+                                             unconditional_conditioning=uc_, dynamic_threshold=dynamic_threshold)
+                pred_img_right.append(img_[:, :, :, img_.shape[-1] // 2:])
+                new_img.append(img_)
+            random.shuffle(pred_img_right)  # the reference picks a random view's target half (ddim.py:205-207)
+            random_right = pred_img_right[0].clone()
+            for j in range(len(new_img)):
+                new_img[j][:, :, :, random_right.shape[-1]:] = random_right
+            img = new_img
+            if callback:
+                callback(i)
+        return img[0], intermediates
 
     @torch.no_grad()
     def ddim_sampling(self, cond, shape, x_T=None, ddim_use_original_steps=False, callback=None, timesteps=None,

@@ -145,6 +145,9 @@ class UNetModel(nn.Module):
                  disable_self_attentions=None, num_attention_blocks=None, disable_middle_self_attn=False,
                  use_linear_in_transformer=False, view_num=1, concat_target=False, **unused):
         super().__init__()
+        if unused.get("use_sep"):
+            raise NotImplementedError("NVSUnetModel(use_sep=True) (separator columns, inpainting_ldm/NVS_ldm.py:24-31) is "
+                                      "not implemented; the shipped novel_view_synthesis.yaml sets use_sep: False")
         if not use_spatial_transformer or context_dim is None:
             raise NotImplementedError("only the SpatialTransformer UNet (use_spatial_transformer=True with a "
                                       "context_dim) used by every LeftRefill config is implemented")
@@ -319,6 +322,9 @@ class UNetModel(nn.Module):
 
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         assert y is None, "must specify y if and only if the model is class-conditional"
+        if kwargs.get("c_input") is not None:
+            raise NotImplementedError("c_input (NVS input refinement, inpainting_ldm/NVS_ldm.py:49,64-68) is not "
+                                      "implemented; novel_view_synthesis.yaml sets use_input_refinement: False")
         assert timesteps is not None and context is not None
         if not x.is_cuda:
             raise N.LRError("leftrefill_b200.UNetModel runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -344,6 +350,11 @@ class MultiViewUnetModel(UNetModel):
 
     def __init__(self, *args, view_num=4, concat_target=False, **kwargs):
         super().__init__(*args, view_num=view_num, concat_target=concat_target, **kwargs)
+
+
+class NVSUnetModel(UNetModel):
+    """inpainting_ldm/NVS_ldm.py:22-104 with `use_sep=False` (what configs/novel_view_synthesis.yaml uses, where the
+    plain UNetModel is the target): identical to UNetModel. `use_sep=True` and a non-None `c_input` raise."""
 
 
 class _EngineHandle:

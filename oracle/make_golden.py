@@ -188,6 +188,50 @@ def golden_ddim(cfg, sd, m):
     np.savez_compressed(os.path.join(GOLD, "ddim_small.npz"), **out)
 
 
+def golden_ddim_multi(cfg, sd, m):
+    """DDIMSampler.sample with LIST conditioning -> ddim_multi_sampling (ddim.py:104,146-222): two stitched reference
+    views, 3 steps, eta 1, cfg 2.5; the per-step noises and Python's `random` state are pinned."""
+    import random
+    import ldm.models.diffusion.ddim as ddim_mod
+    from ldm.models.diffusion.ddim import DDIMSampler
+    DDIMSampler.register_buffer = lambda self, name, attr: setattr(self, name, attr)
+    model = _FakeLDM(m)
+    g = torch.Generator(device="cpu").manual_seed(47)
+    B, H, W, V, S = 1, 16, 32, 2, 4
+    x_T = [torch.randn(B, 4, H, W, generator=g) for _ in range(V)]
+    c_concat = [torch.randn(B, 5, H, W, generator=g) for _ in range(V)]
+    for c in c_concat:
+        c[:, 0] = (c[:, 0] > 0).float()
+    ctx = [torch.randn(B, 77, cfg["context_dim"], generator=g) for _ in range(V)]
+    uc = torch.randn(1, 77, cfg["context_dim"], generator=g).repeat(B, 1, 1)
+    noises = []
+    orig = ddim_mod.noise_like
+
+    def recording_noise_like(shape, device, repeat=False):
+        n = orig(shape, device, repeat)
+        noises.append(n.clone())
+        return n
+
+    ddim_mod.noise_like = recording_noise_like
+    torch.manual_seed(4321)
+    random.seed(7)
+    sampler = DDIMSampler(model)
+    cond = [{"c_concat": [c_concat[v]], "c_crossattn": [ctx[v]]} for v in range(V)]
+    ucond = [{"c_concat": [c_concat[v]], "c_crossattn": [uc]} for v in range(V)]
+    samples, inter = sampler.sample(S, B, (4, H, W), cond, eta=1.0, x_T=[t.clone() for t in x_T], verbose=False,
+                                    unconditional_guidance_scale=2.5, unconditional_conditioning=ucond)
+    ddim_mod.noise_like = orig
+    assert inter == {} and len(noises) == S * V
+    print(f"DDIMSampler.sample (list conditioning -> ddim_multi_sampling) V={V} S={S}: samples {tuple(samples.shape)}")
+    out = {"samples": samples.numpy(), "noises": torch.stack(noises).numpy(), "uc_context": uc.numpy(), "S": S, "V": V,
+           "random_seed": 7}
+    for v in range(V):
+        out[f"x_T{v}"] = x_T[v].numpy()
+        out[f"c_concat{v}"] = c_concat[v].numpy()
+        out[f"context{v}"] = ctx[v].numpy()
+    np.savez_compressed(os.path.join(GOLD, "ddim_multi_small.npz"), **out)
+
+
 def validate_full():
     cfg = O.DEFAULT_CFG
     t0 = time.time()
@@ -207,13 +251,20 @@ def validate_full():
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--only-multi", action="store_true", help="regenerate only tests/golden/ddim_multi_small.npz")
     args = ap.parse_args()
     assert os.path.isdir(REF), "the reference tree is only available in the build container"
     os.makedirs(GOLD, exist_ok=True)
     torch.set_grad_enabled(False)
+    if args.only_multi:
+        cfg = O.SMALL_CFG
+        sd = O.make_state_dict(cfg, seed=0)
+        golden_ddim_multi(cfg, sd, ref_unet(cfg, sd))
+        sys.exit(0)
     cfg, sd, m = golden_unet()
     golden_multiview()
     golden_ddim(cfg, sd, m)
+    golden_ddim_multi(cfg, sd, m)
     if args.full:
         validate_full()
     print("golden fixtures written to", GOLD)

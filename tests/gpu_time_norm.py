@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 
 GN_SHAPES = [(8, 64, 128, 320, 0), (8, 64, 128, 640, 320), (8, 32, 64, 640, 0), (8, 32, 64, 1280, 640),
              (8, 16, 32, 1280, 0), (8, 16, 32, 1280, 1280), (8, 8, 16, 1280, 0), (8, 8, 16, 1280, 1280)]
-LN_SHAPES = [(65536, 320), (16384, 640), (4096, 1280), (1024, 1280)]
+LN_SHAPES = [(65536, 320), (16384, 640), (4096, 1280), (1024, 1280)] if os.environ.get("LR_TAG", "default") == "default" else []
 
 
 def timeit(fns, iters=20):
@@ -83,10 +83,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         run()
     else:
-        schemes = [("default", {}), ("twopass/64", {"LR_GN_FUSED_KB": "0"}),
-                   ("twopass/32", {"LR_GN_FUSED_KB": "0", "LR_GN_CHUNK_DIV": "32"}),
-                   ("twopass/128", {"LR_GN_FUSED_KB": "0", "LR_GN_CHUNK_DIV": "128"}),
-                   ("fused<=1MB", {"LR_GN_FUSED_KB": "128"})]
+        schemes = [("default", {}), ("fused<=3.5MB", {"LR_GN_FUSED_KB": "448"}), ("twopass/32", {"LR_GN_FUSED_KB": "0"}),
+                   ("twopass/64", {"LR_GN_FUSED_KB": "0", "LR_GN_CHUNK_DIV": "64"})]
         for tag, env in schemes:
             e = dict(os.environ, LR_TAG=tag, **env)
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "run"], env=e, capture_output=True,

@@ -140,6 +140,38 @@ def test_ddim_sampler_vs_reference_golden(small, tag, eta):
     _assert_parity(inter["pred_x0"][-1], g[f"{tag}.pred_x0_last"])
 
 
+def test_ddim_multi_sampling_vs_reference_golden(small):
+    """DDIMSampler.sample with LIST conditioning (reference ddim.py:104 -> ddim_multi_sampling :146-222): two stitched
+    views denoised separately, one randomly chosen target half copied into both after every step. Golden from the
+    unmodified reference sampler (oracle/make_golden.py --only-multi), same noises, same `random` seed."""
+    import random
+    import leftrefill_b200 as lr
+    m, _ = small
+    g = load_golden("ddim_multi_small.npz")
+    dev = torch.device("cuda")
+    V, S = int(g["V"]), int(g["S"])
+    noises = torch.tensor(g["noises"]).to(dev)
+    s = lr.DDIMSampler(FakeLDM(m, dev))
+    calls = {"n": 0}
+
+    def noise_source(shape, device, i):
+        n = noises[calls["n"]]
+        calls["n"] += 1
+        return n
+
+    s.noise_source = noise_source
+    uc = torch.tensor(g["uc_context"]).to(dev)
+    cond = [{"c_concat": [torch.tensor(g[f"c_concat{v}"]).to(dev)], "c_crossattn": [torch.tensor(g[f"context{v}"]).to(dev)]}
+            for v in range(V)]
+    ucond = [{"c_concat": [torch.tensor(g[f"c_concat{v}"]).to(dev)], "c_crossattn": [uc]} for v in range(V)]
+    x_T = [torch.tensor(g[f"x_T{v}"]).to(dev) for v in range(V)]
+    random.seed(int(g["random_seed"]))
+    samples, inter = s.sample(S, 1, (4, 16, 32), cond, eta=1.0, x_T=x_T, verbose=False,
+                              unconditional_guidance_scale=2.5, unconditional_conditioning=ucond)
+    assert inter == {} and calls["n"] == S * V
+    _assert_parity(samples, g["samples"])
+
+
 def test_sampler_generic_path_equals_fast_path(small):
     """apply_model route (any model) and the hoisted native route must agree; RNG consumption must be identical."""
     import leftrefill_b200 as lr
