@@ -10,6 +10,13 @@
 //     conv padding, and the tensor map's element strides implement stride 2.
 //   * the skip concat `th.cat([h, hs.pop()], 1)` (openaimodel.py:781) is never materialised: the K loop walks two
 //     tensor maps (source 0 = h, source 1 = skip) back to back.
+//   * HALO mode (stride-1 3x3 convs on images at least 16 rows high): the output tile is 8 pixels wide x 16 rows, and
+//     for every 64-channel chunk ONE TMA box of (8+2) x (16+2) input pixels is loaded and re-used by all nine taps: the
+//     A descriptor of tap (dy, dx) simply starts ((dy+1)*10 + (dx+1)) rows further into that box, with a stride of
+//     10 rows between its 8-row groups (the 128B swizzle is a function of the shared-memory address bits, so a
+//     row-shifted, row-padded operand reads correctly with base_offset 0 - tests/umma_halo_probe.cu). Activation
+//     traffic from L2 drops 6.25x (23 KB instead of 9 x 16 KB per chunk); weights stream through their own ring, one
+//     tile per (chunk, tap). The main loop of the non-halo path is bound by L2->SM bytes.
 //
 // Structure (one CTA per SM, persistent over output tiles of 128 x block_n):
 //   warp 0 (1 lane)  TMA producer      -> smem ring of {A 128x64, B block_n x 64} fp16 stages, 128B swizzle
@@ -38,6 +45,10 @@ struct GemmParams {
   int cstage_bufs;   // 1 or 2 staging buffers (2: short main loops, where the epilogue sets the tile period: it then never
                      // waits for a TMA store to drain its buffer)
   int cstage_bytes;  // bytes of one staging buffer (multiple of 1024)
+  int halo;          // 1: halo mode (see the header comment); tile box is bw = 8, bh = 16, bn = 1
+  int a_stages;      // halo: depth of the activation (halo tile) ring; `stages` is then the depth of the weight ring
+  int a_slot_bytes;  // halo: bytes of one activation slot (multiple of 1024)
+  int ring_bytes;    // bytes of all pipeline rings = offset of the barrier block inside dynamic smem
   int n_img, H, W;   // OUTPUT pixel grid
   int bw, bh, bn;    // tile box: bw*bh*bn == 128 output pixels
   int tiles_x, tiles_y, tiles_b, tiles_n;
@@ -82,7 +93,10 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kMaxStages = 8;
+constexpr int kMaxAStages = 4;
+constexpr int kHaloBW = 8, kHaloBH = 16;  // halo-mode output tile: 8 pixels wide x 16 rows
 constexpr int kGemmAuxBytes = 256 /*barriers*/ + 2 * 256 * 4 /*bias staging, double buffered*/;
+static_assert((2 * kMaxStages + 4 + 2 * kMaxAStages) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
 
 // bytes of one pipeline stage in ONE CTA (cg = CTAs cooperating on a tile: each holds block_n / cg weight rows)
 __host__ __device__ inline int gemm_stage_bytes(int block_n, int cg = 1) {
@@ -117,12 +131,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   const int stage_bytes = gemm_stage_bytes(p.block_n, CG);
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.ring_bytes);
   uint64_t* full = bars;                   // [kMaxStages]
   uint64_t* empty = bars + kMaxStages;     // [kMaxStages]
   uint64_t* tfull = bars + 2 * kMaxStages; // [2]
   uint64_t* tempty = tfull + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* a_full = tempty + 2;           // [kMaxAStages]  (halo mode)
+  uint64_t* a_empty = a_full + kMaxAStages;  // [kMaxAStages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + kMaxAStages);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][256]
 
   const int hw_warp = threadIdx.x >> 5;
@@ -150,6 +166,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kEpiWarps * CG);  // the leader's MMA thread waits for the epilogues of BOTH CTAs
     }
+    for (int i = 0; i < kMaxAStages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -176,7 +196,61 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   const int unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
   const int b_rows = p.block_n / CG;
 
-  if (warp == 0) {
+  if (warp == 0 && p.halo) {
+    // ------------------------------- TMA producer, halo mode ------------------------------------------------
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    uint8_t* b_ring = smem + p.a_stages * p.a_slot_bytes;
+    const int b_bytes = b_rows * kBlockK * 2;
+    const int a_tx = (kHaloBW + 2) * (kHaloBH + 2) * kBlockK * 2;  // TMA credits the full box, zero-filled parts included
+    int tcount = 0;
+    for (int tile = unit0; tile < num_tiles; tile += unit_step, ++tcount) {
+      LR_GEMM_TR(0, tcount, 0);
+      const int tn = tile % p.tiles_n;
+      int tm = min((tile / p.tiles_n) * CG + static_cast<int>(rank), tiles_m - 1);
+      const int tx = tm % p.tiles_x;
+      tm /= p.tiles_x;
+      const int ty = tm % p.tiles_y;
+      const int tb = tm / p.tiles_y;
+      const int x0 = tx * kHaloBW, y0 = ty * kHaloBH, n0 = tb;
+      const int ncol0 = tn * p.block_n + static_cast<int>(rank) * b_rows;  // this CTA's share of the weight rows
+      for (int kc = 0; kc < p.kc0 + p.kc1; ++kc) {
+        const bool src0 = kc < p.kc0;
+        const int kch = (src0 ? kc : kc - p.kc0) * kBlockK;
+        const CUtensorMap* ta = src0 ? &p.tmA0 : &p.tmA1;
+        mbar_wait(&a_empty[sa], pha ^ 1);
+        if (elect_one()) {
+          uint8_t* a_s = smem + sa * p.a_slot_bytes;
+          if (CG == 2) {
+            if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * a_tx);
+            tma_load_4d_2sm(a_s, ta, &a_full[sa], kch, x0 - 1, y0 - 1, n0);
+          } else {
+            mbar_arrive_expect_tx(&a_full[sa], a_tx);
+            tma_load_4d(a_s, ta, &a_full[sa], kch, x0 - 1, y0 - 1, n0);
+          }
+        }
+        __syncwarp();
+        if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&empty[sb], phb ^ 1);
+          if (elect_one()) {
+            const int kb = tap * p.ctot + (src0 ? 0 : p.c0) + kch;
+            uint8_t* b_s = b_ring + sb * b_bytes;
+            if (CG == 2) {
+              if (leader) mbar_arrive_expect_tx(&full[sb], 2 * b_bytes);
+              tma_load_2d_2sm(b_s, &p.tmB, &full[sb], kb, ncol0);
+            } else {
+              mbar_arrive_expect_tx(&full[sb], b_bytes);
+              tma_load_2d(b_s, &p.tmB, &full[sb], kb, ncol0);
+            }
+          }
+          __syncwarp();
+          if (++sb == p.stages) { sb = 0; phb ^= 1; }
+        }
+      }
+      LR_GEMM_TR(0, tcount, 1);
+    }
+  } else if (warp == 0) {
     // ------------------------------- TMA producer (whole warp loops, one elected lane issues) ---------------
     int s = 0;
     uint32_t ph = 0;
@@ -220,6 +294,66 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         }
       }
       LR_GEMM_TR(0, tcount, 1);
+    }
+  } else if (warp == 1 && p.halo) {
+    // ------------------------------- MMA issuer, halo mode -------------------------------------------------
+    if (leader) {
+      const uint32_t idesc = umma_idesc_f16(kBlockM * CG, p.block_n, 0);
+      const uint32_t desc_hi_a = umma_desc_hi_sw128((kHaloBW + 2) * 128);  // 8-row groups = image rows, 10 pixels apart
+      const uint32_t desc_hi_b = umma_desc_hi_sw128(1024);
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem), 16);
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(smem) + p.a_stages * p.a_slot_bytes, 16);
+      const uint32_t a_units = static_cast<uint32_t>(p.a_slot_bytes) >> 4;
+      const uint32_t b_units = static_cast<uint32_t>(b_rows * kBlockK * 2) >> 4;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      int tcount = 0;
+      for (int tile = unit0; tile < num_tiles; tile += unit_step, ++tcount) {
+        LR_GEMM_TR(1, tcount, 0);
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        LR_GEMM_TR(1, tcount, 1);
+        const uint32_t d_tmem = tmem_base + as * 256;
+        uint32_t started = 0;
+        for (int kc = 0; kc < p.kc0 + p.kc1; ++kc) {
+          mbar_wait(&a_full[sa], pha);
+          tc_fence_after();
+          if (kc == 0) LR_GEMM_TR(1, tcount, 2);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&full[sb], phb);
+            tc_fence_after();
+            if (elect_one()) {
+              // tap (dy, dx) = (tap / 3 - 1, tap % 3 - 1): start (dy + 1) * 10 + (dx + 1) rows (128 B = 8 units) into the box
+              const uint32_t a_lo = a_lo0 + sa * a_units + static_cast<uint32_t>((tap / 3) * (kHaloBW + 2) + tap % 3) * 8u;
+              const uint32_t b_lo = b_lo0 + sb * b_units;
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                const uint64_t ad = umma_desc_make(desc_hi_a, a_lo + 2 * k);
+                const uint64_t bd = umma_desc_make(desc_hi_b, b_lo + 2 * k);
+                if (CG == 2) umma_f16_2sm(d_tmem, ad, bd, idesc, (started | k) != 0 ? 1u : 0u);
+                else umma_f16(d_tmem, ad, bd, idesc, (started | k) != 0 ? 1u : 0u);
+              }
+              if (CG == 2) umma_commit_2sm(&empty[sb]); else umma_commit(&empty[sb]);
+            }
+            started = 1;
+            __syncwarp();
+            if (++sb == p.stages) { sb = 0; phb ^= 1; }
+          }
+          if (elect_one()) {
+            if (CG == 2) umma_commit_2sm(&a_empty[sa]); else umma_commit(&a_empty[sa]);
+          }
+          __syncwarp();
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+        }
+        if (elect_one()) {
+          if (CG == 2) umma_commit_2sm(&tfull[as]); else umma_commit(&tfull[as]);
+        }
+        __syncwarp();
+        LR_GEMM_TR(1, tcount, 3);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer (whole warp loops, one elected lane issues) ----------------

@@ -158,9 +158,17 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   const int Wo = (s.stride == 1) ? s.in_w : (s.in_w - 1) / 2 + 1;
   op->out_h = Ho;
   op->out_w = Wo;
+  // halo mode (gemm_tc.cuh): stride-1 3x3 convs on images at least one halo tile high
+  static const bool halo_enabled = getenv("LR_NO_HALO") == nullptr;
+  const bool halo = halo_enabled && s.taps == 9 && s.stride == 1 && s.in_h >= kHaloBH && s.in_w >= kHaloBW;
   // tile box: power-of-two (bw, bh, bn) with product 128 minimising the number of (partially empty) tiles
   int best_tiles = INT32_MAX, bw = 128, bh = 1, bn = 1;
-  for (int w = 128; w >= 1; w >>= 1) {
+  if (halo) {
+    bw = kHaloBW;
+    bh = kHaloBH;
+    bn = 1;
+  }
+  for (int w = 128; w >= 1 && !halo; w >>= 1) {
     for (int h = 128 / w; h >= 1; h >>= 1) {
       const int n = 128 / (w * h);
       const long long t = 1LL * cdiv(Wo, w) * cdiv(Ho, h) * cdiv(s.n_img, n);
@@ -206,7 +214,9 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
         const long long slots = sm_count() / c;
         const long long waves = (units + slots - 1) / slots;
         const double tensor = bnn;                               // ~ cycles / 0.5 per k16 step
-        const double ingest = 1.0 * (128.0 + bnn / c);           // bytes-bound mainloop (calibrated on B200, ncu r1)
+        // bytes-bound mainloop (calibrated on B200, ncu r1): rows of activations + weights each SM pulls per k-chunk;
+        // in halo mode one 180-row box serves nine chunks
+        const double ingest = (halo ? 20.0 : 128.0) + bnn / c;
         const double per_tile = (tensor > ingest ? tensor : ingest) + 40.0;
         const double cost = waves * per_tile;
         if (cost < best) {
@@ -237,16 +247,38 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   const int kiters = s.taps * (cdiv(s.c0, kBlockK) + cdiv(s.c1, kBlockK));
   static const int two_below = env_int("LR_GEMM_TWO_CSTAGE_KITERS", 24);
   int bufs = (tma_store && kiters <= two_below) ? 2 : 1;
-  int stages = (232448 - 2048 - kGemmAuxBytes - bufs * cstage_bytes) / gemm_stage_bytes(block_n, cg);
-  if (bufs == 2 && stages < 3) {
-    bufs = 1;
-    stages = (232448 - 2048 - kGemmAuxBytes - cstage_bytes) / gemm_stage_bytes(block_n, cg);
+  const int budget = 232448 - 2048 - kGemmAuxBytes;
+  int stages, a_stages = 0, ring_bytes;
+  const int a_slot = ((kHaloBW + 2) * (kHaloBH + 2) * kBlockK * 2 + 1023) & ~1023;
+  if (halo) {
+    // two rings: activation halo tiles (one per 64-channel chunk) and weight tiles (one per chunk and tap)
+    const int b_bytes = (block_n / cg) * kBlockK * 2;
+    a_stages = 3;
+    stages = (budget - a_stages * a_slot - bufs * cstage_bytes) / b_bytes;
+    if (stages < 4) {
+      a_stages = 2;
+      stages = (budget - a_stages * a_slot - bufs * cstage_bytes) / b_bytes;
+    }
+    if (stages > kMaxStages) stages = kMaxStages;
+    LR_CHECK(stages >= 2, "conv (halo): not enough shared memory for 2 weight stages");
+    ring_bytes = a_stages * a_slot + stages * b_bytes;
+  } else {
+    stages = (budget - bufs * cstage_bytes) / gemm_stage_bytes(block_n, cg);
+    if (bufs == 2 && stages < 3) {
+      bufs = 1;
+      stages = (budget - cstage_bytes) / gemm_stage_bytes(block_n, cg);
+    }
+    if (stages > kMaxStages) stages = kMaxStages;
+    LR_CHECK(stages >= 2, "conv: not enough shared memory for 2 stages");
+    ring_bytes = stages * gemm_stage_bytes(block_n, cg);
   }
-  if (stages > kMaxStages) stages = kMaxStages;
-  LR_CHECK(stages >= 2, "conv: not enough shared memory for 2 stages");
   p.stages = stages;
+  p.halo = halo ? 1 : 0;
+  p.a_stages = a_stages;
+  p.a_slot_bytes = a_slot;
+  p.ring_bytes = ring_bytes;
   p.tma_store = tma_store ? 1 : 0;
-  p.cstage_off = (stages * gemm_stage_bytes(block_n, cg) + kGemmAuxBytes + 1023) & ~1023;  // swizzle needs 1024 B
+  p.cstage_off = (ring_bytes + kGemmAuxBytes + 1023) & ~1023;  // swizzle needs 1024 B
   p.cstage_bufs = bufs;
   p.cstage_bytes = cstage_bytes;
   p.bias = s.bias;
@@ -272,8 +304,8 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
                         static_cast<uint64_t>(s.n_img)};
     uint64_t str[3] = {static_cast<uint64_t>(s.lda0) * 2, static_cast<uint64_t>(s.lda0) * 2 * s.in_w,
                        static_cast<uint64_t>(s.lda0) * 2 * s.in_w * s.in_h};
-    uint32_t box[4] = {kBlockK, static_cast<uint32_t>(bw * s.stride), static_cast<uint32_t>(bh * s.stride),
-                       static_cast<uint32_t>(bn)};
+    uint32_t box[4] = {kBlockK, static_cast<uint32_t>(halo ? bw + 2 : bw * s.stride),
+                       static_cast<uint32_t>(halo ? bh + 2 : bh * s.stride), static_cast<uint32_t>(bn)};
     uint32_t es[4] = {1, static_cast<uint32_t>(s.stride), static_cast<uint32_t>(s.stride), 1};
     LR_TRY(make_tmap(&p.tmA0, s.a0, 4, dims, str, box, es));
     if (s.a1 != nullptr) {
@@ -309,7 +341,7 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   const int num_units = cdiv(tiles_m, cg) * p.tiles_n;
   const int slots = sm_count() / cg;
   op->grid = (num_units < slots ? num_units : slots) * cg;
-  op->smem = tma_store ? p.cstage_off + bufs * cstage_bytes : gemm_smem_bytes(block_n, stages, cg);
+  op->smem = tma_store ? p.cstage_off + bufs * cstage_bytes : 1024 + ring_bytes + kGemmAuxBytes;
   op->block_n = block_n;
   op->stages = stages;
   op->tiles = num_units;

@@ -225,6 +225,10 @@ CASES = {
     "conv_2sm_concat": lambda: case_conv(2, 16, 32, 128, 128, c1=64, force=2128),
     "conv_2sm_odd": lambda: case_conv(3, 24, 40, 64, 96, force=2096),
     "conv_2sm_s2": lambda: case_conv(2, 64, 128, 64, 64, stride=2, force=2064),
+    "conv_halo_ragged": lambda: case_conv(2, 17, 9, 64, 96),
+    "conv_halo_big": lambda: case_conv(2, 64, 128, 320, 320, bias_img=True, residual=True),
+    "conv_halo_concat": lambda: case_conv(1, 32, 64, 128, 160, c1=192, force=2160),
+    "conv_halo_1cta": lambda: case_conv(3, 40, 24, 64, 64, residual=True, force=1064),
     "conv_s2": lambda: case_conv(2, 16, 32, 64, 64, stride=2),
     "conv_s2_big": lambda: case_conv(2, 64, 128, 64, 64, stride=2),
     "conv_cout4": lambda: case_conv(2, 16, 32, 64, 4),
