@@ -51,7 +51,7 @@ def show_gemm(name, fn, reps=3):
             row = tr[(r * 16 + t) * 8:(r * 16 + t) * 8 + 8]
             if not any(row):
                 continue
-            print(f"   {roles[r]:9s} tile {t:2d}: " + " ".join(f"{(v - t0) if v else -1:7d}" for v in row[:6]))
+            print(f"   {roles[r]:9s} tile {t:2d}: " + " ".join(f"{(v - t0) if v else -1:7d}" for v in row[:8]))
 
 
 def show_attn(name, fn):
