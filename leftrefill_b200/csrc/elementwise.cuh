@@ -755,6 +755,49 @@ __global__ void ddim_update_dev_kernel(const float* x /* may alias x_prev */, co
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Split-K reduction of gemm_conv_kernel partial tiles: out[m, n] = fp16( sum_s partial[s][m][n] + bias[n]
+// + bias_img[img(m)][n] + residual[m][n] ), 8 columns per thread, fixed summation order s = 0, 1, 2 (bit-reproducible).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int ksplit, size_t M,
+                                                            int ncols, int rows_per_img, const float* __restrict__ bias,
+                                                            const float* __restrict__ bias_img, int ld_bias_img,
+                                                            const __half* __restrict__ residual, int ld_res,
+                                                            __half* __restrict__ out, int ld_out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int nvec = ncols / 8;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= M * nvec) return;
+  const size_t m = idx / nvec;
+  const int col = static_cast<int>(idx % nvec) * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int s = 0; s < ksplit; ++s) {
+    const float4* pp = reinterpret_cast<const float4*>(partial + (static_cast<size_t>(s) * M + m) * ncols + col);
+    const float4 a = __ldg(pp), b = __ldg(pp + 1);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+  }
+  if (bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __ldg(bias + col + j);
+  }
+  if (bias_img != nullptr) {
+    const float* bi = bias_img + (m / rows_per_img) * ld_bias_img + col;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __ldg(bi + j);
+  }
+  if (residual != nullptr) {
+    float r[8];
+    load8(residual + m * ld_res + col, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += r[j];
+  }
+  store8(out + m * ld_out + col, acc);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Weight repacking (fp32 PyTorch layouts -> fp16 GEMM layouts), run once per weight update.
 // ------------------------------------------------------------------------------------------------------------
 // conv OIHW fp32 -> [O][tap][I] fp16 (tap = ky*3+kx), row stride ldk (>= 9*I, zero padded)

@@ -399,16 +399,31 @@ struct lr_unet {
     *out = static_cast<float*>(p);
     return 0;
   }
-  int add_conv_step(const ConvSpec& s) {
+  int add_conv_step(const ConvSpec& s_in) {
+    ConvSpec s = s_in;
+    void* ws = nullptr;
+    if (s.taps == 9 && s.workspace == nullptr) {
+      // split-K scratch for convs with few output pixels (the 8x16 level): plan-owned, recycled right after this step
+      const int Ho = s.stride == 1 ? s.in_h : (s.in_h - 1) / 2 + 1, Wo = s.stride == 1 ? s.in_w : (s.in_w - 1) / 2 + 1;
+      const size_t m_out = static_cast<size_t>(s.n_img) * Ho * Wo;
+      if (m_out <= 2048) {
+        const size_t bytes = 3 * m_out * s.ncols * sizeof(float);
+        LR_TRY(pool.acquire(bytes, &ws));
+        s.workspace = static_cast<float*>(ws);
+        s.workspace_bytes = bytes;
+      }
+    }
     auto op = std::make_unique<ConvOp>();
     LR_TRY(build_conv_op(op.get(), s));
+    if (ws) pool.release(ws);
     flops += op->flops;
     ConvOp* raw = op.get();
     conv_ops.push_back(std::move(op));
     char d[200];
-    snprintf(d, sizeof(d), "%s n=%d %dx%d s%d c=%d+%d->%d%s bn=%d st=%d tiles=%d",
+    snprintf(d, sizeof(d), "%s n=%d %dx%d s%d c=%d+%d->%d%s bn=%d st=%d tiles=%d%s",
              s.taps == 9 ? "conv3x3" : "linear", s.n_img, s.in_h, s.in_w, s.stride, s.c0, s.c1, s.ncols,
-             s.geglu ? " geglu" : (s.residual ? " +res" : ""), raw->block_n, raw->stages, raw->tiles);
+             s.geglu ? " geglu" : (s.residual ? " +res" : ""), raw->block_n, raw->stages, raw->tiles,
+             raw->ksplit > 1 ? " splitK3" : "");
     push([raw](cudaStream_t st) { return launch_conv_op(*raw, st); }, 0, raw->flops, d);
     return 0;
   }
@@ -1213,6 +1228,15 @@ int lr_conv3x3_f16(const void* x0, int c0, const void* x1, int c1, int n, int h,
   s.ld_out = cout;
   s.force_block_n = force_block_n % 1000;
   s.force_cg = force_block_n / 1000;
+  {
+    const int Ho = stride == 1 ? h : (h - 1) / 2 + 1, Wo = stride == 1 ? w : (w - 1) / 2 + 1;
+    const size_t m_out = static_cast<size_t>(n) * Ho * Wo;
+    if (m_out <= 2048) {
+      s.workspace_bytes = 3 * m_out * cout * sizeof(float);
+      s.workspace = op_level_workspace(s.workspace_bytes);
+      if (s.workspace == nullptr) s.workspace_bytes = 0;
+    }
+  }
   ConvOp op;
   LR_TRY(build_conv_op(&op, s));
   return launch_conv_op(op, static_cast<cudaStream_t>(stream));

@@ -49,6 +49,10 @@ struct GemmParams {
   int a_stages;      // halo: depth of the activation (halo tile) ring; `stages` is then the depth of the weight ring
   int a_slot_bytes;  // halo: bytes of one activation slot (multiple of 1024)
   int ring_bytes;    // bytes of all pipeline rings = offset of the barrier block inside dynamic smem
+  int ksplit;        // split-K over the filter taps (1 = off, 3 = taps {0-2}, {3-5}, {6-8} as separate work units): for
+                     // convs whose M is too small to fill the GPU. Units then write raw fp32 partial tiles to `partial`
+                     // ([ksplit][M][ncols]) and splitk_reduce_kernel applies bias / residual and converts to fp16.
+  float* partial;
   int n_img, H, W;   // OUTPUT pixel grid
   int bw, bh, bn;    // tile box: bw*bh*bn == 128 output pixels
   int tiles_x, tiles_y, tiles_b, tiles_n;
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
   const int tiles_mp = (tiles_m + CG - 1) / CG;
   const int num_tiles = tiles_mp * p.tiles_n;
-  const int kiters = p.taps * (p.kc0 + p.kc1);
+  const int num_units = num_tiles * p.ksplit;  // unit u = (tile u / ksplit, tap range u % ksplit)
   const int unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
   const int b_rows = p.block_n / CG;
 
@@ -270,8 +274,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     int s = 0;
     uint32_t ph = 0;
     int tcount = 0;
-    for (int tile = unit0; tile < num_tiles; tile += unit_step, ++tcount) {
+    for (int u = unit0; u < num_units; u += unit_step, ++tcount) {
       LR_GEMM_TR(0, tcount, 0);
+      const int tile = u / p.ksplit, sp = u % p.ksplit;
+      const int tap_b = sp * p.taps / p.ksplit, tap_e = (sp + 1) * p.taps / p.ksplit;
       const int tn = tile % p.tiles_n;
       int tm = min((tile / p.tiles_n) * CG + static_cast<int>(rank), tiles_m - 1);
       const int tx = tm % p.tiles_x;
@@ -280,7 +286,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       const int tb = tm / p.tiles_y;
       const int x0 = tx * p.bw * p.stride, y0 = ty * p.bh * p.stride, n0 = tb * p.bn;
       const int ncol0 = tn * p.block_n + static_cast<int>(rank) * b_rows;  // this CTA's share of the weight rows
-      for (int tap = 0; tap < p.taps; ++tap) {
+      for (int tap = tap_b; tap < tap_e; ++tap) {
         const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
         const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
         for (int kc = 0; kc < p.kc0 + p.kc1; ++kc) {
@@ -383,12 +389,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       int as = 0;
       uint32_t aph = 0;
       int tcount = 0;
-      for (int tile = unit0; tile < num_tiles; tile += unit_step, ++tcount) {
+      for (int u = unit0; u < num_units; u += unit_step, ++tcount) {
         LR_GEMM_TR(1, tcount, 0);
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         LR_GEMM_TR(1, tcount, 1);
         const uint32_t d_tmem = tmem_base + as * 256;
+        const int sp = u % p.ksplit;
+        const int kiters = ((sp + 1) * p.taps / p.ksplit - sp * p.taps / p.ksplit) * (p.kc0 + p.kc1);
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
@@ -434,14 +442,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     bool stores_pending = false;
     // bias: one column per epilogue thread (block_n <= 256 = kEpiThreads), fetched ONE TILE AHEAD into a register
     auto fetch_bias = [&](int tile) -> float {
-      if (tile >= num_tiles || p.bias == nullptr || etid >= p.block_n || (p.dbg & 16)) return 0.f;
+      if (tile >= num_tiles || p.bias == nullptr || etid >= p.block_n || (p.dbg & 16)) return 0.f;  // tile = u / ksplit
       const int col = (tile % p.tiles_n) * p.block_n + etid;
       return col < p.ncols ? __ldg(p.bias + col) : 0.f;
     };
-    float bias_next = fetch_bias(unit0);
+    float bias_next = fetch_bias(unit0 / p.ksplit);
+    const size_t m_total = static_cast<size_t>(p.n_img) * p.H * p.W;
     int tcount = 0;
-    for (int tile = unit0; tile < num_tiles; tile += unit_step, ++tcount) {
+    for (int u = unit0; u < num_units; u += unit_step, ++tcount) {
       if (ew == 0) LR_GEMM_TR(2, tcount, 0);
+      const int tile = u / p.ksplit, sp = u % p.ksplit;
       uint8_t* cstage = smem + p.cstage_off + ((p.cstage_bufs == 2) ? (tcount & 1) * p.cstage_bytes : 0);
       const int tn = tile % p.tiles_n;
       int tm = (tile / p.tiles_n) * CG + static_cast<int>(rank);
@@ -472,7 +482,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       float* sb = sbias + as * 256;
       if (etid < p.block_n) sb[etid] = bias_next;
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      bias_next = fetch_bias(tile + unit_step);
+      bias_next = fetch_bias((u + unit_step) < num_units ? (u + unit_step) / p.ksplit : num_tiles);
 
       // residual of the first chunk is fetched before the accumulator is ready (it does not depend on the MMA)
       const bool fast = vec_ok && row_ok && !p.geglu;
@@ -509,6 +519,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         }
         tmem_ld_wait();
         const int col0 = ncol0 + c;
+        if (p.partial != nullptr) {
+          // split-K unit: raw fp32 partial sums; bias / residual / fp16 conversion happen in splitk_reduce_kernel
+          if (row_ok && col0 < p.ncols) {
+            float* po = p.partial + (static_cast<size_t>(sp) * m_total + grow) * p.ncols + col0;
+            if (col0 + 32 <= p.ncols && (p.ncols & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                reinterpret_cast<uint4*>(po)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.ncols) po[j] = __uint_as_float(v[j]);
+            }
+          }
+          continue;
+        }
         if (row_ok && col0 < p.ncols) {
           float f[32];
 #pragma unroll

@@ -200,35 +200,45 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   // (cg, block_n): minimise waves * per-tile cost. The per-tile cost models the measured behaviour of the kernel:
   // tensor time ~ block_n, but the mainloop is bound by the bytes each SM pulls from L2 per k-chunk,
   // (128 + block_n / cg) rows, when that exceeds what the SM can ingest while the MMAs run.
-  int block_n = s.force_block_n, cg = s.force_cg;
+  int block_n = s.force_block_n, cg = s.force_cg, ksplit = 1;
   {
+    // split-K over the nine taps (3 work units per output tile + a reduction pass) for convs whose M cannot fill the
+    // GPU with full-width tiles: needs scratch for the fp32 partial tiles
+    const size_t m_out = static_cast<size_t>(s.n_img) * Ho * Wo;
+    static const bool splitk_enabled = getenv("LR_NO_SPLITK") == nullptr;
+    const bool can_split = splitk_enabled && s.taps == 9 && !halo && !s.geglu && s.workspace != nullptr &&
+                           s.workspace_bytes >= 3 * m_out * s.ncols * sizeof(float) && s.ncols % 8 == 0 &&
+                           s.ld_out % 8 == 0 && (s.residual == nullptr || s.ld_res % 8 == 0);
     double best = 1e300;
-    int best_bn = 0, best_cg = 0;
-    for (int c = 1; c <= 2; ++c) {
-      if (s.force_cg && c != s.force_cg) continue;
-      if (c == 2 && tiles_m < 2) continue;
-      for (int bnn = 256; bnn >= 32; bnn -= 32) {
-        if (s.force_block_n && bnn != s.force_block_n) continue;
-        if (c == 2 && bnn % 32 != 0) continue;
-        const long long units = 1LL * cdiv(tiles_m, c) * cdiv(s.ncols, bnn);
-        const long long slots = sm_count() / c;
-        const long long waves = (units + slots - 1) / slots;
-        const double tensor = bnn;                               // ~ cycles / 0.5 per k16 step
-        // bytes-bound mainloop (calibrated on B200, ncu r1): rows of activations + weights each SM pulls per k-chunk;
-        // in halo mode one 180-row box serves nine chunks
-        const double ingest = (halo ? 20.0 : 128.0) + bnn / c;
-        const double per_tile = (tensor > ingest ? tensor : ingest) + 40.0;
-        const double cost = waves * per_tile;
-        if (cost < best) {
-          best = cost;
-          best_bn = bnn;
-          best_cg = c;
+    int best_bn = 0, best_cg = 0, best_ks = 1;
+    for (int ks = 1; ks <= (can_split ? 3 : 1); ks += 2) {
+      for (int c = 1; c <= 2; ++c) {
+        if (s.force_cg && c != s.force_cg) continue;
+        if (c == 2 && tiles_m < 2) continue;
+        for (int bnn = 256; bnn >= 32; bnn -= 32) {
+          if (s.force_block_n && bnn != s.force_block_n) continue;
+          const long long units = 1LL * cdiv(tiles_m, c) * cdiv(s.ncols, bnn) * ks;
+          const long long slots = sm_count() / c;
+          const long long waves = (units + slots - 1) / slots;
+          const double tensor = bnn;  // ~ cycles / 0.5 per k16 step
+          // bytes-bound mainloop (calibrated on B200, ncu r1): rows of activations + weights each SM pulls per k-chunk;
+          // in halo mode one 180-row box serves nine chunks
+          const double ingest = (halo ? 20.0 : 128.0) + bnn / c;
+          const double per_tile = (tensor > ingest ? tensor : ingest) / ks + 40.0 + (ks > 1 ? 25.0 : 0.0);
+          const double cost = waves * per_tile;
+          if (cost < best) {
+            best = cost;
+            best_bn = bnn;
+            best_cg = c;
+            best_ks = ks;
+          }
         }
       }
     }
     LR_CHECK(best_bn != 0, "conv: no feasible tile configuration");
     block_n = best_bn;
     cg = best_cg;
+    ksplit = best_ks;
   }
   LR_CHECK(block_n % 32 == 0 && block_n >= 32 && block_n <= 256, "conv: bad block_n");
   LR_CHECK(!s.geglu || (s.ncols % 2 == 0), "conv: GEGLU needs an even column count");
@@ -238,7 +248,7 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   // one 32-column remainder, and (with a residual) whole 32-column chunks
   const int n_valid = s.geglu ? s.ncols / 2 : s.ncols;
   const int ocols_tile = s.geglu ? block_n / 2 : block_n;
-  const bool tma_store = (s.ld_out % 8 == 0) && ((ocols_tile % 64) == 0 || (ocols_tile % 64) == 32) &&
+  const bool tma_store = ksplit == 1 && (s.ld_out % 8 == 0) && ((ocols_tile % 64) == 0 || (ocols_tile % 64) == 32) &&
                          (s.residual == nullptr || (n_valid % 32 == 0 && s.ld_res % 8 == 0)) &&
                          getenv("LR_NO_TMA_STORE") == nullptr;
   const int cstage_bytes = tma_store ? kBlockM * ocols_tile * 2 : 0;  // multiple of 8 KB: keeps 1024 B alignment
@@ -281,10 +291,12 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   p.cstage_off = (ring_bytes + kGemmAuxBytes + 1023) & ~1023;  // swizzle needs 1024 B
   p.cstage_bufs = bufs;
   p.cstage_bytes = cstage_bytes;
-  p.bias = s.bias;
-  p.bias_img = s.bias_img;
+  p.ksplit = ksplit;
+  p.partial = ksplit > 1 ? s.workspace : nullptr;
+  p.bias = ksplit > 1 ? nullptr : s.bias;  // split-K: bias / per-image bias / residual are applied by the reduction
+  p.bias_img = ksplit > 1 ? nullptr : s.bias_img;
   p.ld_bias_img = s.ld_bias_img > 0 ? s.ld_bias_img : s.ncols;
-  p.residual = s.residual;
+  p.residual = ksplit > 1 ? nullptr : s.residual;
   p.ld_res = s.ld_res;
   p.out = s.out;
   p.ld_out = s.ld_out;
@@ -338,7 +350,19 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
     box[0] = 32;
     LR_TRY(make_tmap(&p.tmC2, s.out, 4, dims, str, box, es, false));
   }
-  const int num_units = cdiv(tiles_m, cg) * p.tiles_n;
+  const int num_units = cdiv(tiles_m, cg) * p.tiles_n * ksplit;
+  op->ksplit = ksplit;
+  op->ncols = s.ncols;
+  op->rows_per_img = Ho * Wo;
+  op->ld_bias_img = s.ld_bias_img > 0 ? s.ld_bias_img : s.ncols;
+  op->ld_res = s.ld_res;
+  op->ld_out = s.ld_out;
+  op->m_out = static_cast<size_t>(s.n_img) * Ho * Wo;
+  op->partial = s.workspace;
+  op->bias = s.bias;
+  op->bias_img = s.bias_img;
+  op->residual = s.residual;
+  op->out = s.out;
   const int slots = sm_count() / cg;
   op->grid = (num_units < slots ? num_units : slots) * cg;
   op->smem = tma_store ? p.cstage_off + bufs * cstage_bytes : 1024 + ring_bytes + kGemmAuxBytes;
@@ -365,7 +389,30 @@ int launch_conv_op(const ConvOp& op, cudaStream_t st) {
     LR_CUDA(launch_pdl(gemm_conv_kernel<1>, dim3(op.grid), dim3(kGemmThreads), op.smem, st, 1, *p));
   }
   LR_LAUNCHED();
+  if (op.ksplit > 1) {
+    const size_t total = op.m_out * (op.ncols / 8);
+    LR_CUDA(launch_pdl(splitk_reduce_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, 1,
+                       static_cast<const float*>(op.partial), op.ksplit, op.m_out, op.ncols, op.rows_per_img, op.bias,
+                       op.bias_img, op.ld_bias_img, op.residual, op.ld_res, op.out, op.ld_out));
+    LR_LAUNCHED();
+  }
   return 0;
+}
+
+// Scratch for the op-level entry points (lr_conv3x3_f16): grown on demand, never shrunk, one per process. The engine
+// passes plan-owned scratch instead.
+float* op_level_workspace(size_t bytes) {
+  static float* ws = nullptr;
+  static size_t ws_bytes = 0;
+  if (bytes > (size_t(64) << 20)) return nullptr;
+  if (bytes > ws_bytes) {
+    if (ws) cudaFree(ws);
+    ws = nullptr;
+    ws_bytes = 0;
+    if (cudaMalloc(&ws, bytes) != cudaSuccess) return nullptr;
+    ws_bytes = bytes;
+  }
+  return ws;
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -53,6 +53,8 @@ struct ConvSpec {
   __half* out = nullptr;
   int ld_out = 0;
   int geglu = 0;
+  float* workspace = nullptr;  // optional split-K scratch (fp32 partial tiles), workspace_bytes >= 3 * M_out * ncols * 4
+  size_t workspace_bytes = 0;
   int force_block_n = 0;  // testing hook: 0 = heuristic
   int force_cg = 0;       // testing hook: 0 = heuristic, 1 = single CTA, 2 = CTA pair (cta_group::2)
 };
@@ -61,10 +63,19 @@ struct ConvOp {
   int grid = 0, smem = 0;
   int out_h = 0, out_w = 0;
   int block_n = 0, stages = 0, tiles = 0, cg = 1;
+  // split-K (ksplit > 1): the GEMM kernel writes fp32 partials, launch_conv_op then runs the reduction
+  int ksplit = 1, ncols = 0, rows_per_img = 0, ld_bias_img = 0, ld_res = 0, ld_out = 0;
+  size_t m_out = 0;
+  float* partial = nullptr;
+  const float* bias = nullptr;
+  const float* bias_img = nullptr;
+  const __half* residual = nullptr;
+  __half* out = nullptr;
   double flops = 0;
 };
 int build_conv_op(ConvOp* op, const ConvSpec& s);
 int launch_conv_op(const ConvOp& op, cudaStream_t st);
+float* op_level_workspace(size_t bytes);
 
 // ---- attention ----
 struct AttnSpec {

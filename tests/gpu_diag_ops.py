@@ -229,6 +229,9 @@ CASES = {
     "conv_halo_big": lambda: case_conv(2, 64, 128, 320, 320, bias_img=True, residual=True),
     "conv_halo_concat": lambda: case_conv(1, 32, 64, 128, 160, c1=192, force=2160),
     "conv_halo_1cta": lambda: case_conv(3, 40, 24, 64, 64, residual=True, force=1064),
+    "conv_splitk": lambda: case_conv(8, 8, 16, 128, 256, bias_img=True, residual=True),
+    "conv_splitk_concat": lambda: case_conv(4, 8, 16, 64, 192, c1=128),
+    "conv_splitk_s2": lambda: case_conv(2, 16, 32, 64, 128, stride=2, residual=True),
     "conv_s2": lambda: case_conv(2, 16, 32, 64, 64, stride=2),
     "conv_s2_big": lambda: case_conv(2, 64, 128, 64, 64, stride=2),
     "conv_cout4": lambda: case_conv(2, 16, 32, 64, 4),
