@@ -49,6 +49,12 @@ struct GemmParams {
   int a_stages;      // halo: depth of the activation (halo tile) ring; `stages` is then the depth of the weight ring
   int a_slot_bytes;  // halo: bytes of one activation slot (multiple of 1024)
   int ring_bytes;    // bytes of all pipeline rings = offset of the barrier block inside dynamic smem
+  int res_tma;       // 1: the residual tile is TMA-loaded into the (double-buffered) staging buffer one tile ahead and
+                     // the epilogue adds it in place. A thread-per-row LDG.128 of the residual touches 32 different
+                     // 128-byte lines per instruction (rows are ld_res apart): ~3000 L1 wavefront cycles per tile,
+                     // which is what made "+ residual" cost 17 us on the 65536 x 320 -> 320 linears.
+  CUtensorMap tmR;   // residual [n_valid, W, H, N], box (64 cols, bw, bh, bn), 128B swizzle (same geometry as tmC)
+  CUtensorMap tmR2;  // 32-column remainder slab, no swizzle (same geometry as tmC2)
   int ksplit;        // split-K over the filter taps (1 = off, 3 = taps {0-2}, {3-5}, {6-8} as separate work units): for
                      // convs whose M is too small to fill the GPU. Units then write raw fp32 partial tiles to `partial`
                      // ([ksplit][M][ncols]) and splitk_reduce_kernel applies bias / residual and converts to fp16.
@@ -109,7 +115,7 @@ constexpr int kMaxAStages = 4;
 constexpr int kHaloBW = 8, kHaloBH = 16;  // halo-mode output tile: 8 pixels wide x 16 rows
 constexpr int kBarBytes = 512;
 constexpr int kGemmAuxBytes = kBarBytes /*barriers*/ + 2 * 256 * 4 /*bias staging, double buffered*/;
-static_assert((2 * kMaxStages + 4 + 2 * kMaxAStages + 4) * 8 + 4 <= kBarBytes, "barrier block overflows");
+static_assert((2 * kMaxStages + 4 + 2 * kMaxAStages + 6) * 8 + 4 <= kBarBytes, "barrier block overflows");
 
 // bytes of one pipeline stage in ONE CTA (cg = CTAs cooperating on a tile: each holds block_n / cg weight rows)
 __host__ __device__ inline int gemm_stage_bytes(int block_n, int cg = 1) {
@@ -153,7 +159,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   uint64_t* a_empty = a_full + kMaxAStages;  // [kMaxAStages]
   uint64_t* cfull = a_empty + kMaxAStages;   // [2] staged output tile complete (all epilogue threads arrived)
   uint64_t* cfree = cfull + 2;               // [2] its TMA stores have finished reading the staging buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfree + 2);
+  uint64_t* rfull = cfree + 2;               // [2] residual tile has landed in staging buffer b (res_tma)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);  // [2][256]
 
   const int hw_warp = threadIdx.x >> 5;
@@ -188,6 +195,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     for (int i = 0; i < 2; ++i) {
       mbar_init(&cfull[i], kEpiThreads);
       mbar_init(&cfree[i], 1);
+      mbar_init(&rfull[i], 1);
     }
     fence_barrier_init();
   }
@@ -448,6 +456,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     };
     float bias_next = fetch_bias(unit0 / p.ksplit);
     const size_t m_total = static_cast<size_t>(p.n_img) * p.H * p.W;
+    // res_tma: (one thread) loads the residual tile of unit `un` into staging buffer `buf`
+    auto issue_res = [&](int un, int buf) {
+      const int tile2 = un / p.ksplit;
+      int tm2 = min((tile2 / p.tiles_n) * CG + static_cast<int>(rank), tiles_m - 1);
+      const int tx2 = tm2 % p.tiles_x;
+      tm2 /= p.tiles_x;
+      const int ty2 = tm2 % p.tiles_y;
+      const int tb2 = tm2 / p.tiles_y;
+      const int oc0 = (tile2 % p.tiles_n) * p.block_n;
+      uint8_t* dst = smem + p.cstage_off + buf * p.cstage_bytes;
+      int bytes = 0;
+      for (int sl = 0; sl < full_slabs; ++sl)
+        if (oc0 + sl * 64 < p.n_valid) bytes += kBlockM * 128;
+      const bool rem = (ocols_tile & 63) != 0 && oc0 + full_slabs * 64 < p.n_valid;
+      if (rem) bytes += kBlockM * 64;
+      mbar_arrive_expect_tx(&rfull[buf], bytes);
+      for (int sl = 0; sl < full_slabs; ++sl)
+        if (oc0 + sl * 64 < p.n_valid)
+          tma_load_4d(dst + sl * (kBlockM * 128), &p.tmR, &rfull[buf], oc0 + sl * 64, tx2 * p.bw, ty2 * p.bh, tb2 * p.bn);
+      if (rem)
+        tma_load_4d(dst + full_slabs * (kBlockM * 128), &p.tmR2, &rfull[buf], oc0 + full_slabs * 64, tx2 * p.bw,
+                    ty2 * p.bh, tb2 * p.bn);
+    };
+    if (p.res_tma && etid == 0 && unit0 < num_units) issue_res(unit0, 0);
     int tcount = 0;
     for (int u = unit0; u < num_units; u += unit_step, ++tcount) {
       if (ew == 0) LR_GEMM_TR(2, tcount, 0);
@@ -485,7 +517,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       bias_next = fetch_bias((u + unit_step) < num_units ? (u + unit_step) / p.ksplit : num_tiles);
 
       // residual of the first chunk is fetched before the accumulator is ready (it does not depend on the MMA)
-      const bool fast = vec_ok && row_ok && !p.geglu;
+      const bool fast = vec_ok && row_ok && !p.geglu && !p.res_tma;
       const __half* res_row = (p.residual != nullptr) ? p.residual + grow * p.ld_res : nullptr;
       uint4 rnext[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
       int c = half * 32;
@@ -498,6 +530,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       if (ew == 0) LR_GEMM_TR(2, tcount, 1);
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
+      if (p.res_tma) mbar_wait(&rfull[tcount & 1], (tcount >> 1) & 1);  // residual tile is in the staging buffer
       if (ew == 0) LR_GEMM_TR(2, tcount, 2);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
       for (; c < p.block_n; c += 64) {
@@ -511,6 +544,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         uint4 rcur[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) rcur[k] = rnext[k];
+        if (p.res_tma) {
+          // the residual chunk sits exactly where this thread will write its output chunk
+          const int slab = c >> 6, cp0 = (c & 63) >> 3;
+          const uint8_t* rowp = (slab < full_slabs) ? cstage + slab * (kBlockM * 128) + r * 128
+                                                    : cstage + full_slabs * (kBlockM * 128) + r * 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            rcur[k] = (slab < full_slabs) ? *reinterpret_cast<const uint4*>(rowp + (((cp0 + k) ^ (r & 7)) << 4))
+                                          : *reinterpret_cast<const uint4*>(rowp + ((cp0 + k) << 4));
+        }
         const int cn = c + 64;
         if (fast && res_row != nullptr && cn < p.block_n && ncol0 + cn + 32 <= p.n_valid) {
           const uint4* rp = reinterpret_cast<const uint4*>(res_row + ncol0 + cn);
@@ -658,6 +701,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
           tma_store_commit();
           stores_pending = true;
         }
+        // the other staging buffer is free (its last store was confirmed above): fetch the next tile's residual into it
+        if (p.res_tma && etid == 0 && u + unit_step < num_units) issue_res(u + unit_step, (tcount + 1) & 1);
         if (ew == 0) LR_GEMM_TR(2, tcount, 5);
       }
 #endif

@@ -338,6 +338,21 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
     uint32_t es[2] = {1, 1};
     LR_TRY(make_tmap(&p.tmB, s.w, 2, dims, str, box, es));
   }
+  p.res_tma = 0;
+  static const bool res_tma_enabled = getenv("LR_NO_RES_TMA") == nullptr;
+  if (res_tma_enabled && tma_store && s.residual != nullptr && bufs == 2 && ksplit == 1) {
+    // residual tile loaded by TMA into the staging buffer, same tiling as the output
+    uint64_t dims[4] = {static_cast<uint64_t>(n_valid), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
+                        static_cast<uint64_t>(s.n_img)};
+    uint64_t str[3] = {static_cast<uint64_t>(s.ld_res) * 2, static_cast<uint64_t>(s.ld_res) * 2 * Wo,
+                       static_cast<uint64_t>(s.ld_res) * 2 * Wo * Ho};
+    uint32_t box[4] = {64, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
+    uint32_t es[4] = {1, 1, 1, 1};
+    LR_TRY(make_tmap(&p.tmR, s.residual, 4, dims, str, box, es, true));
+    box[0] = 32;
+    LR_TRY(make_tmap(&p.tmR2, s.residual, 4, dims, str, box, es, false));
+    p.res_tma = 1;
+  }
   if (tma_store) {
     // output tensor as the kernel tiles it: [cols, W, H, N] over the OUTPUT pixel grid
     uint64_t dims[4] = {static_cast<uint64_t>(n_valid), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),

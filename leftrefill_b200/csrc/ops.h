@@ -59,7 +59,7 @@ struct ConvSpec {
   int force_cg = 0;       // testing hook: 0 = heuristic, 1 = single CTA, 2 = CTA pair (cta_group::2)
 };
 struct ConvOp {
-  alignas(64) unsigned char params[1024];  // GemmParams (opaque here so headers stay CUDA-kernel free)
+  alignas(64) unsigned char params[2048];  // GemmParams (opaque here so headers stay CUDA-kernel free)
   int grid = 0, smem = 0;
   int out_h = 0, out_w = 0;
   int block_n = 0, stages = 0, tiles = 0, cg = 1;
