@@ -48,6 +48,9 @@ struct GemmParams {
   int halo;          // 1: halo mode (see the header comment); tile box is bw = 8, bh = 16, bn = 1
   int a_stages;      // halo: depth of the activation (halo tile) ring; `stages` is then the depth of the weight ring
   int a_slot_bytes;  // halo: bytes of one activation slot (multiple of 1024)
+  int b_group;       // halo: weight tiles (taps) per weight-ring stage: 1, or 3 = one filter row (dx = -1, 0, 1) per barrier
+                     // round trip (the producer <-> MMA handshake costs ~440 cycles, more than the MMAs of one
+                     // 160-column tap)
   int ring_bytes;    // bytes of all pipeline rings = offset of the barrier block inside dynamic smem
   int res_tma;       // 1: the residual tile is TMA-loaded into the (double-buffered) staging buffer one tile ahead and
                      // the epilogue adds it in place. A thread-per-row LDG.128 of the residual touches 32 different
@@ -142,6 +145,11 @@ __device__ __forceinline__ float fast_erf(float x) {
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
 
+template <int V>
+struct IntTag {
+  static constexpr int value = V;
+};
+
 template <int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -225,11 +233,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
 
   if (warp == 0 && p.halo) {
     // ------------------------------- TMA producer, halo mode ------------------------------------------------
-    int sa = 0, sb = 0;
-    uint32_t pha = 0, phb = 0;
     uint8_t* b_ring = smem + p.a_stages * p.a_slot_bytes;
     const int b_bytes = b_rows * kBlockK * 2;
     const int a_tx = (kHaloBW + 2) * (kHaloBH + 2) * kBlockK * 2;  // TMA credits the full box, zero-filled parts included
+    auto produce = [&](auto g_tag) {
+    constexpr int kG = decltype(g_tag)::value;  // weight tiles (taps) per weight-ring stage
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
     int tcount = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_step, ++tcount) {
       LR_GEMM_TR(0, tcount, 0);
@@ -258,17 +268,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         }
         __syncwarp();
         if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < 9; tap += kG) {
           mbar_wait(&empty[sb], phb ^ 1);
           if (elect_one()) {
-            const int kb = tap * p.ctot + (src0 ? 0 : p.c0) + kch;
-            uint8_t* b_s = b_ring + sb * b_bytes;
+            uint8_t* b_s = b_ring + sb * b_bytes * kG;
             if (CG == 2) {
-              if (leader) mbar_arrive_expect_tx(&full[sb], 2 * b_bytes);
-              tma_load_2d_2sm(b_s, &p.tmB, &full[sb], kb, ncol0);
+              if (leader) mbar_arrive_expect_tx(&full[sb], 2 * b_bytes * kG);
             } else {
-              mbar_arrive_expect_tx(&full[sb], b_bytes);
-              tma_load_2d(b_s, &p.tmB, &full[sb], kb, ncol0);
+              mbar_arrive_expect_tx(&full[sb], b_bytes * kG);
+            }
+#pragma unroll
+            for (int g = 0; g < kG; ++g) {
+              const int kb = (tap + g) * p.ctot + (src0 ? 0 : p.c0) + kch;
+              if (CG == 2) tma_load_2d_2sm(b_s + g * b_bytes, &p.tmB, &full[sb], kb, ncol0);
+              else tma_load_2d(b_s + g * b_bytes, &p.tmB, &full[sb], kb, ncol0);
             }
           }
           __syncwarp();
@@ -277,6 +290,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       }
       LR_GEMM_TR(0, tcount, 1);
     }
+    };
+    if (p.b_group == 3) produce(IntTag<3>{}); else produce(IntTag<1>{});
   } else if (warp == 0) {
     // ------------------------------- TMA producer (whole warp loops, one elected lane issues) ---------------
     int s = 0;
@@ -334,6 +349,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       const uint32_t b_lo0 = umma_desc_lo(smem_u32(smem) + p.a_stages * p.a_slot_bytes, 16);
       const uint32_t a_units = static_cast<uint32_t>(p.a_slot_bytes) >> 4;
       const uint32_t b_units = static_cast<uint32_t>(b_rows * kBlockK * 2) >> 4;
+      auto issue = [&](auto g_tag) {
+      constexpr int kG = decltype(g_tag)::value;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int as = 0;
@@ -350,19 +367,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
           mbar_wait(&a_full[sa], pha);
           tc_fence_after();
           if (kc == 0) LR_GEMM_TR(1, tcount, 2);
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap0 = 0; tap0 < 9; tap0 += kG) {
             mbar_wait(&full[sb], phb);
             tc_fence_after();
             if (elect_one()) {
-              // tap (dy, dx) = (tap / 3 - 1, tap % 3 - 1): start (dy + 1) * 10 + (dx + 1) rows (128 B = 8 units) into the box
-              const uint32_t a_lo = a_lo0 + sa * a_units + static_cast<uint32_t>((tap / 3) * (kHaloBW + 2) + tap % 3) * 8u;
-              const uint32_t b_lo = b_lo0 + sb * b_units;
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                const uint64_t ad = umma_desc_make(desc_hi_a, a_lo + 2 * k);
-                const uint64_t bd = umma_desc_make(desc_hi_b, b_lo + 2 * k);
-                if (CG == 2) umma_f16_2sm(d_tmem, ad, bd, idesc, (started | k) != 0 ? 1u : 0u);
-                else umma_f16(d_tmem, ad, bd, idesc, (started | k) != 0 ? 1u : 0u);
+              for (int g = 0; g < kG; ++g) {
+                const int tap = tap0 + g;
+                // tap (dy, dx) = (tap / 3 - 1, tap % 3 - 1): start (dy + 1) * 10 + (dx + 1) rows (128 B = 8 units) into the box
+                const uint32_t a_lo = a_lo0 + sa * a_units + static_cast<uint32_t>((tap / 3) * (kHaloBW + 2) + tap % 3) * 8u;
+                const uint32_t b_lo = b_lo0 + (sb * kG + g) * b_units;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  const uint64_t ad = umma_desc_make(desc_hi_a, a_lo + 2 * k);
+                  const uint64_t bd = umma_desc_make(desc_hi_b, b_lo + 2 * k);
+                  if (CG == 2) umma_f16_2sm(d_tmem, ad, bd, idesc, (started | g | k) != 0 ? 1u : 0u);
+                  else umma_f16(d_tmem, ad, bd, idesc, (started | g | k) != 0 ? 1u : 0u);
+                }
               }
               if (CG == 2) umma_commit_2sm(&empty[sb]); else umma_commit(&empty[sb]);
             }
@@ -383,6 +404,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         LR_GEMM_TR(1, tcount, 3);
         if (++as == 2) { as = 0; aph ^= 1; }
       }
+      };
+      if (p.b_group == 3) issue(IntTag<3>{}); else issue(IntTag<1>{});
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer (whole warp loops, one elected lane issues) ----------------

@@ -262,15 +262,23 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   const int a_slot = ((kHaloBW + 2) * (kHaloBH + 2) * kBlockK * 2 + 1023) & ~1023;
   if (halo) {
     // two rings: activation halo tiles (one per 64-channel chunk) and weight tiles (one per chunk and tap)
-    const int b_bytes = (block_n / cg) * kBlockK * 2;
+    static const int bgroup_max_bn = env_int("LR_HALO_BGROUP_MAX_BN", 192);  // one filter row per stage up to this block_n
+    int b_group = (block_n <= bgroup_max_bn) ? 3 : 1;
+    int b_bytes = (block_n / cg) * kBlockK * 2 * b_group;
     a_stages = 3;
     stages = (budget - a_stages * a_slot - bufs * cstage_bytes) / b_bytes;
-    if (stages < 4) {
+    if (b_group == 3 && stages < 3) {  // not enough room for three grouped stages: one tap per stage
+      b_group = 1;
+      b_bytes = (block_n / cg) * kBlockK * 2;
+      stages = (budget - a_stages * a_slot - bufs * cstage_bytes) / b_bytes;
+    }
+    if (stages < 4 && b_group == 1) {
       a_stages = 2;
       stages = (budget - a_stages * a_slot - bufs * cstage_bytes) / b_bytes;
     }
     if (stages > kMaxStages) stages = kMaxStages;
     LR_CHECK(stages >= 2, "conv (halo): not enough shared memory for 2 weight stages");
+    p.b_group = b_group;
     ring_bytes = a_stages * a_slot + stages * b_bytes;
   } else {
     stages = (budget - bufs * cstage_bytes) / gemm_stage_bytes(block_n, cg);
