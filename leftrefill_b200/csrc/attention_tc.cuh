@@ -34,7 +34,10 @@ constexpr int kAttnTile = 128;                          // rows of one query til
 constexpr int kAttnQBlock = 2 * kAttnTile;              // queries per CTA
 constexpr int kAttnD = 64;
 constexpr int kAttnTileBytes = kAttnTile * kAttnD * 2;  // 16 KB
-constexpr int kAttnStages = 4;
+#ifndef LR_ATTN_STAGES
+#define LR_ATTN_STAGES 4
+#endif
+constexpr int kAttnStages = LR_ATTN_STAGES;
 constexpr int kAttnSmemBytes = 2 * kAttnTileBytes /*Q0,Q1*/ + kAttnStages * 2 * kAttnTileBytes /*K,V ring*/ +
                                256 /*barriers*/;
 constexpr int kTmemS = 0, kTmemP = 256, kTmemO = 384;  // column bases (S: 128 per tile, P: 64, O: 64)
