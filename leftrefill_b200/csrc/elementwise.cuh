@@ -342,7 +342,9 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                : "memory");
 }
 
-template <int VPL>  // 8-channel vectors per lane: ceil(C / 256)
+// kStatsOnly: writes (mean, rstd) per row to `out` (reinterpreted as float2*) instead of the normalised rows: the
+// LayerNorm itself is then folded into the consuming GEMM (gemm_tc.cuh, GemmParams::ln_stats).
+template <int VPL, bool kStatsOnly>  // 8-channel vectors per lane: ceil(C / 256)
 __global__ void __launch_bounds__(kLnThreads) layernorm_kernel(const __half* __restrict__ x, int M, int C,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float eps,
@@ -362,9 +364,11 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_kernel(const __half* __r
     fence_barrier_init();
   }
   // weights are never written inside a forward: safe to read before pdl_wait
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    gb[i] = gamma[i];
-    gb[C + i] = beta[i];
+  if (!kStatsOnly) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      gb[i] = gamma[i];
+      gb[C + i] = beta[i];
+    }
   }
   __syncthreads();
   pdl_wait();
@@ -452,8 +456,15 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_kernel(const __half* __r
 #pragma unroll
     for (int r = 0; r < kLnRowsPerWarp; ++r) rstd[r] = rsqrtf(rstd[r] * inv_c + eps);
     const long long row_base = static_cast<long long>(t) * kLnTileRows + r0;
+    if (kStatsOnly) {
+      if (lane == 0) {
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
+        for (int r = 0; r < kLnRowsPerWarp; ++r)
+          if (row_base + r < M) reinterpret_cast<float2*>(out)[row_base + r] = make_float2(mean[r], rstd[r]);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < (kStatsOnly ? 0 : VPL); ++v) {
       const int vi = lane + v * 32;
       if (vi < nvec) {
         const float4 g0 = *reinterpret_cast<const float4*>(gb + vi * 8);
@@ -474,6 +485,35 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_kernel(const __half* __r
         }
       }
     }
+  }
+}
+
+// LayerNorm folding (run once per weight update): for a Linear W [rows, K] (fp16, GEMM layout) that consumes
+// LayerNorm(gamma, beta): Wf[j, k] = fp16(W[j, k] * gamma[k]), s[j] = sum_k Wf[j, k], bf[j] = bias[j] + sum_k W[j, k] beta[k].
+// One warp per output row.
+__global__ void __launch_bounds__(256) ln_fold_kernel(const __half* __restrict__ w, int rows, int K,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ bias, __half* __restrict__ wf,
+                                                      float* __restrict__ s_out, float* __restrict__ bf_out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float s = 0.f, bacc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = __half2float(w[static_cast<size_t>(row) * K + k]);
+    const __half h = __float2half_rn(wv * gamma[k]);
+    wf[static_cast<size_t>(row) * K + k] = h;
+    s += __half2float(h);
+    bacc = fmaf(wv, beta[k], bacc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    bacc += __shfl_xor_sync(0xffffffffu, bacc, o);
+  }
+  if (lane == 0) {
+    s_out[row] = s;
+    bf_out[row] = (bias != nullptr ? bias[row] : 0.f) + bacc;
   }
 }
 

@@ -39,6 +39,9 @@ struct TBlockW {
   size_t ln1_g, ln1_b, qkv_w, out1_w, out1_b;
   size_t ln2_g, ln2_b, q2_w, kv2_w, out2_w, out2_b;
   size_t ln3_g, ln3_b, ff1_w, ff1_b, ff2_w, ff2_b;
+  // LayerNorm folded into its consuming Linear (gemm_tc.cuh, GemmParams::ln_stats): gamma-scaled fp16 copies of the
+  // weights, their column sums and the beta-shifted biases, rebuilt by run_folds() whenever a weight changes
+  size_t qkv_wf, qkv_s, qkv_bf, q2_wf, q2_s, q2_bf, ff1_wf, ff1_s, ff1_bf;
   int kv_slot = 0;
 };
 struct STW {
@@ -267,6 +270,15 @@ struct lr_unet {
       t.ln2_b = reg_vec(b + "norm2.bias", C);
       t.ln3_g = reg_vec(b + "norm3.weight", C);
       t.ln3_b = reg_vec(b + "norm3.bias", C);
+      t.qkv_wf = halloc(static_cast<size_t>(3) * C * C);
+      t.qkv_s = falloc(3 * C);
+      t.qkv_bf = falloc(3 * C);
+      t.q2_wf = halloc(static_cast<size_t>(C) * C);
+      t.q2_s = falloc(C);
+      t.q2_bf = falloc(C);
+      t.ff1_wf = halloc(static_cast<size_t>(8) * C * C);
+      t.ff1_s = falloc(8 * C);
+      t.ff1_bf = falloc(8 * C);
       t.kv_slot = n_kv_slots++;
       kv_C.push_back(C);
       s.blocks.push_back(t);
@@ -371,6 +383,22 @@ struct lr_unet {
     return 0;
   }
 
+  bool fold_dirty = true;
+  bool ln_fold = getenv("LR_NO_LN_FOLD") == nullptr;
+  int run_folds(cudaStream_t st) {
+    if (!fold_dirty || !ln_fold) return 0;
+    for (const STW& s : sts) {
+      const int C = s.C;
+      for (const TBlockW& b : s.blocks) {
+        LR_TRY(launch_ln_fold(H(b.qkv_w), 3 * C, C, F(b.ln1_g), F(b.ln1_b), nullptr, H(b.qkv_wf), F(b.qkv_s), F(b.qkv_bf), st));
+        LR_TRY(launch_ln_fold(H(b.q2_w), C, C, F(b.ln2_g), F(b.ln2_b), nullptr, H(b.q2_wf), F(b.q2_s), F(b.q2_bf), st));
+        LR_TRY(launch_ln_fold(H(b.ff1_w), 8 * C, C, F(b.ln3_g), F(b.ln3_b), F(b.ff1_b), H(b.ff1_wf), F(b.ff1_s), F(b.ff1_bf), st));
+      }
+    }
+    fold_dirty = false;
+    return 0;
+  }
+
   int ensure_arenas() {
     if (harena == nullptr) {
       LR_CUDA(cudaMalloc(&harena, half_elems * sizeof(__half)));
@@ -428,8 +456,11 @@ struct lr_unet {
     return 0;
   }
   int add_linear(const __half* a, int M, int K, const __half* w, int ncols, const float* bias, const __half* residual,
-                 int ld_res, __half* out, int ld_out, int geglu) {
+                 int ld_res, __half* out, int ld_out, int geglu, const float* ln_stats = nullptr,
+                 const float* ln_s = nullptr) {
     ConvSpec s;
+    s.ln_stats = ln_stats;
+    s.ln_s = ln_s;
     s.a0 = a;
     s.c0 = K;
     s.lda0 = K;
@@ -460,6 +491,11 @@ struct lr_unet {
       return launch_groupnorm(x0, c0, x1, c1, n, P, 32, eps, g, b, silu, st_, 1, out, st);
     }, 2, 0.0, "groupnorm n=" + std::to_string(n) + " P=" + std::to_string(P) + " c=" + std::to_string(c0) + "+" +
                    std::to_string(c1));
+    return 0;
+  }
+  int add_ln_stats(const __half* x, int M, int C, float* stats) {
+    push([=](cudaStream_t st) { return launch_layernorm_stats(x, M, C, 1e-5f, stats, st); }, 3, 0.0,
+         "layernorm-stats M=" + std::to_string(M) + " C=" + std::to_string(C));
     return 0;
   }
   int add_ln(const __half* x, int M, int C, const float* g, const float* b, __half* out) {
@@ -601,6 +637,8 @@ struct lr_unet {
     pool.release(xn);
     LR_TRY(acquire_h(static_cast<size_t>(Mfull) * C, &t));
     LR_TRY(acquire_h(static_cast<size_t>(Mfull) * C, &a));
+    float* lnst;  // (mean, rstd) per token row for the folded LayerNorms
+    LR_TRY(acquire_f(static_cast<size_t>(Mfull) * 2, &lnst));
     bool first_block = true;
     for (const TBlockW& b : s.blocks) {
       if (!first_block && n != n_full) {  // depth > 1: only block 0's self-attention is shared
@@ -610,9 +648,14 @@ struct lr_unet {
         M = Mfull;
       }
       // self-attention: x = attn1(norm1(x)) + x
-      LR_TRY(add_ln(h, M, C, F(b.ln1_g), F(b.ln1_b), t));
       LR_TRY(acquire_h(static_cast<size_t>(M) * 3 * C, &qkv));
-      LR_TRY(add_linear(t, M, C, H(b.qkv_w), 3 * C, nullptr, nullptr, 0, qkv, 3 * C, 0));
+      if (ln_fold) {  // LayerNorm folded into the QKV projection: stats pass + epilogue correction
+        LR_TRY(add_ln_stats(h, M, C, lnst));
+        LR_TRY(add_linear(h, M, C, H(b.qkv_wf), 3 * C, F(b.qkv_bf), nullptr, 0, qkv, 3 * C, 0, lnst, F(b.qkv_s)));
+      } else {
+        LR_TRY(add_ln(h, M, C, F(b.ln1_g), F(b.ln1_b), t));
+        LR_TRY(add_linear(t, M, C, H(b.qkv_w), 3 * C, nullptr, nullptr, 0, qkv, 3 * C, 0));
+      }
       LR_CHECK(!(shared_ns > 0 && cfg.view_num > 1), "CFG-pair sharing is not implemented for the multiview UNet");
       if (cfg.view_num > 1 && cfg.concat_target) {
         // multiview_attention.py:436-462: rows are stitched [ref_i | target] canvases; attend over
@@ -677,10 +720,15 @@ struct lr_unet {
       }
       first_block = false;
       // cross-attention against the cached context K/V
-      LR_TRY(add_ln(h, M, C, F(b.ln2_g), F(b.ln2_b), t));
       __half* q2;
       LR_TRY(acquire_h(static_cast<size_t>(M) * C, &q2));
-      LR_TRY(add_linear(t, M, C, H(b.q2_w), C, nullptr, nullptr, 0, q2, C, 0));
+      if (ln_fold) {
+        LR_TRY(add_ln_stats(h, M, C, lnst));
+        LR_TRY(add_linear(h, M, C, H(b.q2_wf), C, F(b.q2_bf), nullptr, 0, q2, C, 0, lnst, F(b.q2_s)));
+      } else {
+        LR_TRY(add_ln(h, M, C, F(b.ln2_g), F(b.ln2_b), t));
+        LR_TRY(add_linear(t, M, C, H(b.q2_w), C, nullptr, nullptr, 0, q2, C, 0));
+      }
       {
         AttnSpec as;
         as.q = q2; as.ldq = C; as.q_col0 = 0;
@@ -694,14 +742,20 @@ struct lr_unet {
       pool.release(q2);
       LR_TRY(add_linear(a, M, C, H(b.out2_w), C, F(b.out2_b), h, C, h, C, 0));
       // GEGLU feed-forward
-      LR_TRY(add_ln(h, M, C, F(b.ln3_g), F(b.ln3_b), t));
       LR_TRY(acquire_h(static_cast<size_t>(M) * 4 * C, &g));
-      LR_TRY(add_linear(t, M, C, H(b.ff1_w), 8 * C, F(b.ff1_b), nullptr, 0, g, 4 * C, 1));
+      if (ln_fold) {
+        LR_TRY(add_ln_stats(h, M, C, lnst));
+        LR_TRY(add_linear(h, M, C, H(b.ff1_wf), 8 * C, F(b.ff1_bf), nullptr, 0, g, 4 * C, 1, lnst, F(b.ff1_s)));
+      } else {
+        LR_TRY(add_ln(h, M, C, F(b.ln3_g), F(b.ln3_b), t));
+        LR_TRY(add_linear(t, M, C, H(b.ff1_w), 8 * C, F(b.ff1_b), nullptr, 0, g, 4 * C, 1));
+      }
       LR_TRY(add_linear(g, M, 4 * C, H(b.ff2_w), C, F(b.ff2_b), h, C, h, C, 0));
       pool.release(g);
     }
     pool.release(t);
     pool.release(a);
+    pool.release(lnst);
     LR_TRY(acquire_h(static_cast<size_t>(M) * C, &o));
     LR_TRY(add_linear(h, M, C, H(s.pout_w), C, F(s.pout_b), x.p, C, o, C, 0));
     pool.release(h);
@@ -1038,6 +1092,7 @@ int lr_unet_set_weight(lr_unet* h, const char* name, const float* data, const in
       break;
   }
   w.loaded = true;
+  h->fold_dirty = true;  // LayerNorm-folded weight copies depend on norm{1,2,3} and their consuming Linears
   h->ctx_valid = false;  // cached K/V depend on attn2.to_k / to_v
   return 0;
 }
@@ -1062,6 +1117,7 @@ int lr_unet_forward(lr_unet* h, const float* x, const int64_t* timesteps, const 
   } else {
     LR_CHECK(h->ctx_valid && h->ctx_n == n, "lr_unet_forward: no cached context for this batch size");
   }
+  LR_TRY(h->run_folds(st));
   LR_TRY(h->build_plan(n, H, W));
   h->in_x = x;
   h->in_t = timesteps;
@@ -1139,6 +1195,7 @@ int lr_unet_forward_cfg_pair(lr_unet* h, const float* x, const int64_t* timestep
   LR_CHECK(h->ctx_valid && h->ctx_n == 2 * n_canvas,
            "lr_unet_forward_cfg_pair: lr_unet_set_context must have cached 2*n_canvas contexts (uncond first)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LR_TRY(h->run_folds(st));
   LR_TRY(h->build_plan(2 * n_canvas, H, W, 1));
   h->in_x = x;
   h->in_t = timesteps;

@@ -58,6 +58,12 @@ struct GemmParams {
                      // which is what made "+ residual" cost 17 us on the 65536 x 320 -> 320 linears.
   CUtensorMap tmR;   // residual [n_valid, W, H, N], box (64 cols, bw, bh, bn), 128B swizzle (same geometry as tmC)
   CUtensorMap tmR2;  // 32-column remainder slab, no swizzle (same geometry as tmC2)
+  // LayerNorm folded into this GEMM (attention.py:279-283: every LayerNorm feeds a Linear). The weight carries gamma
+  // (W' = W * gamma, fp16), `bias` carries b + W beta, and the epilogue finishes the normalisation per output row r:
+  //   out[r, j] = rstd_r * acc[r, j] - rstd_r * mean_r * ln_s[j] + bias[j],   ln_s[j] = sum_k W'[j, k]
+  // so the normalised activation tensor is never written or re-read; a stats-only pass produces (mean, rstd) per row.
+  const float2* ln_stats;  // [M] (mean, rstd) or nullptr
+  const float* ln_s;       // [ncols]
   int ksplit;        // split-K over the filter taps (1 = off, 3 = taps {0-2}, {3-5}, {6-8} as separate work units): for
                      // convs whose M is too small to fill the GPU. Units then write raw fp32 partial tiles to `partial`
                      // ([ksplit][M][ncols]) and splitk_reduce_kernel applies bias / residual and converts to fp16.
@@ -117,7 +123,7 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxAStages = 4;
 constexpr int kHaloBW = 8, kHaloBH = 16;  // halo-mode output tile: 8 pixels wide x 16 rows
 constexpr int kBarBytes = 512;
-constexpr int kGemmAuxBytes = kBarBytes /*barriers*/ + 2 * 256 * 4 /*bias staging, double buffered*/;
+constexpr int kGemmAuxBytes = kBarBytes /*barriers*/ + 4 * 256 * 4 /*bias + LayerNorm column-sum staging, double buffered*/;
 static_assert((2 * kMaxStages + 4 + 2 * kMaxAStages + 6) * 8 + 4 <= kBarBytes, "barrier block overflows");
 
 // bytes of one pipeline stage in ONE CTA (cg = CTAs cooperating on a tile: each holds block_n / cg weight rows)
@@ -170,6 +176,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   uint64_t* rfull = cfree + 2;               // [2] residual tile has landed in staging buffer b (res_tma)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);  // [2][256]
+  float* slns = sbias + 512;                                                               // [2][256] ln_s slice
 
   const int hw_warp = threadIdx.x >> 5;
 #if LR_HI_WARP_ISSUE
@@ -477,7 +484,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       const int col = (tile % p.tiles_n) * p.block_n + etid;
       return col < p.ncols ? __ldg(p.bias + col) : 0.f;
     };
+    auto fetch_lns = [&](int tile) -> float {
+      if (tile >= num_tiles || p.ln_stats == nullptr || etid >= p.block_n) return 0.f;
+      const int col = (tile % p.tiles_n) * p.block_n + etid;
+      return col < p.ncols ? __ldg(p.ln_s + col) : 0.f;
+    };
     float bias_next = fetch_bias(unit0 / p.ksplit);
+    float lns_next = fetch_lns(unit0 / p.ksplit);
     const size_t m_total = static_cast<size_t>(p.n_img) * p.H * p.W;
     // res_tma: (one thread) loads the residual tile of unit `un` into staging buffer `buf`
     auto issue_res = [&](int un, int buf) {
@@ -535,9 +548,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
 #endif
       // stage this tile's bias slice (double buffered by accumulator stage; the named barrier orders reuse)
       float* sb = sbias + as * 256;
-      if (etid < p.block_n) sb[etid] = bias_next;
+      float* sl = slns + as * 256;
+      if (etid < p.block_n) {
+        sb[etid] = bias_next;
+        sl[etid] = lns_next;
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       bias_next = fetch_bias((u + unit_step) < num_units ? (u + unit_step) / p.ksplit : num_tiles);
+      lns_next = fetch_lns((u + unit_step) < num_units ? (u + unit_step) / p.ksplit : num_tiles);
+      // folded LayerNorm: this thread's row statistics (they do not depend on the MMA either)
+      float ln_rstd = 1.f, ln_nrm = 0.f;
+      if (p.ln_stats != nullptr && row_ok) {
+        const float2 st = __ldg(p.ln_stats + grow);
+        ln_rstd = st.y;
+        ln_nrm = -st.x * st.y;
+      }
 
       // residual of the first chunk is fetched before the accumulator is ready (it does not depend on the MMA)
       const bool fast = vec_ok && row_ok && !p.geglu && !p.res_tma;
@@ -602,13 +627,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         }
         if (row_ok && col0 < p.ncols) {
           float f[32];
+          if (p.ln_stats != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sb + c + j);
-            f[j] = __uint_as_float(v[j]) + b4.x;
-            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sb + c + j);
+              const float4 s4 = *reinterpret_cast<const float4*>(sl + c + j);
+              f[j] = fmaf(ln_rstd, __uint_as_float(v[j]), fmaf(ln_nrm, s4.x, b4.x));
+              f[j + 1] = fmaf(ln_rstd, __uint_as_float(v[j + 1]), fmaf(ln_nrm, s4.y, b4.y));
+              f[j + 2] = fmaf(ln_rstd, __uint_as_float(v[j + 2]), fmaf(ln_nrm, s4.z, b4.z));
+              f[j + 3] = fmaf(ln_rstd, __uint_as_float(v[j + 3]), fmaf(ln_nrm, s4.w, b4.w));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sb + c + j);
+              f[j] = __uint_as_float(v[j]) + b4.x;
+              f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+              f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+              f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            }
           }
           if (p.bias_img != nullptr) {
             const float* bi = p.bias_img + static_cast<size_t>(n) * p.ld_bias_img + col0;

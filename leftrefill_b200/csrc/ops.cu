@@ -299,6 +299,10 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   p.cstage_off = (ring_bytes + kGemmAuxBytes + 1023) & ~1023;  // swizzle needs 1024 B
   p.cstage_bufs = bufs;
   p.cstage_bytes = cstage_bytes;
+  LR_CHECK(s.ln_stats == nullptr || (s.ln_s != nullptr && s.bias != nullptr && s.taps == 1 && ksplit == 1),
+           "conv: folded LayerNorm needs ln_s, a (folded) bias and a Linear geometry");
+  p.ln_stats = reinterpret_cast<const float2*>(s.ln_stats);
+  p.ln_s = s.ln_s;
   p.ksplit = ksplit;
   p.partial = ksplit > 1 ? s.workspace : nullptr;
   p.bias = ksplit > 1 ? nullptr : s.bias;  // split-K: bias / per-image bias / residual are applied by the reduction
@@ -539,7 +543,7 @@ int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_i
   return 0;
 }
 
-template <int VPL>
+template <int VPL, bool kStatsOnly>
 static int launch_ln_t(const __half* x, int M, int C, const float* gamma, const float* beta, float eps, __half* out,
                        cudaStream_t st) {
   const int tile_bytes = kLnTileRows * C * 2;
@@ -550,7 +554,8 @@ static int launch_ln_t(const __half* x, int M, int C, const float* gamma, const 
                       static_cast<size_t>(2) * stages * sizeof(uint64_t);
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    LR_CUDA(cudaFuncSetAttribute(layernorm_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LR_CUDA(cudaFuncSetAttribute(layernorm_kernel<VPL, kStatsOnly>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
     attr_set = true;
   }
   const int ntiles = cdiv(M, kLnTileRows);
@@ -559,27 +564,44 @@ static int launch_ln_t(const __half* x, int M, int C, const float* gamma, const 
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   int blocks = sm_count() * ctas_per_sm;
   if (blocks > ntiles) blocks = ntiles;
-  LR_CUDA(launch_pdl(layernorm_kernel<VPL>, dim3(blocks), dim3(kLnThreads), smem, st, 1, x, M, C, gamma, beta, eps, out,
-                     stages));
+  LR_CUDA(launch_pdl(layernorm_kernel<VPL, kStatsOnly>, dim3(blocks), dim3(kLnThreads), smem, st, 1, x, M, C, gamma, beta,
+                     eps, out, stages));
   LR_LAUNCHED();
   return 0;
 }
 
-int launch_layernorm(const __half* x, int M, int C, const float* gamma, const float* beta, float eps, __half* out,
-                     cudaStream_t st) {
+template <bool kStatsOnly>
+static int launch_ln_any(const __half* x, int M, int C, const float* gamma, const float* beta, float eps, __half* out,
+                         cudaStream_t st) {
   LR_CHECK(C % 8 == 0, "layernorm: C must be a multiple of 8");
   LR_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0, "layernorm: input must be 16-byte aligned");
   const int nvec = C / 8;
   const int vpl = cdiv(nvec, 32);
   switch (vpl) {
-    case 1: return launch_ln_t<1>(x, M, C, gamma, beta, eps, out, st);
-    case 2: return launch_ln_t<2>(x, M, C, gamma, beta, eps, out, st);
-    case 3: return launch_ln_t<3>(x, M, C, gamma, beta, eps, out, st);
-    case 4: return launch_ln_t<4>(x, M, C, gamma, beta, eps, out, st);
-    case 5: return launch_ln_t<5>(x, M, C, gamma, beta, eps, out, st);
-    case 6: case 7: case 8: return launch_ln_t<8>(x, M, C, gamma, beta, eps, out, st);
+    case 1: return launch_ln_t<1, kStatsOnly>(x, M, C, gamma, beta, eps, out, st);
+    case 2: return launch_ln_t<2, kStatsOnly>(x, M, C, gamma, beta, eps, out, st);
+    case 3: return launch_ln_t<3, kStatsOnly>(x, M, C, gamma, beta, eps, out, st);
+    case 4: return launch_ln_t<4, kStatsOnly>(x, M, C, gamma, beta, eps, out, st);
+    case 5: return launch_ln_t<5, kStatsOnly>(x, M, C, gamma, beta, eps, out, st);
+    case 6: case 7: case 8: return launch_ln_t<8, kStatsOnly>(x, M, C, gamma, beta, eps, out, st);
     default: LR_CHECK(false, "layernorm: C > 2048 unsupported");
   }
+  return 0;
+}
+
+int launch_layernorm(const __half* x, int M, int C, const float* gamma, const float* beta, float eps, __half* out,
+                     cudaStream_t st) {
+  return launch_ln_any<false>(x, M, C, gamma, beta, eps, out, st);
+}
+
+int launch_layernorm_stats(const __half* x, int M, int C, float eps, float* stats, cudaStream_t st) {
+  return launch_ln_any<true>(x, M, C, nullptr, nullptr, eps, reinterpret_cast<__half*>(stats), st);
+}
+
+int launch_ln_fold(const __half* w, int rows, int K, const float* gamma, const float* beta, const float* bias, __half* wf,
+                   float* s_out, float* bf_out, cudaStream_t st) {
+  ln_fold_kernel<<<cdiv(rows, 8), 256, 0, st>>>(w, rows, K, gamma, beta, bias, wf, s_out, bf_out);
+  LR_LAUNCHED();
   return 0;
 }
 

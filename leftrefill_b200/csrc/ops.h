@@ -53,6 +53,8 @@ struct ConvSpec {
   __half* out = nullptr;
   int ld_out = 0;
   int geglu = 0;
+  const float* ln_stats = nullptr;  // folded LayerNorm: [M] float2 (mean, rstd) of the input rows, or nullptr
+  const float* ln_s = nullptr;      //                   [ncols] column sums of the gamma-folded weight
   float* workspace = nullptr;  // optional split-K scratch (fp32 partial tiles), workspace_bytes >= 3 * M_out * ncols * 4
   size_t workspace_bytes = 0;
   int force_block_n = 0;  // testing hook: 0 = heuristic
@@ -103,6 +105,10 @@ int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_i
                      __half* out, cudaStream_t st);
 int launch_layernorm(const __half* x, int M, int C, const float* gamma, const float* beta, float eps, __half* out,
                      cudaStream_t st);
+// (mean, rstd) per row -> stats [M] float2; the normalisation itself is folded into the consuming GEMM
+int launch_layernorm_stats(const __half* x, int M, int C, float eps, float* stats, cudaStream_t st);
+int launch_ln_fold(const __half* w, int rows, int K, const float* gamma, const float* beta, const float* bias, __half* wf,
+                   float* s_out, float* bf_out, cudaStream_t st);
 int launch_im2col_nchw_f32(const float* x, int n_img, int cin, int H, int W, int kpad, __half* out, cudaStream_t st);
 int launch_upsample2x(const __half* x, int n_img, int H, int W, int C, __half* out, cudaStream_t st);
 int launch_mv_gather(const __half* src, int ld_src, int ncols, int b, int v, int hh, int side, __half* dst,
