@@ -488,6 +488,78 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_kernel(const __half* __r
   }
 }
 
+// Stats-only LayerNorm pass, read-only: (mean, rstd) per row -> stats[M]. One warp handles RPW rows per iteration with all
+// of their 16-byte loads issued up front (no shared memory, no stores besides 8 bytes per row): a plain grid-stride
+// kernel beats the TMA pipeline above here because nothing has to be written back.
+template <int VPL, int RPW>
+__global__ void __launch_bounds__(256) ln_stats_kernel(const __half* __restrict__ x, int M, int C, float eps,
+                                                       float2* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int nvec = C / 8;
+  const float inv_c = 1.0f / static_cast<float>(C);
+  const long long stride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5) * RPW;
+  for (long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW; row0 < M;
+       row0 += stride) {
+    uint4 raw[RPW][VPL];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int vi = lane + v * 32;
+        raw[r][v] = (row0 + r < M && vi < nvec) ? ldg16(x + static_cast<size_t>(row0 + r) * C + vi * 8)
+                                                : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    float mean[RPW], var[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      float acc = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        float f[8];
+        unpack8(raw[r][v], f);
+        acc += ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
+      }
+      mean[r] = acc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      mean[r] *= inv_c;
+      float q = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        if (lane + v * 32 < nvec) {
+          float f[8];
+          unpack8(raw[r][v], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = f[j] - mean[r];
+            q = fmaf(d, d, q);
+          }
+        }
+      }
+      var[r] = q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) var[r] += __shfl_xor_sync(0xffffffffu, var[r], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < RPW; ++r)
+        if (row0 + r < M) stats[row0 + r] = make_float2(mean[r], rsqrtf(var[r] * inv_c + eps));
+    }
+  }
+}
+
 // LayerNorm folding (run once per weight update): for a Linear W [rows, K] (fp16, GEMM layout) that consumes
 // LayerNorm(gamma, beta): Wf[j, k] = fp16(W[j, k] * gamma[k]), s[j] = sum_k Wf[j, k], bf[j] = bias[j] + sum_k W[j, k] beta[k].
 // One warp per output row.

@@ -594,8 +594,32 @@ int launch_layernorm(const __half* x, int M, int C, const float* gamma, const fl
   return launch_ln_any<false>(x, M, C, gamma, beta, eps, out, st);
 }
 
+template <int VPL, int RPW>
+static int launch_ln_stats_t(const __half* x, int M, int C, float eps, float* stats, cudaStream_t st) {
+  int blocks = cdiv(M, 8 * RPW);
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  LR_CUDA(launch_pdl(ln_stats_kernel<VPL, RPW>, dim3(blocks), dim3(256), 0, st, 1, x, M, C, eps,
+                     reinterpret_cast<float2*>(stats)));
+  LR_LAUNCHED();
+  return 0;
+}
+
 int launch_layernorm_stats(const __half* x, int M, int C, float eps, float* stats, cudaStream_t st) {
-  return launch_ln_any<true>(x, M, C, nullptr, nullptr, eps, reinterpret_cast<__half*>(stats), st);
+  static const bool tma_stats = getenv("LR_LN_STATS_TMA") != nullptr;  // A/B: the TMA-pipeline kernel in stats-only mode
+  if (tma_stats) return launch_ln_any<true>(x, M, C, nullptr, nullptr, eps, reinterpret_cast<__half*>(stats), st);
+  LR_CHECK(C % 8 == 0, "layernorm: C must be a multiple of 8");
+  LR_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0, "layernorm: input must be 16-byte aligned");
+  switch (cdiv(C / 8, 32)) {
+    case 1: return launch_ln_stats_t<1, 4>(x, M, C, eps, stats, st);
+    case 2: return launch_ln_stats_t<2, 4>(x, M, C, eps, stats, st);
+    case 3: return launch_ln_stats_t<3, 2>(x, M, C, eps, stats, st);
+    case 4: return launch_ln_stats_t<4, 2>(x, M, C, eps, stats, st);
+    case 5: return launch_ln_stats_t<5, 2>(x, M, C, eps, stats, st);
+    case 6: case 7: case 8: return launch_ln_stats_t<8, 1>(x, M, C, eps, stats, st);
+    default: LR_CHECK(false, "layernorm: C > 2048 unsupported");
+  }
+  return 0;
 }
 
 int launch_ln_fold(const __half* w, int rows, int K, const float* gamma, const float* beta, const float* bias, __half* wf,
