@@ -56,6 +56,24 @@ def test_unsupported_options_fail_loudly():
         leftrefill_b200.UNetModel(**dict(O.SMALL_CFG, use_spatial_transformer=False, context_dim=None))
 
 
+def test_nvs_unet_and_multi_sampling_surface():
+    """N4 rows of SURVEY §8f: NVSUnetModel (inpainting_ldm/NVS_ldm.py:22-104) is the plain UNet when use_sep is False;
+    use_sep=True / c_input raise instead of silently computing something else; DDIMSampler exposes
+    ddim_multi_sampling with the reference's keyword surface (ddim.py:146-158)."""
+    import inspect
+    m = leftrefill_b200.NVSUnetModel(**dict(O.SMALL_CFG, use_sep=False))
+    assert list(m.state_dict().keys()) == [n for n, _ in O.unet_spec(O.SMALL_CFG)]
+    with pytest.raises(NotImplementedError):
+        leftrefill_b200.NVSUnetModel(**dict(O.SMALL_CFG, use_sep=True))
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 9, 16, 32), torch.zeros(1, dtype=torch.long), context=torch.zeros(1, 77, 256),
+          c_input=torch.zeros(1, 64, 16, 32))
+    sig = inspect.signature(leftrefill_b200.DDIMSampler.ddim_multi_sampling)
+    for kw in ("cond", "shape", "x_T", "timesteps", "temperature", "noise_dropout", "unconditional_guidance_scale",
+               "unconditional_conditioning", "ucg_schedule", "mask", "x0", "callback", "img_callback"):
+        assert kw in sig.parameters, kw
+
+
 def test_no_cpu_fallback():
     m = leftrefill_b200.UNetModel(**O.SMALL_CFG)
     with pytest.raises(N.LRError):
