@@ -1100,6 +1100,9 @@ int lr_unet_set_weight(lr_unet* h, const char* name, const float* data, const in
 int lr_unet_set_context(lr_unet* h, const float* context, int n, int L, void* stream) {
   LR_CHECK(h && context, "lr_unet_set_context: null argument");
   LR_CHECK(lr_unet_missing_weights(h) == 0, "lr_unet_set_context: weights missing");
+  // A captured step graph replays lr_unet_forward* without passing through it: weight-derived state (the LayerNorm-folded
+  // copies) is therefore refreshed here as well, the one call the sampler makes before every loop.
+  LR_TRY(h->run_folds(static_cast<cudaStream_t>(stream)));
   return h->set_context(context, n, L, static_cast<cudaStream_t>(stream));
 }
 

@@ -230,6 +230,41 @@ def test_sampler_cuda_graph_equals_eager_loop(small, monkeypatch):
     assert not torch.equal(results[(1234, "graph")][0], results[(77, "graph")][0])
 
 
+def test_sampler_graph_sees_weight_updates(small, monkeypatch):
+    """Weights that change between two sample() calls (EMA swap, fine-tuning) must reach a replayed step graph, including
+    the LayerNorm-folded weight copies the engine derives from them."""
+    import leftrefill_b200 as lr
+    m, _ = small
+    dev = torch.device("cuda")
+    x_T, c_cat, ctx, uc = synthetic_inputs(1, h=16, w=32, ctx_dim=256, seed=5, device=dev)
+    cond = {"c_concat": [c_cat], "c_crossattn": [ctx]}
+    ucond = {"c_concat": [c_cat], "c_crossattn": [uc]}
+
+    def run():
+        s = lr.DDIMSampler(FakeLDM(m, dev))
+        y, _ = s.sample(4, 1, (4, 16, 32), cond, eta=0.0, x_T=x_T, verbose=False, unconditional_guidance_scale=2.5,
+                        unconditional_conditioning=ucond)
+        return y
+
+    monkeypatch.delenv("LR_NO_CUDA_GRAPH", raising=False)
+    y0 = run()
+    w = m.input_blocks[1][1].transformer_blocks[0].norm1.weight
+    old = w.detach().clone()
+    try:
+        with torch.no_grad():
+            w.mul_(1.5)
+        y_graph = run()                      # replays the cached graph
+        monkeypatch.setenv("LR_NO_CUDA_GRAPH", "1")
+        y_eager = run()
+    finally:
+        with torch.no_grad():
+            w.copy_(old)
+    assert not torch.allclose(y_graph, y0, rtol=1e-3, atol=1e-3), "the weight update did not reach the graph"
+    assert torch.equal(y_graph, y_eager)
+    monkeypatch.delenv("LR_NO_CUDA_GRAPH", raising=False)
+    assert torch.equal(run(), y0)            # restored weights -> original result
+
+
 def _cfg_pair_check(m, cfg, hw, nb):
     dev = "cuda"
     xT, c_cat, ctx, uc = synthetic_inputs(nb, h=hw[0], w=hw[1], ctx_dim=cfg["context_dim"], device=dev)
