@@ -615,26 +615,6 @@ __global__ void im2col_nchw_f32_kernel(const float* __restrict__ x, int n_img, i
   out[idx] = __float2half_rn(v);
 }
 
-// Generic NHWC fp16 im2col (fallback for channel counts that are not multiples of 8): out [M_out, kpad].
-__global__ void im2col_nhwc_kernel(const __half* __restrict__ x, int n_img, int C, int H, int W, int stride, int Ho,
-                                   int Wo, int kpad, __half* __restrict__ out) {
-  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t total = static_cast<size_t>(n_img) * Ho * Wo * kpad;
-  if (idx >= total) return;
-  const int k = static_cast<int>(idx % kpad);
-  const size_t m = idx / kpad;
-  const int xo = static_cast<int>(m % Wo);
-  const int yo = static_cast<int>((m / Wo) % Ho);
-  const int n = static_cast<int>(m / (static_cast<size_t>(Wo) * Ho));
-  __half v = __float2half_rn(0.f);
-  if (k < 9 * C) {
-    const int tap = k / C, c = k % C;
-    const int yy = yo * stride + tap / 3 - 1, xx = xo * stride + tap % 3 - 1;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x[((static_cast<size_t>(n) * H + yy) * W + xx) * C + c];
-  }
-  out[idx] = v;
-}
-
 // Upsample (openaimodel.py:108-116): F.interpolate(scale_factor=2, mode="nearest"), NHWC fp16, 8-channel vectors.
 __global__ void upsample2x_nhwc_kernel(const __half* __restrict__ x, int n_img, int H, int W, int C,
                                        __half* __restrict__ out) {

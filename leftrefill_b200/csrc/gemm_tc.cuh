@@ -130,9 +130,6 @@ static_assert((2 * kMaxStages + 4 + 2 * kMaxAStages + 6) * 8 + 4 <= kBarBytes, "
 __host__ __device__ inline int gemm_stage_bytes(int block_n, int cg = 1) {
   return kATileBytes + (block_n / cg) * kBlockK * 2;
 }
-__host__ inline int gemm_smem_bytes(int block_n, int stages, int cg = 1) {
-  return 1024 /*align slack*/ + stages * gemm_stage_bytes(block_n, cg) + kGemmAuxBytes;
-}
 
 // erf with |abs error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): one MUFU.RCP + one MUFU.EX2 + 8 FMA-pipe ops.
 // GELU here is the exact-erf form of F.gelu (attention.py:58); the output is rounded to fp16 (2^-11) afterwards.

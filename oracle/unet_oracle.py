@@ -360,3 +360,33 @@ def ddim_sample(sd, cfg, x_T, c_concat, context, uc_context, S, eta, cfg_scale, 
         x, _ = ddim_step(x, e_u, e_c, noises[i], cfg_scale, float(alphas[index]), float(alphas_prev[index]),
                          float(sigmas[index]))
     return x
+
+
+def ddim_multi_sample(sd, cfg, x_T, c_concat, context, uc_context, S, eta, cfg_scale, noises, rng):
+    """DDIMSampler.ddim_multi_sampling (ddim.py:146-222): `x_T`, `c_concat`, `context` are lists with one entry per
+    reference view, `noises` is the flat list of per-(step, view) noises in call order and `rng` a `random.Random` in the
+    state the reference's module-level `random` had (it picks the view whose target half is copied into all canvases
+    with `random.shuffle`, ddim.py:205-207). Returns the first canvas, like the reference."""
+    steps, alphas, alphas_prev, sigmas = make_schedule(S, eta, make_alphas_cumprod())
+    img = [x.clone() for x in x_T]
+    b = img[0].shape[0]
+    k = 0
+    for i, step in enumerate(np.flip(steps)):
+        index = len(steps) - i - 1
+        t = torch.full((2 * b,), int(step), dtype=torch.long)
+        rights, new_img = [], []
+        for v in range(len(img)):
+            xc = torch.cat([torch.cat([img[v]] * 2), torch.cat([c_concat[v]] * 2)], dim=1)
+            e = unet_forward(sd, cfg, xc, t, torch.cat([uc_context, context[v]]))
+            e_u, e_c = e.chunk(2)
+            x, _ = ddim_step(img[v], e_u, e_c, noises[k], cfg_scale, float(alphas[index]), float(alphas_prev[index]),
+                             float(sigmas[index]))
+            k += 1
+            rights.append(x[:, :, :, x.shape[-1] // 2:])
+            new_img.append(x)
+        rng.shuffle(rights)
+        right = rights[0].clone()
+        for x in new_img:
+            x[:, :, :, right.shape[-1]:] = right
+        img = new_img
+    return img[0]

@@ -74,3 +74,17 @@ def test_timestep_embedding_edge_cases():
     assert e.shape == (3, 320)
     assert torch.allclose(e[0, :160], torch.ones(160)) and torch.allclose(e[0, 160:], torch.zeros(160))
     assert O.timestep_embedding(torch.tensor([5]), 321).shape == (1, 321)  # odd dim gets a zero column
+
+
+def test_ddim_multi_sampling_vs_reference_golden(small_sd):
+    """List conditioning -> ddim_multi_sampling (ddim.py:104,146-222): two views, 4 steps, eta 1, cfg 2.5, the reference's
+    recorded noises and `random` seed (oracle/make_golden.py --only-multi)."""
+    import random
+    g = load_golden("ddim_multi_small.npz")
+    V, S = int(g["V"]), int(g["S"])
+    noises = [torch.tensor(n) for n in g["noises"]]
+    s = O.ddim_multi_sample(small_sd, O.SMALL_CFG, [torch.tensor(g[f"x_T{v}"]) for v in range(V)],
+                            [torch.tensor(g[f"c_concat{v}"]) for v in range(V)],
+                            [torch.tensor(g[f"context{v}"]) for v in range(V)], torch.tensor(g["uc_context"]), S, 1.0,
+                            2.5, noises, random.Random(int(g["random_seed"])))
+    _close(s.numpy(), g["samples"], tol=2e-4)
