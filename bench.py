@@ -246,11 +246,23 @@ def run_native(args):
     n_c = (ctypes.c_int * 5)()
     acc_ms, acc_fl, acc_n = [0.0] * 5, [0.0] * 5, [0] * 5
     prof_iters = 5
+    self_ms, self_fl = 0.0, 0.0  # self-attention only (tq == tk): the cross-attention launches are HBM-, not tensor-bound
     for i in range(prof_iters + 1):
         unet.forward_native(xc, tt, None)
         N.check(N.lib().lr_unet_read_profile(h, ms_c, fl_c, n_c), "read_profile")
         if i == 0:
             continue  # warm-up of the event pool
+        for k in range(N.lib().lr_unet_num_steps(h)):
+            ms_k, fl_k, cls_k = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+            buf = ctypes.create_string_buffer(256)
+            N.check(N.lib().lr_unet_step_info(h, k, ctypes.byref(ms_k), ctypes.byref(fl_k), ctypes.byref(cls_k), buf,
+                                              256), "step_info")
+            if cls_k.value == 1:
+                d = buf.value.decode()
+                tq, tk = [int(d.split(key + "=")[1].split()[0]) for key in ("tq", "tk")]
+                if tq == tk and ms_k.value > 0:
+                    self_ms += ms_k.value
+                    self_fl += fl_k.value
         for c in range(5):
             acc_ms[c] += ms_c[c]
             acc_fl[c] += fl_c[c]
@@ -277,6 +289,8 @@ def run_native(args):
                           "steps_per_forward": acc_n[c] // prof_iters} for c in range(5)}
     gemm_launches = acc_n[0]
     achieved = acc_fl[0] / acc_ms[0] / 1e9
+    sm_mhz = (clk or {}).get("sm_mhz") or 0
+    mufu_bound = 148 * 16 * sm_mhz * 1e6 * 256 / 1e12 if sm_mhz else None
     roofline = {"kernel": "gemm_conv_kernel (tcgen05 implicit-GEMM conv3x3 + linear, all launches of a UNet forward)",
                 "bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                 "frac": achieved / sustained, "traffic": _ncu_traffic(),
@@ -286,7 +300,14 @@ def run_native(args):
                 "flops_per_launch": acc_fl[0] / gemm_launches, "ms_per_launch": acc_ms[0] / gemm_launches,
                 "launches_timed": gemm_launches,
                 "attention_kernel": {"achieved": classes["attention_kernel"]["tflops"], "peak": sustained,
-                                     "frac": (classes["attention_kernel"]["tflops"] or 0) / sustained},
+                                     "frac": (classes["attention_kernel"]["tflops"] or 0) / sustained,
+                                     "self_attention_tflops": (self_fl / self_ms / 1e9) if self_ms > 0 else None,
+                                     "mufu_bound_tflops": mufu_bound,
+                                     "self_attention_frac_of_mufu_bound":
+                                         (self_fl / self_ms / 1e9 / mufu_bound) if self_ms > 0 and mufu_bound else None,
+                                     "note": "d_head = 64: every score costs 256 tensor FLOP and one ex2; the MUFU unit "
+                                             "issues 16 ex2/clk/SM, which caps the kernel at 148 SMs x 16 x clock x 256 "
+                                             "FLOP (clock = median SM clock sampled during the run)"},
                 "by_class": classes}
 
     cb = None
