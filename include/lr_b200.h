@@ -3,6 +3,10 @@
  * Plain pointers and sizes only; no torch / C++ types. All pointers are CUDA device pointers unless stated.
  * Every entry point returns 0 on success, non-zero on failure; lr_last_error() then gives the reason (thread local).
  * Calls are asynchronous on the `stream` argument (a cudaStream_t passed as void*); no hidden device synchronisation.
+ * Threading: one host thread per engine handle at a time (the reference drives its model from a single Python thread);
+ * process-wide lazy initialisation (kernel attributes, the op-level scratch buffer) is not synchronised, so make the
+ * first call of each entry point from one thread. The op-level entry points keep one scratch buffer per process and
+ * therefore serve one device per process; the engine (lr_unet_*) owns its memory per handle.
  * Citations are relative to the reference tree (ewrfcas/LeftRefill @ 893c3220).
  */
 #ifndef LR_B200_H_
