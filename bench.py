@@ -155,7 +155,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _ensure_built():
+    """liblr_b200.so is a build artefact (git-ignored, shipped with the gpurun snapshot): build it if this checkout does
+    not have it yet. The product path itself never falls back to anything when the library is missing."""
+    from leftrefill_b200 import build as b
+    if b.is_stale() and int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        b.build(force=True, verbose=False)
+
+
 def run_native(args):
+    _ensure_built()
     import torch
     import torch.distributed as dist
     from helpers import FakeLDM, O, synthetic_inputs
