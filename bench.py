@@ -159,8 +159,14 @@ def _ensure_built():
     """liblr_b200.so is a build artefact (git-ignored, shipped with the gpurun snapshot): build it if this checkout does
     not have it yet. The product path itself never falls back to anything when the library is missing."""
     from leftrefill_b200 import build as b
-    if b.is_stale() and int(os.environ.get("LOCAL_RANK", "0")) == 0:
+    if not b.is_stale():
+        return
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
         b.build(force=True, verbose=False)
+    else:  # another local rank is building: wait for it
+        t0 = time.time()
+        while b.is_stale() and time.time() - t0 < 300:
+            time.sleep(1.0)
 
 
 def run_native(args):
