@@ -3,10 +3,10 @@
  * Plain pointers and sizes only; no torch / C++ types. All pointers are CUDA device pointers unless stated.
  * Every entry point returns 0 on success, non-zero on failure; lr_last_error() then gives the reason (thread local).
  * Calls are asynchronous on the `stream` argument (a cudaStream_t passed as void*); no hidden device synchronisation.
- * Threading: one host thread per engine handle at a time (the reference drives its model from a single Python thread);
- * process-wide lazy initialisation (kernel attributes, the op-level scratch buffer) is not synchronised, so make the
- * first call of each entry point from one thread. The op-level entry points keep one scratch buffer per process and
- * therefore serve one device per process; the engine (lr_unet_*) owns its memory per handle.
+ * Threading: one host thread per engine handle at a time (the reference drives its model from a single Python thread).
+ * Per-device lazy initialisation (kernel attributes, SM count) is keyed by the CURRENT CUDA device and atomic; the
+ * op-level entry points keep one split-K scratch buffer per device (callers on one device use one stream at a time);
+ * the engine (lr_unet_* / lr_vae_*) owns its memory per handle and must be used with its device current.
  * Citations are relative to the reference tree (ewrfcas/LeftRefill @ 893c3220).
  */
 #ifndef LR_B200_H_
@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define LR_B200_ABI_VERSION 1
+#define LR_B200_ABI_VERSION 2
 
 /* ---- library ---------------------------------------------------------------------------------------------- */
 int lr_abi_version(void);
@@ -54,6 +54,10 @@ typedef struct lr_unet_cfg {
   /* multiview variant (ldm/modules/multiview_attention.py:431-468): self-attention runs over view_num views */
   int view_num;            /* 1 = plain UNetModel */
   int concat_target;       /* 0/1 (multiview only) */
+  /* NVSUnetModel (inpainting_ldm/NVS_ldm.py:22-31): 1 = a learned separator column `sep_token.<channels>` is inserted
+   * between the two halves of the stitched canvas before every non-resampling block and removed after it (:57-97);
+   * the weight table then ends with sep_token.{in_channels, ...} in the reference's order. */
+  int use_sep;
 } lr_unet_cfg;
 
 /* Host-only: builds the layer graph and the weight table. Device memory is allocated lazily. */
@@ -75,6 +79,12 @@ int lr_unet_missing_weights(const lr_unet* h);
 /* Cross-attention K/V of `context` [n, L, context_dim] fp32 are step-invariant (attention.py:170-171): compute them
  * once for all layers. lr_unet_forward with context == NULL reuses this cache. */
 int lr_unet_set_context(lr_unet* h, const float* context, int n, int L, void* stream);
+
+/* NVS input refinement (NVS_ldm.py:49,64-68): c_input [n, model_channels, H, Wc] fp32 NCHW is added to the output of
+ * the input conv of every following lr_unet_forward, over the whole feature width (Wc == Wh) or over its right part
+ * (Wc == Wh - Wh/2, columns from Wh/2 on), where Wh = W (+1 with use_sep) and W is the UNet input width. NULL clears it.
+ * The engine keeps its own fp16 copy: `c_input` may be released once `stream` has passed this call. */
+int lr_unet_set_c_input(lr_unet* h, const float* c_input, int n, int C, int H, int Wc, int W, void* stream);
 
 /* x [n, in_channels, H, W] fp32 NCHW, timesteps [n] int64, context [n, L, context_dim] fp32 or NULL (cached),
  * out [n, out_channels, H, W] fp32 NCHW. */

@@ -4,6 +4,8 @@ Public surface (mirrors the reference class surface):
     UNetModel, MultiViewUnetModel, NVSUnetModel, ResBlock, Upsample, Downsample, TimestepEmbedSequential   (openaimodel.py)
     CrossAttention, BasicTransformerBlock, SpatialTransformer, FeedForward, GEGLU            (attention.py)
     DDIMSampler                                                                              (ddim.py)
+    PromptContextCache, install_context_cache    memoised prompt contexts for the learned-prompt text encoders
+                                                 (Refill_modules.py:160-191)
     install()  -> makes `ldm.modules.diffusionmodules.openaimodel.UNetModel`, `ldm.modules.attention.CrossAttention`
                   and `ldm.models.diffusion.ddim.DDIMSampler` resolve to the classes above, so yaml `target:` strings
                   and `from ldm... import ...` lines of the reference drivers keep working unchanged.
@@ -20,6 +22,7 @@ _LAZY = {
     "CrossAttention": "attention", "MemoryEfficientCrossAttention": "attention", "BasicTransformerBlock": "attention",
     "SpatialTransformer": "attention", "FeedForward": "attention", "GEGLU": "attention",
     "DDIMSampler": "ddim",
+    "PromptContextCache": "context_cache", "install_context_cache": "context_cache",
 }
 
 

@@ -11,6 +11,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LR_B200_LIB") or os.path.join(_HERE, "liblr_b200.so")
 
 
+ABI_VERSION = 2  # LR_B200_ABI_VERSION of include/lr_b200.h
+
+
 class LRError(RuntimeError):
     pass
 
@@ -31,6 +34,7 @@ class UNetCfg(Structure):
         ("use_linear_in_transformer", c_int),
         ("view_num", c_int),
         ("concat_target", c_int),
+        ("use_sep", c_int),
     ]
 
 
@@ -50,6 +54,7 @@ SIGNATURES = {
     "lr_unet_set_weight": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int, c_void_p]),
     "lr_unet_missing_weights": (c_int, [c_void_p]),
     "lr_unet_set_context": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "lr_unet_set_c_input": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lr_unet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                 c_void_p]),
     "lr_unet_forward_cfg_pair": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -96,7 +101,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the ABI lost a symbol
             fn.restype = res
             fn.argtypes = args
-        if handle.lr_abi_version() != 1:
+        if handle.lr_abi_version() != ABI_VERSION:
             raise LRError("liblr_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -685,6 +685,81 @@ __global__ void mv_scatter_kernel(const __half* __restrict__ src, int ncols, int
       *reinterpret_cast<const uint4*>(src + srow * ncols + vec * 8);
 }
 
+// NVSUnetModel(use_sep=True) (inpainting_ldm/NVS_ldm.py:57-71,74-97): before every non-resampling block ONE learned
+// separator column sep[c] is inserted between the left (reference) and right (target) halves of the stitched canvas,
+// `cat([h[..., :W/2], sep, h[..., W/2:]], -1)`, and removed again after the block, `cat([h[..., :W/2], h[..., -W/2:]])`.
+// NHWC: in [n, H, W, C] -> out [n, H, W + 1, C]; sep points at this source's slice of the (concatenated) token.
+__global__ void sep_insert_nhwc_kernel(const __half* __restrict__ x, const float* __restrict__ sep, int n_img, int H,
+                                       int W, int C, __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int nvec = C / 8;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(n_img) * H * (W + 1) * nvec;
+  if (idx >= total) return;
+  const int v = static_cast<int>(idx % nvec);
+  const size_t m = idx / nvec;
+  const int xo = static_cast<int>(m % (W + 1));
+  const size_t ny = m / (W + 1);
+  uint4 val;
+  if (xo == W / 2) {
+    const float* sp = sep + v * 8;
+    val = make_uint4(pack_half2(sp[0], sp[1]), pack_half2(sp[2], sp[3]), pack_half2(sp[4], sp[5]), pack_half2(sp[6], sp[7]));
+  } else {
+    const int xi = xo < W / 2 ? xo : xo - 1;
+    val = *reinterpret_cast<const uint4*>(x + (ny * W + xi) * C + v * 8);
+  }
+  *reinterpret_cast<uint4*>(out + m * C + v * 8) = val;
+}
+// in [n, H, W1, C] -> out [n, H, W1 - 1, C]: drops column (W1 - 1) / 2
+__global__ void sep_remove_nhwc_kernel(const __half* __restrict__ x, int n_img, int H, int W1, int C,
+                                       __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int nvec = C / 8;
+  const int W = W1 - 1;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(n_img) * H * W * nvec;
+  if (idx >= total) return;
+  const int v = static_cast<int>(idx % nvec);
+  const size_t m = idx / nvec;
+  const int xo = static_cast<int>(m % W);
+  const size_t ny = m / W;
+  const int xi = xo < W / 2 ? xo : xo + 1;
+  *reinterpret_cast<uint4*>(out + m * C + v * 8) = *reinterpret_cast<const uint4*>(x + (ny * W1 + xi) * C + v * 8);
+}
+// the same insertion on the NCHW fp32 UNet input (in_channels = 9 is not a multiple of 8)
+__global__ void sep_insert_nchw_f32_kernel(const float* __restrict__ x, const float* __restrict__ sep, int n_img, int C,
+                                           int H, int W, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(n_img) * C * H * (W + 1);
+  if (idx >= total) return;
+  const int xo = static_cast<int>(idx % (W + 1));
+  const size_t ncy = idx / (W + 1);
+  const int c = static_cast<int>((ncy / H) % C);
+  out[idx] = (xo == W / 2) ? sep[c] : x[ncy * W + (xo < W / 2 ? xo : xo - 1)];
+}
+// NVS input refinement (NVS_ldm.py:64-68): c_input [n, C, H, Wc] fp32 NCHW is added to the output of the input conv,
+// either over the whole width or over the columns from x_off on. Staged as an NHWC fp16 [n, H, Wh, C] residual (zeros
+// outside [x_off, x_off + Wc)) that the input conv's epilogue adds.
+__global__ void cinput_nchw_to_nhwc_kernel(const float* __restrict__ x, int n_img, int C, int H, int Wc, int x_off,
+                                           int Wh, __half* __restrict__ out) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(n_img) * H * Wh * C;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C);
+  const size_t m = idx / C;
+  const int xo = static_cast<int>(m % Wh);
+  const int y = static_cast<int>((m / Wh) % H);
+  const int n = static_cast<int>(m / (static_cast<size_t>(Wh) * H));
+  const int xi = xo - x_off;
+  float v = 0.f;
+  if (xi >= 0 && xi < Wc) v = x[((static_cast<size_t>(n) * C + c) * H + y) * Wc + xi];
+  out[idx] = __float2half_rn(v);
+}
+
 // fp32 -> fp16 cast (context tokens)
 __global__ void cast_f32_f16_kernel(const float* __restrict__ x, size_t n, __half* __restrict__ out) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;

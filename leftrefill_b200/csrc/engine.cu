@@ -124,6 +124,13 @@ struct lr_unet {
   int emb_total = 0;            // sum of ResBlock out_channels
   size_t emb_w_base = 0, emb_b_base = 0;
   int n_gn_sites = 0;
+  // NVSUnetModel(use_sep=True): one learned separator token per channel count (NVS_ldm.py:24-31)
+  std::map<int, size_t> sep_w;
+  // NVS input refinement: c_input staged as an NHWC fp16 residual of the input conv (NVS_ldm.py:64-68)
+  __half* cin_h = nullptr;
+  int cin_n = 0, cin_H = 0, cin_Wh = 0;
+  bool cin_on = false;
+  int pcin = 0;  // planned with c_input
 
   // ---- plan state ----
   int pn = 0, ph = 0, pw = 0;  // planned shape
@@ -164,6 +171,7 @@ struct lr_unet {
     if (harena) cudaFree(harena);
     if (farena) cudaFree(farena);
     if (ctx_h) cudaFree(ctx_h);
+    if (cin_h) cudaFree(cin_h);
     for (auto p : kv)
       if (p) cudaFree(p);
   }
@@ -374,6 +382,27 @@ struct lr_unet {
     head_gn_b = reg_vec("out.0.bias", ch);
     LR_CHECK(ch == mc, "head channel mismatch");
     head_idx = add_conv("out.2.", mc, cfg.out_channels, 9 * mc);
+    if (cfg.use_sep) {
+      // channel counts that receive a separator, in order of first use: the inputs of every block that does not end
+      // in a Downsample / Upsample (for SD2: 9, 320, 640, 1280, 2560, 1920, 960 - the reference's hard-coded list)
+      std::vector<int> order;
+      auto want = [&](int c) {
+        if (std::find(order.begin(), order.end(), c) == order.end()) order.push_back(c);
+      };
+      auto in_ch = [&](const std::vector<Node>& blk) {
+        const Node& f = blk[0];
+        if (f.kind == N_CONV_IN) return cfg.in_channels;
+        if (f.kind == N_RES) return res[f.idx].cin;
+        return convs[f.idx].cin;
+      };
+      auto sep_block = [&](const std::vector<Node>& blk) { return blk.back().kind != N_DOWN && blk.back().kind != N_UP; };
+      for (const auto& blk : input_blocks)
+        if (sep_block(blk)) want(in_ch(blk));
+      want(in_ch(middle));
+      for (const auto& blk : output_blocks)
+        if (sep_block(blk)) want(in_ch(blk));
+      for (int c : order) sep_w[c] = reg_vec("sep_token." + std::to_string(c), c);
+    }
     emb_w_base = halloc(static_cast<size_t>(emb_total) * temb);
     emb_b_base = falloc(emb_total);
     for (Weight& w : weights) {
@@ -434,7 +463,7 @@ struct lr_unet {
       // split-K scratch for convs with few output pixels (the 8x16 level): plan-owned, recycled right after this step
       const int Ho = s.stride == 1 ? s.in_h : (s.in_h - 1) / 2 + 1, Wo = s.stride == 1 ? s.in_w : (s.in_w - 1) / 2 + 1;
       const size_t m_out = static_cast<size_t>(s.n_img) * Ho * Wo;
-      if (m_out <= 2048) {
+      if (Ho * Wo <= kSplitKMaxPixels) {
         const size_t bytes = 3 * m_out * s.ncols * sizeof(float);
         LR_TRY(pool.acquire(bytes, &ws));
         s.workspace = static_cast<float*>(ws);
@@ -827,13 +856,79 @@ struct lr_unet {
     return 0;
   }
 
+  // ---- NVSUnetModel(use_sep=True): separator column around every non-resampling block (NVS_ldm.py:57-97) ----
+  int plan_sep_insert(Act x, const float* sep, int n, Act* out) {
+    __half* o;
+    LR_TRY(acquire_h(static_cast<size_t>(n) * x.H * (x.W + 1) * x.C, &o));
+    const __half* src = x.p;
+    const int hh = x.H, ww = x.W, cc = x.C;
+    push([=](cudaStream_t st) { return launch_sep_insert(src, sep, n, hh, ww, cc, o, st); });
+    *out = Act{o, x.C, x.H, x.W + 1};
+    return 0;
+  }
+  int plan_sep_remove(Act x, int n, Act* out) {
+    __half* o;
+    LR_TRY(acquire_h(static_cast<size_t>(n) * x.H * (x.W - 1) * x.C, &o));
+    const __half* src = x.p;
+    const int hh = x.H, w1 = x.W, cc = x.C;
+    push([=](cudaStream_t st) { return launch_sep_remove(src, n, hh, w1, cc, o, st); });
+    *out = Act{o, x.C, x.H, x.W - 1};
+    return 0;
+  }
+  // plan_block with the separator inserted before and removed after when the block does not end in a resampling op
+  int plan_block_sep(const std::vector<Node>& blk, Act h, Act skip, int n, Act* out, bool release_input) {
+    const bool sep_blk = cfg.use_sep && blk.back().kind != N_DOWN && blk.back().kind != N_UP;
+    if (!sep_blk) return plan_block(blk, h, skip, n, out, release_input);
+    const int ctot = h.C + skip.C;
+    auto it = sep_w.find(ctot);
+    LR_CHECK(it != sep_w.end(), "use_sep: no separator token for " + std::to_string(ctot) + " channels");
+    Act hs_, ss_{};
+    LR_TRY(plan_sep_insert(h, F(it->second), n, &hs_));
+    if (skip.p != nullptr) LR_TRY(plan_sep_insert(skip, F(it->second) + h.C, n, &ss_));
+    if (release_input) pool.release(h.p);
+    if (skip.p != nullptr) pool.release(skip.p);
+    Act t;
+    LR_TRY(plan_block(blk, hs_, ss_, n, &t, true));  // releases the two widened copies
+    LR_TRY(plan_sep_remove(t, n, out));
+    pool.release(t.p);
+    return 0;
+  }
+
+  int set_c_input(const float* c_input, int n, int C, int Hh, int Wc, int Wh, cudaStream_t st) {
+    if (c_input == nullptr) {
+      if (cin_on) { cin_on = false; pn = 0; }
+      return 0;
+    }
+    LR_CHECK(C == cfg.model_channels, "c_input must have model_channels channels (it is added to the input conv's output)");
+    LR_CHECK(Wc == Wh || Wc == Wh - Wh / 2, "c_input width must equal the feature width or its right part (NVS_ldm.py:65-68)");
+    if (cin_h == nullptr || cin_n != n || cin_H != Hh || cin_Wh != Wh) {
+      if (cin_h) cudaFree(cin_h);
+      cin_h = nullptr;
+      cin_n = cin_H = cin_Wh = 0;
+      pn = 0;
+      ++plan_generation;
+      LR_CUDA(cudaMalloc(&cin_h, static_cast<size_t>(n) * Hh * Wh * C * sizeof(__half)));
+      cin_n = n; cin_H = Hh; cin_Wh = Wh;
+    }
+    LR_TRY(launch_cinput_to_nhwc(c_input, n, C, Hh, Wc, Wc == Wh ? 0 : Wh / 2, Wh, cin_h, st));
+    if (!cin_on) { cin_on = true; pn = 0; }
+    return 0;
+  }
+
   int build_kv_cache(int n, int L) {
     if (ctx_n == n && ctx_L == L && ctx_h != nullptr) return 0;
+    // The old buffers go away: every attention op of the current plan and every captured step graph points at them.
+    // Invalidate both BEFORE freeing (a failed allocation below must not leave a state that looks valid).
     if (ctx_h) cudaFree(ctx_h);
+    ctx_h = nullptr;
     for (auto p : kv)
       if (p) cudaFree(p);
     kv.assign(n_kv_slots, nullptr);
     kv_ops.clear();
+    ctx_n = ctx_L = 0;
+    ctx_valid = false;
+    pn = 0;             // attention ops hold kv pointers: force a re-plan
+    ++plan_generation;  // DDIMSampler's cached step graphs compare this counter (ddim.py _StepGraph.valid)
     const size_t rows = static_cast<size_t>(n) * L;
     LR_CUDA(cudaMalloc(&ctx_h, rows * cfg.context_dim * sizeof(__half)));
     for (int i = 0; i < n_kv_slots; ++i) LR_CUDA(cudaMalloc(&kv[i], rows * 2 * kv_C[i] * sizeof(__half)));
@@ -858,10 +953,8 @@ struct lr_unet {
         kv_ops.push_back(std::move(op));
       }
     }
-    ctx_n = n;
+    ctx_n = n;  // committed only after every allocation succeeded
     ctx_L = L;
-    ctx_valid = false;
-    pn = 0;  // attention ops hold kv pointers: force a re-plan
     return 0;
   }
 
@@ -875,8 +968,11 @@ struct lr_unet {
   }
 
   int build_plan(int n, int Hh, int Ww, int shared = 0) {
-    if (pn == n && ph == Hh && pw == Ww && pshared == shared) return 0;
+    if (pn == n && ph == Hh && pw == Ww && pshared == shared && pcin == (cin_on ? 1 : 0)) return 0;
     LR_CHECK(!shared || n % 2 == 0, "CFG-pair forward needs an even UNet batch");
+    LR_CHECK(!(shared && (cfg.use_sep || cin_on)), "CFG-pair sharing is not implemented with use_sep / c_input");
+    const int Wh = Ww + (cfg.use_sep ? 1 : 0);  // width seen by the input conv (separator column inserted)
+    LR_CHECK(!cin_on || (cin_n == n && cin_H == Hh && cin_Wh == Wh), "c_input was staged for another batch / latent shape");
     const int ns = shared ? n / 2 : n;  // images whose x / t are distinct
     steps.clear();
     conv_ops.clear();
@@ -928,20 +1024,39 @@ struct lr_unet {
     // --- input conv: im2col of the NCHW fp32 boundary tensor, then a GEMM ---
     const size_t M0 = static_cast<size_t>(n) * Hh * Ww;
     const size_t M0s = static_cast<size_t>(ns) * Hh * Ww;  // rows computed by the input conv (x is [ns, ...])
+    const size_t M0h = static_cast<size_t>(n) * Hh * Wh, M0hs = static_cast<size_t>(ns) * Hh * Wh;  // with the separator
     __half* col;
-    LR_TRY(acquire_h(M0s * kpad_in, &col));
+    LR_TRY(acquire_h(M0hs * kpad_in, &col));
     {
       const int cin = cfg.in_channels, kp = kpad_in;
-      push(
-          [=](cudaStream_t st) { return launch_im2col_nchw_f32(this->in_x, ns, cin, Hh, Ww, kp, col, st); });
+      if (cfg.use_sep) {
+        float* xsep;
+        LR_TRY(acquire_f(static_cast<size_t>(ns) * cin * Hh * Wh, &xsep));
+        auto it = sep_w.find(cin);
+        LR_CHECK(it != sep_w.end(), "use_sep: no separator token for the input channels");
+        const float* sp = F(it->second);
+        push([=](cudaStream_t st) { return launch_sep_insert_nchw_f32(this->in_x, sp, ns, cin, Hh, Ww, xsep, st); });
+        push([=](cudaStream_t st) { return launch_im2col_nchw_f32(xsep, ns, cin, Hh, Wh, kp, col, st); });
+        pool.release(xsep);
+      } else {
+        push(
+            [=](cudaStream_t st) { return launch_im2col_nchw_f32(this->in_x, ns, cin, Hh, Ww, kp, col, st); });
+      }
     }
     Act h;
     {
       __half* o;
-      LR_TRY(acquire_h(M0 * mc, &o));
+      LR_TRY(acquire_h(M0h * mc, &o));
       const ConvW& c = convs[conv_in_idx];
-      LR_TRY(add_linear(col, static_cast<int>(M0s), kpad_in, H(c.w), mc, F(c.b), nullptr, 0, o, mc, 0));
-      h = Act{o, mc, Hh, Ww};
+      // c_input (NVS_ldm.py:64-68) is added to the input conv's output BEFORE the separator is removed
+      LR_TRY(add_linear(col, static_cast<int>(M0hs), kpad_in, H(c.w), mc, F(c.b), cin_on ? cin_h : nullptr, mc, o, mc, 0));
+      h = Act{o, mc, Hh, Wh};
+      if (cfg.use_sep) {
+        Act t;
+        LR_TRY(plan_sep_remove(h, n, &t));
+        pool.release(h.p);
+        h = t;
+      }
     }
     pool.release(col);
     std::vector<Act> hs{h};
@@ -961,14 +1076,14 @@ struct lr_unet {
         }
         add_dup_half(hs[0].p, M0s * mc);  // conv_in output: also a skip connection for both halves
       } else {
-        LR_TRY(plan_block(input_blocks[i], h, Act{}, n, &o, false));
+        LR_TRY(plan_block_sep(input_blocks[i], h, Act{}, n, &o, false));
       }
       hs.push_back(o);
       h = o;
     }
     {
       Act o;
-      LR_TRY(plan_block(middle, h, Act{}, n, &o, false));
+      LR_TRY(plan_block_sep(middle, h, Act{}, n, &o, false));
       h = o;
     }
     for (size_t i = 0; i < output_blocks.size(); ++i) {
@@ -977,7 +1092,7 @@ struct lr_unet {
       LR_CHECK(skip.H == h.H && skip.W == h.W, "skip connection spatial mismatch (H, W must be divisible by 2^levels)");
       Act o;
       // h is a temporary except right after the middle block when it still aliases nothing in hs
-      LR_TRY(plan_block(output_blocks[i], h, skip, n, &o, true));
+      LR_TRY(plan_block_sep(output_blocks[i], h, skip, n, &o, true));
       h = o;
     }
     // --- head: GroupNorm32 -> SiLU -> conv3x3 (openaimodel.py:727-731,787) ---
@@ -1010,6 +1125,7 @@ struct lr_unet {
     ph = Hh;
     pw = Ww;
     pshared = shared;
+    pcin = cin_on ? 1 : 0;
     ++plan_generation;
     return 0;
   }
@@ -1104,6 +1220,14 @@ int lr_unet_set_context(lr_unet* h, const float* context, int n, int L, void* st
   // copies) is therefore refreshed here as well, the one call the sampler makes before every loop.
   LR_TRY(h->run_folds(static_cast<cudaStream_t>(stream)));
   return h->set_context(context, n, L, static_cast<cudaStream_t>(stream));
+}
+
+int lr_unet_set_c_input(lr_unet* h, const float* c_input, int n, int C, int H, int Wc, int W, void* stream) {
+  LR_CHECK(h != nullptr, "lr_unet_set_c_input: null handle");
+  LR_CHECK(c_input == nullptr || (n > 0 && C > 0 && H > 0 && Wc > 0 && W > 0), "lr_unet_set_c_input: empty input");
+  // feature width at the point of the addition: the input conv runs on the separator-widened canvas when use_sep
+  const int Wh = W + (h->cfg.use_sep ? 1 : 0);
+  return h->set_c_input(c_input, n, C, H, Wc, Wh, static_cast<cudaStream_t>(stream));
 }
 
 int lr_unet_forward(lr_unet* h, const float* x, const int64_t* timesteps, const float* context, int L, float* out,
@@ -1291,7 +1415,7 @@ int lr_conv3x3_f16(const void* x0, int c0, const void* x1, int c1, int n, int h,
   {
     const int Ho = stride == 1 ? h : (h - 1) / 2 + 1, Wo = stride == 1 ? w : (w - 1) / 2 + 1;
     const size_t m_out = static_cast<size_t>(n) * Ho * Wo;
-    if (m_out <= 2048) {
+    if (Ho * Wo <= kSplitKMaxPixels) {
       s.workspace_bytes = 3 * m_out * cout * sizeof(float);
       s.workspace = op_level_workspace(s.workspace_bytes);
       if (s.workspace == nullptr) s.workspace_bytes = 0;

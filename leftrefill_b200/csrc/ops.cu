@@ -123,15 +123,30 @@ int debug_read_trace(void* dst, size_t bytes, int clear) {
   return 0;
 }
 
+// Per-device caches (a process may drive several GPUs: cudaFuncSetAttribute and the SM count are per device).
+constexpr int kMaxDevices = 64;
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = current_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
+}
+// true exactly once per (device, slot): the caller then sets its per-device function attributes
+static bool first_use_on_device(int slot) {
+  static std::atomic<unsigned> done[kMaxDevices];
+  const int dev = current_device();
+  const unsigned bit = 1u << slot;
+  return (done[dev].fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -202,16 +217,18 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   // (128 + block_n / cg) rows, when that exceeds what the SM can ingest while the MMAs run.
   int block_n = s.force_block_n, cg = s.force_cg, ksplit = 1;
   {
-    // split-K over the nine taps (3 work units per output tile + a reduction pass) for convs whose M cannot fill the
-    // GPU with full-width tiles: needs scratch for the fp32 partial tiles
+    // split-K over the nine taps (3 work units per output tile + a reduction pass) for convs whose images are too
+    // small for a halo tile (<= 256 output pixels per image: the 8x16 level): needs scratch for the fp32 partial tiles.
+    // The decision depends on the per-image geometry ONLY, never on the batch size: split-K changes the summation
+    // order, and results must not depend on how a batch is sharded over GPUs (tests/test_multigpu.py).
     const size_t m_out = static_cast<size_t>(s.n_img) * Ho * Wo;
     static const bool splitk_enabled = getenv("LR_NO_SPLITK") == nullptr;
-    const bool can_split = splitk_enabled && s.taps == 9 && !halo && !s.geglu && s.workspace != nullptr &&
-                           s.workspace_bytes >= 3 * m_out * s.ncols * sizeof(float) && s.ncols % 8 == 0 &&
-                           s.ld_out % 8 == 0 && (s.residual == nullptr || s.ld_res % 8 == 0);
+    const bool can_split = splitk_enabled && s.taps == 9 && !halo && !s.geglu && Ho * Wo <= kSplitKMaxPixels &&
+                           s.workspace != nullptr && s.workspace_bytes >= 3 * m_out * s.ncols * sizeof(float) &&
+                           s.ncols % 8 == 0 && s.ld_out % 8 == 0 && (s.residual == nullptr || s.ld_res % 8 == 0);
     double best = 1e300;
     int best_bn = 0, best_cg = 0, best_ks = 1;
-    for (int ks = 1; ks <= (can_split ? 3 : 1); ks += 2) {
+    for (int ks = (can_split ? 3 : 1); ks <= (can_split ? 3 : 1); ks += 2) {
       for (int c = 1; c <= 2; ++c) {
         if (s.force_cg && c != s.force_cg) continue;
         if (c == 2 && tiles_m < 2) continue;
@@ -399,11 +416,9 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   op->cg = cg;
   op->flops = 2.0 * s.n_img * Ho * Wo * static_cast<double>(s.ncols) * s.taps * (s.c0 + s.c1);
   memcpy(op->params, &p, sizeof(p));
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(0)) {
     LR_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     LR_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
   }
   return 0;
 }
@@ -426,14 +441,23 @@ int launch_conv_op(const ConvOp& op, cudaStream_t st) {
   return 0;
 }
 
-// Scratch for the op-level entry points (lr_conv3x3_f16): grown on demand, never shrunk, one per process. The engine
+// Scratch for the op-level entry points (lr_conv3x3_f16): grown on demand, never shrunk, one per device (op-level calls
+// on one device are expected to be issued from one stream at a time: the engine never uses this). The engine
 // passes plan-owned scratch instead.
 float* op_level_workspace(size_t bytes) {
-  static float* ws = nullptr;
-  static size_t ws_bytes = 0;
-  if (bytes > (size_t(64) << 20)) return nullptr;
+  static float* ws_[kMaxDevices];
+  static size_t ws_bytes_[kMaxDevices];
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  const int dev = current_device();
+  float*& ws = ws_[dev];
+  size_t& ws_bytes = ws_bytes_[dev];
+  if (bytes > (size_t(512) << 20)) return nullptr;
   if (bytes > ws_bytes) {
-    if (ws) cudaFree(ws);
+    if (ws) {
+      cudaDeviceSynchronize();  // an earlier op on another stream may still be using the old block
+      cudaFree(ws);
+    }
     ws = nullptr;
     ws_bytes = 0;
     if (cudaMalloc(&ws, bytes) != cudaSuccess) return nullptr;
@@ -476,11 +500,9 @@ int build_attn_op(AttnOp* op, const AttnSpec& s) {
   op->grid = dim3(cdiv(s.tq, kAttnQBlock), s.heads, s.batch);
   op->flops = 4.0 * s.batch * s.heads * static_cast<double>(s.tq) * s.tk * kAttnD;
   memcpy(op->params, &p, sizeof(p));
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(1)) {
     LR_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
     LR_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
-    attr_set = true;
   }
   return 0;
 }
@@ -552,11 +574,10 @@ static int launch_ln_t(const __half* x, int M, int C, const float* gamma, const 
   if (stages < 2) stages = 2;
   const size_t smem = static_cast<size_t>(stages) * tile_bytes + static_cast<size_t>(2) * C * sizeof(float) +
                       static_cast<size_t>(2) * stages * sizeof(uint64_t);
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  // per instantiation and device (slots 2..17)
+  if (first_use_on_device(2 + (VPL - 1) * 2 + (kStatsOnly ? 1 : 0))) {
     LR_CUDA(cudaFuncSetAttribute(layernorm_kernel<VPL, kStatsOnly>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  200 * 1024));
-    attr_set = true;
   }
   const int ntiles = cdiv(M, kLnTileRows);
   int ctas_per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
@@ -658,6 +679,38 @@ int launch_mv_scatter(const __half* src, int ncols, int b, int v, int hh, int si
   const size_t total = static_cast<size_t>(b) * v * hh * 2 * side * (ncols / 8);
   LR_CUDA(launch_pdl(mv_scatter_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, 1, src, ncols,
                      b, v, hh, side, dst));
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_sep_insert(const __half* x, const float* sep, int n_img, int H, int W, int C, __half* out, cudaStream_t st) {
+  LR_CHECK(C % 8 == 0, "sep_insert: C must be a multiple of 8");
+  const size_t total = static_cast<size_t>(n_img) * H * (W + 1) * (C / 8);
+  LR_CUDA(launch_pdl(sep_insert_nhwc_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, 1, x, sep,
+                     n_img, H, W, C, out));
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_sep_remove(const __half* x, int n_img, int H, int W1, int C, __half* out, cudaStream_t st) {
+  LR_CHECK(C % 8 == 0, "sep_remove: C must be a multiple of 8");
+  const size_t total = static_cast<size_t>(n_img) * H * (W1 - 1) * (C / 8);
+  LR_CUDA(launch_pdl(sep_remove_nhwc_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, 1, x,
+                     n_img, H, W1, C, out));
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_sep_insert_nchw_f32(const float* x, const float* sep, int n_img, int C, int H, int W, float* out,
+                               cudaStream_t st) {
+  const size_t total = static_cast<size_t>(n_img) * C * H * (W + 1);
+  LR_CUDA(launch_pdl(sep_insert_nchw_f32_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, 1, x,
+                     sep, n_img, C, H, W, out));
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_cinput_to_nhwc(const float* x, int n_img, int C, int H, int Wc, int x_off, int Wh, __half* out,
+                          cudaStream_t st) {
+  const size_t total = static_cast<size_t>(n_img) * H * Wh * C;
+  cinput_nchw_to_nhwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, n_img, C, H, Wc, x_off, Wh,
+                                                                                          out);
   LR_LAUNCHED();
   return 0;
 }

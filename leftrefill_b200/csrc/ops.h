@@ -75,6 +75,8 @@ struct ConvOp {
   __half* out = nullptr;
   double flops = 0;
 };
+// 3x3 convs with at most this many OUTPUT pixels per image run split-K over the taps when scratch is provided
+constexpr int kSplitKMaxPixels = 256;
 int build_conv_op(ConvOp* op, const ConvSpec& s);
 int launch_conv_op(const ConvOp& op, cudaStream_t st);
 float* op_level_workspace(size_t bytes);
@@ -114,6 +116,13 @@ int launch_upsample2x(const __half* x, int n_img, int H, int W, int C, __half* o
 int launch_mv_gather(const __half* src, int ld_src, int ncols, int b, int v, int hh, int side, __half* dst,
                      cudaStream_t st);
 int launch_mv_scatter(const __half* src, int ncols, int b, int v, int hh, int side, __half* dst, cudaStream_t st);
+// NVSUnetModel(use_sep=True) separator column (NVS_ldm.py:57-71) and c_input staging (:64-68)
+int launch_sep_insert(const __half* x, const float* sep, int n_img, int H, int W, int C, __half* out, cudaStream_t st);
+int launch_sep_remove(const __half* x, int n_img, int H, int W1, int C, __half* out, cudaStream_t st);
+int launch_sep_insert_nchw_f32(const float* x, const float* sep, int n_img, int C, int H, int W, float* out,
+                               cudaStream_t st);
+int launch_cinput_to_nhwc(const float* x, int n_img, int C, int H, int Wc, int x_off, int Wh, __half* out,
+                          cudaStream_t st);
 int launch_cast_f32_f16(const float* x, size_t n, __half* out, cudaStream_t st);
 int launch_nhwc_to_nchw_f32(const __half* x, int ld, int n_img, int cout, int H, int W, float* out, cudaStream_t st);
 int launch_nchw_f32_to_nhwc(const float* x, int n_img, int C, int H, int W, __half* out, cudaStream_t st);

@@ -72,18 +72,20 @@ class _StepGraph:
         self.noise = torch.zeros_like(self.x)
         self.pred_x0 = torch.zeros_like(self.x)
         self.graph = None
+        self.device = device
         # eager warm-up on a side stream: builds the engine's plan (device allocations are illegal during capture)
-        side = torch.cuda.Stream(device=device)
-        side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side):
-            self._body()
-        torch.cuda.current_stream(device).wait_stream(side)
-        torch.cuda.synchronize(device)
-        self.generation = N.lib().lr_unet_plan_generation(unet.engine())
-        graph = torch.cuda.CUDAGraph()
-        before = N.lib().lr_launch_count()
-        with torch.cuda.graph(graph):
-            self._body()
+        with torch.cuda.device(device):
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                self._body()
+            torch.cuda.current_stream(device).wait_stream(side)
+            torch.cuda.synchronize(device)
+            self.generation = N.lib().lr_unet_plan_generation(unet.engine())
+            graph = torch.cuda.CUDAGraph()
+            before = N.lib().lr_launch_count()
+            with torch.cuda.graph(graph):
+                self._body()
         self.kernels = N.lib().lr_launch_count() - before  # native kernel nodes of one replay
         N.lib().lr_launch_count_add(-self.kernels)          # the capture itself executed nothing
         self.graph = graph
@@ -189,6 +191,8 @@ class DDIMSampler(object):
         unet = getattr(wrapper, "diffusion_model", None)
         if not isinstance(unet, UNetModel) or getattr(wrapper, "conditioning_key", None) != "hybrid":
             return None
+        if type(unet).forward is not UNetModel.forward:
+            return None  # a subclass overrides forward (e.g. the reference NVSUnetModel after install()): honour it
         if getattr(self.model, "parameterization", "eps") != "eps":
             return None
 
@@ -288,18 +292,21 @@ class DDIMSampler(object):
                 c_cat = torch.cat([unconditional_conditioning["c_concat"][0].float(), c_cat])
             # both CFG halves see the same x, t and (in every LeftRefill driver) the same c_concat: then everything
             # before the first cross-attention is computed once (lr_unet_forward_cfg_pair)
-            pair = (use_cfg and unet.view_num == 1 and
+            pair = (use_cfg and unet.view_num == 1 and not unet.use_sep and
                     torch.equal(unconditional_conditioning["c_concat"][0], cond["c_concat"][0]))
             if pair:
                 c_cat = cond["c_concat"][0].float()
             nb = c_cat.shape[0]
+            if getattr(unet, "_cin_active", False):  # a c_input staged by an earlier forward(c_input=...) call
+                unet.set_c_input(None, shape[3])
+                unet._cin_active = False
             unet.set_context(cc)
             xc = torch.empty(nb, img.shape[1] + c_cat.shape[1], shape[2], shape[3], dtype=torch.float32, device=device)
             xc[:, img.shape[1]:] = c_cat
             staged = (xc, nb, pair)
             if noise_dropout == 0. and os.environ.get("LR_NO_CUDA_GRAPH") is None and torch.cuda.is_available():
                 sg = self._step_graph(unet, nb, b, img.shape[1], xc.shape[1], shape[2], shape[3], pair, use_cfg,
-                                      temperature, device)
+                                      temperature, device, cc.shape[1])
                 if sg is not None:
                     return self._graphed_loop(sg, img, c_cat, time_range, total_steps, mask, x0, callback,
                                               img_callback, log_every_t, unconditional_guidance_scale, intermediates)
@@ -339,9 +346,12 @@ class DDIMSampler(object):
         return x, intermediates
 
     # ------------------------------------------------------------------------------------------------------------
-    def _step_graph(self, unet, nb, b, cx, c_total, H, W, pair, use_cfg, temperature, device):
-        """Returns the cached (or freshly captured) step graph for this configuration, None if capture is unavailable."""
-        key = (nb, b, cx, c_total, H, W, bool(pair), bool(use_cfg), float(temperature), str(device))
+    def _step_graph(self, unet, nb, b, cx, c_total, H, W, pair, use_cfg, temperature, device, ctx_len=0):
+        """Returns the cached (or freshly captured) step graph for this configuration, None if capture is unavailable.
+        The context length is part of the key: the cached cross-attention K/V buffers (and the attention launch
+        geometry baked into the graph) depend on it; the engine also bumps its plan generation when they are
+        reallocated, which `_StepGraph.valid` checks."""
+        key = (nb, b, cx, c_total, H, W, bool(pair), bool(use_cfg), float(temperature), str(device), int(ctx_len))
         cache = unet.__dict__.setdefault("_step_graphs", {})
         sg = cache.get(key)
         if sg is not None and sg is not False and sg.valid():

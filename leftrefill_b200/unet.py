@@ -143,11 +143,14 @@ class UNetModel(nn.Module):
                  use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=False,
                  use_spatial_transformer=False, transformer_depth=1, context_dim=None, n_embed=None, legacy=True,
                  disable_self_attentions=None, num_attention_blocks=None, disable_middle_self_attn=False,
-                 use_linear_in_transformer=False, view_num=1, concat_target=False, **unused):
+                 use_linear_in_transformer=False, view_num=1, concat_target=False, use_sep=False, **unused):
         super().__init__()
-        if unused.get("use_sep"):
-            raise NotImplementedError("NVSUnetModel(use_sep=True) (separator columns, inpainting_ldm/NVS_ldm.py:24-31) is "
-                                      "not implemented; the shipped novel_view_synthesis.yaml sets use_sep: False")
+        # Options this implementation does not know must not be dropped silently: a truthy unknown kwarg changes what the
+        # reference computes (e.g. MultiViewUnetModel's no_rearrange_selfattn, multiview_attention.py:437).
+        noop = {"adm_in_channels", "num_attention_blocks", "use_bf16"}
+        bad_kw = [k for k, v in unused.items() if k not in noop and v not in (None, False, 0)]
+        if bad_kw:
+            raise NotImplementedError(f"UNetModel options not implemented (they would change the result): {bad_kw}")
         if not use_spatial_transformer or context_dim is None:
             raise NotImplementedError("only the SpatialTransformer UNet (use_spatial_transformer=True with a "
                                       "context_dim) used by every LeftRefill config is implemented")
@@ -180,6 +183,9 @@ class UNetModel(nn.Module):
         self.predict_codebook_ids = False
         self.context_dim, self.use_linear_in_transformer = context_dim, use_linear_in_transformer
         self.view_num, self.concat_target = int(view_num), bool(concat_target)
+        self.use_sep = bool(use_sep)
+        if self.use_sep and self.view_num > 1:
+            raise NotImplementedError("use_sep is an NVSUnetModel option; it is not combined with the multiview UNet")
 
         mc, temb = model_channels, model_channels * 4
 
@@ -229,8 +235,48 @@ class UNetModel(nn.Module):
                 self.output_blocks.append(TimestepEmbedSequential(*layers))
         self.out = nn.Sequential(normalization(ch), nn.SiLU(),
                                  zero_module(nn.Conv2d(mc, out_channels, 3, padding=1)))
+        if self.use_sep:
+            # NVS_ldm.py:24-31: one learned separator token per channel count that enters a non-resampling block. The
+            # reference hard-codes [9, 320, 640, 1280, 2560, 1920, 960] (model_channels 320); the same walk for any config:
+            self.sep_token = nn.ParameterDict({str(c): nn.Parameter(torch.randn(c)) for c in self._sep_channels()})
+        else:
+            self.sep_token = None
         self._engine = None
         self._synced = {}
+
+    def _sep_channels(self):
+        order = []
+
+        def first_in(block):
+            m = block[0]
+            if isinstance(m, nn.Conv2d):
+                return m.in_channels
+            return m.channels
+
+        def sep_block(block):
+            return not isinstance(block[-1], (Downsample, Upsample))
+
+        for blk in list(self.input_blocks) + [self.middle_block] + list(self.output_blocks):
+            if sep_block(blk) and first_in(blk) not in order:
+                order.append(first_in(blk))
+        return order
+
+    # engine handles are ctypes pointers: never copied or pickled with the module (the copy re-creates its own lazily)
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_engine"], st["_synced"] = None, {}
+        st.pop("_step_graphs", None)
+        st.pop("_ctx_keepalive", None)
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            setattr(new, k, copy.deepcopy(v, memo))
+        return new
 
     # ---- reference API kept for compatibility -------------------------------------------------------------------
     def convert_to_fp16(self):
@@ -256,6 +302,7 @@ class UNetModel(nn.Module):
         cfg.use_linear_in_transformer = int(bool(self.use_linear_in_transformer))
         cfg.view_num = self.view_num
         cfg.concat_target = int(self.concat_target)
+        cfg.use_sep = int(self.use_sep)
         return cfg
 
     def engine(self):
@@ -270,11 +317,28 @@ class UNetModel(nn.Module):
         L, h = N.lib(), self.engine()
         return [L.lr_unet_weight_name(h, i).decode() for i in range(L.lr_unet_num_weights(h))]
 
-    def sync_weights(self):
-        """Uploads every parameter whose storage or version changed since the last call (fp32 -> repacked fp16)."""
+    def invalidate_weights(self):
+        """Forces the next forward / set_context to re-upload every parameter. Needed after writes that PyTorch's version
+        counter does not see: `p.data.copy_(...)` / `p.data.mul_(...)` as done by LitEma.copy_to / restore, ema_scope and
+        most LoRA-merge utilities (ldm/modules/ema.py)."""
+        self._synced = {}
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .half(): storages move, the next sync re-uploads
+        self._synced = {}
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):  # copies through p.data-style paths in some loaders: always re-upload
+        self._synced = {}
+        return super().load_state_dict(*args, **kwargs)
+
+    def sync_weights(self, force=False):
+        """Uploads every parameter whose storage or version changed since the last call (fp32 -> repacked fp16).
+        `force=True` (or invalidate_weights()) re-uploads everything."""
         L, h = N.lib(), self.engine()
         stream = N.current_stream()
         keep = []
+        if force:
+            self._synced = {}
         for name, p in self.named_parameters():
             sig = (p.data_ptr(), p._version, p.dtype)
             if self._synced.get(name) == sig:
@@ -294,37 +358,52 @@ class UNetModel(nn.Module):
 
     def set_context(self, context):
         """Caches the cross-attention K/V of `context` [N, L, context_dim] for subsequent forward(context=None)."""
-        self.sync_weights()
-        c = context.detach().float().contiguous()
-        N.check(N.lib().lr_unet_set_context(self.engine(), N.ptr(c), c.shape[0], c.shape[1], N.current_stream()),
-                "lr_unet_set_context")
+        with torch.cuda.device(context.device):
+            self.sync_weights()
+            c = context.detach().float().contiguous()
+            N.check(N.lib().lr_unet_set_context(self.engine(), N.ptr(c), c.shape[0], c.shape[1], N.current_stream()),
+                    "lr_unet_set_context")
         self._ctx_keepalive = c
+
+    def set_c_input(self, c_input, unet_width):
+        """NVS input refinement (NVS_ldm.py:49,64-68): stages `c_input` [N, model_channels, H, Wc] (or None to clear)
+        for the following forwards; `unet_width` is the width of the UNet input x."""
+        L, h = N.lib(), self.engine()
+        if c_input is None:
+            N.check(L.lr_unet_set_c_input(h, None, 0, 0, 0, 0, 0, N.current_stream()), "lr_unet_set_c_input")
+            return
+        with torch.cuda.device(c_input.device):
+            c = c_input.detach().float().contiguous()
+            n, ch, hh, wc = c.shape
+            N.check(L.lr_unet_set_c_input(h, N.ptr(c), n, ch, hh, wc, int(unet_width), N.current_stream()),
+                    "lr_unet_set_c_input")
+            self._cin_keepalive = c
 
     def forward_native(self, x, timesteps, context=None):
         """x fp32 contiguous NCHW CUDA, timesteps int64 [N]; context None -> use the cached K/V."""
         n, c, hh, ww = x.shape
-        out = torch.empty(n, self.out_channels, hh, ww, dtype=torch.float32, device=x.device)
-        L = 0
-        if context is not None:
-            L = context.shape[1]
-        N.check(N.lib().lr_unet_forward(self.engine(), N.ptr(x), N.ptr(timesteps), N.ptr(context), L, N.ptr(out), n,
-                                        hh, ww, N.current_stream()), "lr_unet_forward")
+        with torch.cuda.device(x.device):
+            out = torch.empty(n, self.out_channels, hh, ww, dtype=torch.float32, device=x.device)
+            L = 0
+            if context is not None:
+                L = context.shape[1]
+            N.check(N.lib().lr_unet_forward(self.engine(), N.ptr(x), N.ptr(timesteps), N.ptr(context), L, N.ptr(out), n,
+                                            hh, ww, N.current_stream()), "lr_unet_forward")
         return out
 
     def forward_native_cfg_pair(self, x, timesteps):
         """CFG pair [uncond | cond] sharing x / timesteps: x [B, C, H, W] -> eps [2B, out, H, W]. The 2B contexts (uncond
         first) must have been cached with set_context. Bit-identical to forward_native on the doubled batch."""
         n, c, hh, ww = x.shape
-        out = torch.empty(2 * n, self.out_channels, hh, ww, dtype=torch.float32, device=x.device)
-        N.check(N.lib().lr_unet_forward_cfg_pair(self.engine(), N.ptr(x), N.ptr(timesteps), N.ptr(out), n, hh, ww,
-                                                 N.current_stream()), "lr_unet_forward_cfg_pair")
+        with torch.cuda.device(x.device):
+            out = torch.empty(2 * n, self.out_channels, hh, ww, dtype=torch.float32, device=x.device)
+            N.check(N.lib().lr_unet_forward_cfg_pair(self.engine(), N.ptr(x), N.ptr(timesteps), N.ptr(out), n, hh, ww,
+                                                     N.current_stream()), "lr_unet_forward_cfg_pair")
         return out
 
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         assert y is None, "must specify y if and only if the model is class-conditional"
-        if kwargs.get("c_input") is not None:
-            raise NotImplementedError("c_input (NVS input refinement, inpainting_ldm/NVS_ldm.py:49,64-68) is not "
-                                      "implemented; novel_view_synthesis.yaml sets use_input_refinement: False")
+        c_input = kwargs.get("c_input")
         assert timesteps is not None and context is not None
         if not x.is_cuda:
             raise N.LRError("leftrefill_b200.UNetModel runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -335,6 +414,9 @@ class UNetModel(nn.Module):
             t = timesteps.to(device=x.device, dtype=torch.long).contiguous()
             ctx = context.detach().to(device=x.device).float().contiguous()
             assert ctx.shape[0] == xf.shape[0] and ctx.shape[2] == self.context_dim
+            if c_input is not None or getattr(self, "_cin_active", False):
+                self.set_c_input(None if c_input is None else c_input.to(x.device), xf.shape[3])
+                self._cin_active = c_input is not None
             out = self.forward_native(xf, t, ctx)
         if torch.is_autocast_enabled():
             return out.half()  # what the reference returns under torch.autocast("cuda")
@@ -353,8 +435,14 @@ class MultiViewUnetModel(UNetModel):
 
 
 class NVSUnetModel(UNetModel):
-    """inpainting_ldm/NVS_ldm.py:22-104 with `use_sep=False` (what configs/novel_view_synthesis.yaml uses, where the
-    plain UNetModel is the target): identical to UNetModel. `use_sep=True` and a non-None `c_input` raise."""
+    """inpainting_ldm/NVS_ldm.py:22-104. `use_sep=True` adds the learned `sep_token.<channels>` parameters and the engine
+    inserts / removes the separator column around every non-resampling block (:57-97, odd feature widths W + 1);
+    `forward(..., c_input=...)` adds the refinement features to the input conv's output (:49,64-68). With
+    `use_sep=False` and no c_input (configs/novel_view_synthesis.yaml) it is the plain UNetModel."""
+
+    def __init__(self, *args, **kwargs):
+        kwargs.setdefault("use_sep", False)
+        super().__init__(*args, **kwargs)
 
 
 class _EngineHandle:

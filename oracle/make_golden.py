@@ -248,14 +248,79 @@ def validate_full():
                         out=y_ref.numpy())
 
 
+def _ref_nvs_class():
+    """The reference NVSUnetModel (inpainting_ldm/NVS_ldm.py:22-104), UNMODIFIED: its module cannot be imported here
+    (it pulls pytorch_lightning, torchmetrics, skimage and the datasets at import time), so the class definition alone
+    is extracted from the reference file with `ast` and executed against the reference's own UNetModel / Downsample /
+    Upsample / timestep_embedding. Nothing of it is copied into this repository."""
+    import ast
+    import torch.nn as nn
+    from ldm.modules.diffusionmodules.openaimodel import Downsample, UNetModel, Upsample, timestep_embedding
+    path = os.path.join(REF, "inpainting_ldm", "NVS_ldm.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    node = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "NVSUnetModel")
+    mod = ast.Module(body=[node], type_ignores=[])
+    ns = {"UNetModel": UNetModel, "Downsample": Downsample, "Upsample": Upsample, "nn": nn, "torch": torch,
+          "timestep_embedding": timestep_embedding}
+    exec(compile(mod, path, "exec"), ns)
+    return ns["NVSUnetModel"]
+
+
+def golden_nvs():
+    """NVSUnetModel(use_sep=True) with and without c_input, full config (the reference hard-codes the separator channel
+    list for model_channels = 320) at a 16x32 latent."""
+    cfg = O.DEFAULT_CFG
+    t0 = time.time()
+    NVS = _ref_nvs_class()
+    sd = O.make_state_dict(cfg, seed=3)
+    sd.update(O.make_sep_tokens(cfg, seed=3))
+    m = NVS(**cfg, use_sep=True)
+    assert sorted(k for k in m.state_dict() if k.startswith("sep_token.")) == sorted(
+        f"sep_token.{c}" for c in O.sep_channels(cfg)), "oracle separator channel walk differs from the reference list"
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    x, ctx = inputs(cfg, 2, 16, 32, seed=61)
+    t = torch.tensor([981, 301], dtype=torch.long)
+    g = torch.Generator(device="cpu").manual_seed(62)
+    c_half = torch.randn(2, cfg["model_channels"], 16, 17, generator=g) * 0.5   # right part of the 33-wide canvas
+    c_full = torch.randn(2, cfg["model_channels"], 16, 33, generator=g) * 0.5
+    out = {"x": x.numpy(), "t": t.numpy(), "context": ctx.numpy(), "c_input_half": c_half.numpy(),
+           "c_input_full": c_full.numpy(), "seed": 3}
+    print(f"NVSUnetModel use_sep=True (full config, 2x9x16x32):")
+    for tag, ci in [("sep", None), ("sep_cin_half", c_half), ("sep_cin_full", c_full)]:
+        with torch.no_grad():
+            y_ref = m(x, t, context=ctx, c_input=None if ci is None else ci.clone())
+            y_or = O.nvs_unet_forward(sd, cfg, x, t, ctx, use_sep=True, c_input=ci)
+        check(tag, y_or, y_ref)
+        out[f"out.{tag}"] = y_ref.numpy()
+    # use_sep=False + c_input (the plain UNet with input refinement)
+    m2 = NVS(**cfg, use_sep=False)
+    m2.load_state_dict({k: v for k, v in sd.items() if not k.startswith("sep_token.")}, strict=True)
+    m2.eval()
+    c_half2 = torch.randn(2, cfg["model_channels"], 16, 16, generator=g) * 0.5
+    with torch.no_grad():
+        y_ref = m2(x, t, context=ctx, c_input=c_half2.clone())
+        y_or = O.nvs_unet_forward(sd, cfg, x, t, ctx, use_sep=False, c_input=c_half2)
+    check("nosep_cin_half", y_or, y_ref)
+    out["c_input_half_nosep"] = c_half2.numpy()
+    out["out.nosep_cin_half"] = y_ref.numpy()
+    np.savez_compressed(os.path.join(GOLD, "nvs_full_16x32.npz"), **out)
+    print(f"  [{time.time() - t0:.0f}s]")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--only-multi", action="store_true", help="regenerate only tests/golden/ddim_multi_small.npz")
+    ap.add_argument("--only-nvs", action="store_true", help="regenerate only tests/golden/nvs_full_16x32.npz")
     args = ap.parse_args()
     assert os.path.isdir(REF), "the reference tree is only available in the build container"
     os.makedirs(GOLD, exist_ok=True)
     torch.set_grad_enabled(False)
+    if args.only_nvs:
+        golden_nvs()
+        sys.exit(0)
     if args.only_multi:
         cfg = O.SMALL_CFG
         sd = O.make_state_dict(cfg, seed=0)
@@ -267,4 +332,5 @@ if __name__ == "__main__":
     golden_ddim_multi(cfg, sd, m)
     if args.full:
         validate_full()
+        golden_nvs()
     print("golden fixtures written to", GOLD)

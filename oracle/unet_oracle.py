@@ -12,6 +12,7 @@ state dict so that it shares no code with the product. It follows (reference tre
   timestep_embedding            ldm/modules/diffusionmodules/util.py:154-174
   make_schedule / ddim_step     ldm/models/diffusion/ddim.py:23-52,304-386; util.py:21-74; ddpm.py:149-170
   multiview self-attention      ldm/modules/multiview_attention.py:431-468 (concat_target False and True)
+  nvs_unet_forward              inpainting_ldm/NVS_ldm.py:22-104 (NVSUnetModel: use_sep separator columns, c_input)
 
 Pinning: the reference ships no tests or golden vectors for this path. The oracle is therefore
 pinned against the reference ITSELF: oracle/make_golden.py imports the reference modules in the build container,
@@ -143,6 +144,29 @@ def unet_spec(cfg):
     spec += [("out.0.weight", (ch,)), ("out.0.bias", (ch,)),
              ("out.2.weight", (cfg["out_channels"], mc, 3, 3)), ("out.2.bias", (cfg["out_channels"],))]
     return spec
+
+
+def sep_channels(cfg):
+    """Channel counts that get a separator token (NVS_ldm.py:27 hard-codes [9, 320, 640, 1280, 2560, 1920, 960] for
+    model_channels = 320): the input channels of every block that does not end in a Downsample / Upsample."""
+    inp, mid, out, _ = unet_layout(cfg)
+    order = []
+    for blk in inp + [mid] + out:
+        if blk[-1][0] in ("down", "up"):
+            continue
+        c = blk[0][2][0]
+        if c not in order:
+            order.append(c)
+    return order
+
+
+def make_sep_tokens(cfg, seed=0):
+    """Deterministic stand-ins for the learned `sep_token.<channels>` parameters (NVS_ldm.py:28-29: randn init)."""
+    sd = {}
+    for i, c in enumerate(sep_channels(cfg)):
+        g = torch.Generator(device="cpu").manual_seed(seed * 7919 + 100 + i)
+        sd[f"sep_token.{c}"] = torch.randn(c, generator=g)
+    return sd
 
 
 def make_state_dict(cfg, seed=0, dtype=torch.float32):
@@ -309,6 +333,77 @@ def unet_forward(sd, cfg, x, timesteps, context, view_num=1, concat_target=False
     return F.conv2d(F.silu(h), sd["out.2.weight"], sd["out.2.bias"], padding=1)
 
 
+def nvs_unet_forward(sd, cfg, x, timesteps, context, use_sep=False, c_input=None):
+    """NVSUnetModel.forward (inpainting_ldm/NVS_ldm.py:33-104). With use_sep every block that does not end in a
+    Downsample / Upsample sees the canvas with one learned column `sep_token.<C>` inserted between its halves (:57-60,
+    :74-77, :86-89) and the column is dropped again afterwards (:70-71, :81-82, :93-94); c_input is added to the
+    output of input block 0 while the separator is still in place (:64-68)."""
+    inp, mid, out, _ = unet_layout(cfg)
+    mc = cfg["model_channels"]
+    emb = timestep_embedding(timesteps, mc)
+    emb = F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])
+    emb = F.linear(F.silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
+
+    def run(blk, h):
+        for kind, p, _meta in blk:
+            if kind == "res":
+                h = _resblock(sd, p, h, emb)
+            elif kind == "st":
+                h = _spatial_transformer(sd, p, h, context, cfg)
+            elif kind == "conv_in":
+                h = F.conv2d(h, sd[p + "weight"], sd[p + "bias"], padding=1)
+            elif kind == "down":
+                h = F.conv2d(h, sd[p + "weight"], sd[p + "bias"], stride=2, padding=1)
+            elif kind == "up":
+                h = F.interpolate(h, scale_factor=2, mode="nearest")
+                h = F.conv2d(h, sd[p + "weight"], sd[p + "bias"], padding=1)
+        return h
+
+    def sep_blk(blk):
+        return use_sep and blk[-1][0] not in ("down", "up")
+
+    def insert(h):
+        B, C, H, W = h.shape
+        sep = sd[f"sep_token.{C}"].to(h).reshape(1, C, 1, 1).repeat(B, 1, H, 1)
+        return torch.cat([h[..., :W // 2], sep, h[..., W // 2:]], dim=-1), W
+
+    def remove(h, W):
+        return torch.cat([h[..., :W // 2], h[..., -(W // 2):]], dim=-1)
+
+    hs = []
+    h = x.float()
+    for i, blk in enumerate(inp):
+        W = None
+        if sep_blk(blk):
+            h, W = insert(h)
+        h = run(blk, h)
+        if i == 0 and c_input is not None:
+            if c_input.shape == h.shape:
+                h = h + c_input
+            else:
+                h = h.clone()
+                h[:, :, :, h.shape[-1] // 2:] += c_input
+        if W is not None:
+            h = remove(h, W)
+        hs.append(h)
+    W = None
+    if use_sep:
+        h, W = insert(h)
+    h = run(mid, h)
+    if W is not None:
+        h = remove(h, W)
+    for blk in out:
+        h = torch.cat([h, hs.pop()], dim=1)
+        W = None
+        if sep_blk(blk):
+            h, W = insert(h)
+        h = run(blk, h)
+        if W is not None:
+            h = remove(h, W)
+    h = F.group_norm(h, 32, sd["out.0.weight"], sd["out.0.bias"], 1e-5)
+    return F.conv2d(F.silu(h), sd["out.2.weight"], sd["out.2.bias"], padding=1)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # DDIM schedule and update
 # ------------------------------------------------------------------------------------------------------------------
@@ -345,20 +440,30 @@ def ddim_step(x, e_uncond, e_cond, noise, cfg_scale, a_t, a_prev, sigma_t):
 
 
 def ddim_sample(sd, cfg, x_T, c_concat, context, uc_context, S, eta, cfg_scale, noises, view_num=1,
-                concat_target=False):
-    """DDIMSampler.sample + DiffusionWrapper 'hybrid' (ddim.py:224-302; ddpm.py:1348-1351) with explicit noises."""
+                concat_target=False, trajectory=None, autocast_unet=False):
+    """DDIMSampler.sample + DiffusionWrapper 'hybrid' (ddim.py:224-302; ddpm.py:1348-1351) with explicit noises.
+    `trajectory`, if a list, receives x after every step. `autocast_unet` runs the UNet call under
+    torch.autocast("cuda") (the reference's precision recipe on a GPU, inpainting_ldm/ref_inpainting_ldm.py) with the
+    DDIM state in fp32, as the reference does."""
     steps, alphas, alphas_prev, sigmas = make_schedule(S, eta, make_alphas_cumprod())
     x = x_T
     b = x.shape[0]
+    dev = x.device
     for i, step in enumerate(np.flip(steps)):
         index = len(steps) - i - 1
-        t = torch.full((2 * b,), int(step), dtype=torch.long)
+        t = torch.full((2 * b,), int(step), dtype=torch.long, device=dev)
         xc = torch.cat([torch.cat([x] * 2), torch.cat([c_concat] * 2)], dim=1)
         cc = torch.cat([uc_context, context])
-        e = unet_forward(sd, cfg, xc, t, cc, view_num, concat_target)
+        if autocast_unet:
+            with torch.autocast("cuda"):
+                e = unet_forward(sd, cfg, xc, t, cc, view_num, concat_target).float()
+        else:
+            e = unet_forward(sd, cfg, xc, t, cc, view_num, concat_target)
         e_u, e_c = e.chunk(2)
         x, _ = ddim_step(x, e_u, e_c, noises[i], cfg_scale, float(alphas[index]), float(alphas_prev[index]),
                          float(sigmas[index]))
+        if trajectory is not None:
+            trajectory.append(x)
     return x
 
 

@@ -115,6 +115,81 @@ def case_attn(b, heads, tq, tk, fused_qkv=False, seed=0):
     return report(f"attn b={b} h={heads} tq={tq} tk={tk} fused={fused_qkv}", out.reshape(-1, C), ref.reshape(-1, C))
 
 
+def case_attn_bigrange(b, heads, tq, tk, logit_std=16.0, ramp=40.0, seed=0):
+    """Adversarial range for the online softmax (attention_tc.cuh lazy rescale, threshold 2^8): scaled logits with
+    standard deviation `logit_std` plus a ramp of `ramp` (log units) along the key index, so that the running row maximum
+    keeps increasing from K/V tile to K/V tile and the TMEM-resident O is rescaled many times."""
+    import torch
+    from leftrefill_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    C = heads * 64
+    s = logit_std ** 0.5                       # q.k/8 over 64 unit-variance products has std s^2
+    q = torch.randn(b, tq, C, generator=g) * s
+    k = torch.randn(b, tk, C, generator=g) * s
+    v = torch.randn(b, tk, C, generator=g)
+    u = torch.randn(heads, 64, generator=g)
+    u = u / u.norm(dim=1, keepdim=True)
+    # q gets +a*u, k_j gets +(j/tk)*c*u: the logit gains a*c*(j/tk)/8 -> choose a*c/8 = ramp
+    a = 4.0
+    c = ramp * 8.0 / a
+    q = q + a * u.reshape(1, 1, C)
+    k = k + (torch.arange(tk).float() / tk).reshape(1, tk, 1) * c * u.reshape(1, 1, C)
+    q, k, v = q.cuda().half(), k.cuda().half(), v.cuda().half()
+    out = ops.attention(q, k, v, heads)
+    torch.cuda.synchronize()
+    qf = q.double().reshape(b, tq, heads, 64).permute(0, 2, 1, 3)
+    kf = k.double().reshape(b, tk, heads, 64).permute(0, 2, 1, 3)
+    vf = v.double().reshape(b, tk, heads, 64).permute(0, 2, 1, 3)
+    sim = (qf @ kf.transpose(-1, -2)) * 0.125
+    ref = (sim.softmax(-1) @ vf).permute(0, 2, 1, 3).reshape(b, tq, C).float()
+    return report(f"attn bigrange b={b} h={heads} tq={tq} tk={tk} std={logit_std} ramp={ramp}", out.reshape(-1, C),
+                  ref.reshape(-1, C))
+
+
+def case_gn_bigmean(n, h, w, c, ratio=50.0, silu=True, seed=0):
+    """GroupNorm with |mean| / std >= `ratio` in every group (real SD2 checkpoints have such outlier channels): the
+    E[x^2] - mean^2 form cancels ~ratio^2 of its leading digits."""
+    import torch
+    import torch.nn.functional as F
+    from leftrefill_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sign = torch.where(torch.arange(c) % 64 < 32, 1.0, -1.0).reshape(1, c, 1, 1)   # groups alternate in sign
+    x = (torch.randn(n, c, h, w, generator=g) * 0.25 + 0.25 * ratio * sign).cuda()
+    gamma = torch.randn(c, generator=g).cuda()
+    beta = torch.randn(c, generator=g).cuda()
+    x0 = ops.to_nhwc_f16(x)
+    out = ops.groupnorm(x0, gamma, beta, 1e-5, silu=silu)
+    torch.cuda.synchronize()
+    xr = x0.float().permute(0, 3, 1, 2).double()
+    ref = F.group_norm(xr, 32, gamma.double(), beta.double(), 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    return report(f"groupnorm bigmean n={n} {h}x{w} c={c} |mean|/std={ratio}", out.reshape(-1, c),
+                  ref.float().permute(0, 2, 3, 1).reshape(-1, c))
+
+
+def case_geglu_big(M, K, Nn, seed=0):
+    """GEGLU with outputs of the order of 3e4 (fp16 max 65504): value ~ +-150, gate ~ +-150 -> v * gelu(g) up to ~4e4;
+    the product must be formed in fp32 and only the result rounded to fp16."""
+    import torch
+    from leftrefill_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    a = (torch.randn(M, K, generator=g)).cuda().half()
+    w32 = (torch.randn(2 * Nn, K, generator=g) * (50.0 / K ** 0.5)).cuda()
+    b = (torch.randn(2 * Nn, generator=g) * 20.0).cuda()
+    wp = ops.repack_linear(w32, geglu=True)
+    bp = torch.empty_like(b)
+    bp[0::2] = b[:Nn]
+    bp[1::2] = b[Nn:]
+    out = ops.linear(a, wp, bias=bp, geglu=True)
+    torch.cuda.synchronize()
+    h = a.double() @ w32.half().double().t() + b.double()
+    ref = (h[:, :Nn] * torch.nn.functional.gelu(h[:, Nn:])).float()
+    ok_range = ref.abs().max().item() > 2.0e4 and ref.abs().max().item() < 6.5e4
+    print(f"  geglu_big ref range max|ref|={ref.abs().max().item():.1f} (want 2e4..6.5e4: {ok_range})")
+    return report(f"geglu big M={M} K={K} N={Nn}", out, ref) and ok_range
+
+
 def case_gn(n, h, w, c0, c1=0, silu=True, eps=1e-5, seed=0):
     import torch
     import torch.nn.functional as F
@@ -243,6 +318,11 @@ CASES = {
     "attn_cross": lambda: case_attn(2, 2, 256, 77),
     "attn_ragged": lambda: case_attn(1, 3, 200, 300),
     "attn_long": lambda: case_attn(1, 1, 1024, 4096),
+    "attn_bigrange": lambda: case_attn_bigrange(1, 2, 256, 2048),
+    "attn_bigrange_ragged": lambda: case_attn_bigrange(2, 1, 200, 1000, logit_std=24.0, ramp=80.0),
+    "gn_bigmean": lambda: case_gn_bigmean(2, 16, 32, 320),
+    "gn_bigmean_twopass": lambda: case_gn_bigmean(1, 64, 128, 320, ratio=60.0),
+    "geglu_big": lambda: case_geglu_big(512, 320, 640),
     "gn": lambda: case_gn(2, 16, 32, 320),
     "gn_concat": lambda: case_gn(2, 8, 16, 1280, c1=640),
     "gn_nosilu": lambda: case_gn(3, 8, 8, 64, silu=False, eps=1e-6),

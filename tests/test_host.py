@@ -21,7 +21,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in lr_b200.h but not exported"
     assert declared == set(N.SIGNATURES), "ctypes signature table and header disagree"
-    assert N.lib().lr_abi_version() == 1
+    assert N.lib().lr_abi_version() == N.ABI_VERSION == 2
 
 
 def _engine_table(model):
@@ -58,20 +58,115 @@ def test_unsupported_options_fail_loudly():
 
 def test_nvs_unet_and_multi_sampling_surface():
     """N4 rows of SURVEY §8f: NVSUnetModel (inpainting_ldm/NVS_ldm.py:22-104) is the plain UNet when use_sep is False;
-    use_sep=True / c_input raise instead of silently computing something else; DDIMSampler exposes
+    use_sep=True adds the `sep_token.<channels>` parameters (the reference's hard-coded list for model_channels 320) to
+    the state dict AND to the engine's weight table; unknown semantics-changing kwargs raise; DDIMSampler exposes
     ddim_multi_sampling with the reference's keyword surface (ddim.py:146-158)."""
     import inspect
     m = leftrefill_b200.NVSUnetModel(**dict(O.SMALL_CFG, use_sep=False))
     assert list(m.state_dict().keys()) == [n for n, _ in O.unet_spec(O.SMALL_CFG)]
+    assert m.sep_token is None
+    ms = leftrefill_b200.NVSUnetModel(**dict(O.DEFAULT_CFG, use_sep=True))
+    want = [9, 320, 640, 1280, 2560, 1920, 960]                      # NVS_ldm.py:27
+    assert O.sep_channels(O.DEFAULT_CFG) == want
+    assert sorted(ms.sep_token.keys()) == sorted(str(c) for c in want)
+    assert all(ms.sep_token[str(c)].shape == (c,) for c in want)
+    table = _engine_table(ms)
+    assert [n for n in ms.engine_weight_names() if n.startswith("sep_token.")] == [f"sep_token.{c}" for c in want]
+    assert set(table) == set(ms.state_dict().keys())
+    small = leftrefill_b200.NVSUnetModel(**dict(O.SMALL_CFG, use_sep=True))
+    assert sorted(int(k) for k in small.sep_token.keys()) == sorted(O.sep_channels(O.SMALL_CFG))
     with pytest.raises(NotImplementedError):
-        leftrefill_b200.NVSUnetModel(**dict(O.SMALL_CFG, use_sep=True))
+        leftrefill_b200.MultiViewUnetModel(**dict(O.SMALL_CFG), view_num=2, no_rearrange_selfattn=True)
     with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 9, 16, 32), torch.zeros(1, dtype=torch.long), context=torch.zeros(1, 77, 256),
-          c_input=torch.zeros(1, 64, 16, 32))
+        leftrefill_b200.MultiViewUnetModel(**dict(O.SMALL_CFG), view_num=2, use_sep=True)
     sig = inspect.signature(leftrefill_b200.DDIMSampler.ddim_multi_sampling)
     for kw in ("cond", "shape", "x_T", "timesteps", "temperature", "noise_dropout", "unconditional_guidance_scale",
                "unconditional_conditioning", "ucg_schedule", "mask", "x0", "callback", "img_callback"):
         assert kw in sig.parameters, kw
+
+
+def test_model_copy_and_pickle_drop_the_engine_handle():
+    import copy
+    import pickle
+    m = leftrefill_b200.UNetModel(**O.SMALL_CFG)
+    m.engine()                                   # a live ctypes handle
+    m2 = copy.deepcopy(m)
+    assert m2._engine is None and m._engine is not None
+    m3 = pickle.loads(pickle.dumps(m))
+    assert m3._engine is None
+    assert list(m3.state_dict().keys()) == list(m.state_dict().keys())
+
+
+class _CountingEmbedder(torch.nn.Module):
+    """Stands in for PromptCLIPEmbedder (Refill_modules.py:100-191): text -> [B, 77, C], counts the strings it encodes."""
+
+    def __init__(self, deep=0):
+        super().__init__()
+        self.special_embeddings = torch.nn.Embedding(4, 8)
+        self.encoded = []
+        self.deep = deep
+
+    def forward(self, text):
+        def one(s):
+            g = torch.Generator().manual_seed(sum(map(ord, s)) + 1)
+            return torch.randn(77, 8, generator=g) + self.special_embeddings.weight.sum()
+        if self.deep:
+            self.encoded += [tuple(layer[i] for layer in text) for i in range(len(text[0]))]
+            return torch.stack([torch.stack([one(layer[i]) for layer in text]) for i in range(len(text[0]))])
+        self.encoded += list(text)
+        return torch.stack([one(s) for s in text])
+
+    def encode(self, text):
+        return self(text)
+
+
+def test_prompt_context_cache():
+    """contexts are memoised per unique prompt string; the encoder sees each string once; parameter
+    updates and invalidate() drop the cache; the deep-prompt layout [n_layer][B] is keyed per sample."""
+    from leftrefill_b200 import PromptContextCache, install_context_cache
+    emb = _CountingEmbedder()
+    ref = _CountingEmbedder()
+    ref.load_state_dict(emb.state_dict())
+    for q in list(emb.parameters()) + list(ref.parameters()):
+        q.requires_grad_(False)                                  # frozen encoder, as at inference (freeze(), :152-155)
+    c = PromptContextCache(emb)
+    p = "<left> <right> a photo"
+    a = c([p] * 4)
+    assert a.shape == (4, 77, 8) and emb.encoded == [p]
+    assert torch.equal(a, ref([p] * 4))
+    u = c.encode([""] * 4)                                       # get_unconditional_conditioning, ref_inpainting_ldm.py:35
+    assert emb.encoded == [p, ""] and torch.equal(u, ref([""] * 4))
+    b = c([p, "", "other", p])
+    assert emb.encoded == [p, "", "other"] and torch.equal(b, ref([p, "", "other", p]))
+    assert c.hits == 3 + 3 + 3 and c.misses == 3 and c.encoder_calls == 3
+    with torch.no_grad():
+        emb.special_embeddings.weight.add_(1.0)                  # optimizer step: version counter moves
+        ref.special_embeddings.weight.add_(1.0)
+    assert torch.equal(c([p]), ref([p])) and emb.encoded[-1] == p and len(emb.encoded) == 4
+    emb.special_embeddings.weight.data.mul_(2.0)                 # invisible to the version counter
+    ref.special_embeddings.weight.data.mul_(2.0)
+    c.invalidate()
+    assert torch.equal(c([p]), ref([p])) and len(emb.encoded) == 5
+    # deep prompt: [n_layer][B] lists, output [B, n_layer, L, C] (Refill_modules.py:162-171)
+    d = _CountingEmbedder(deep=3)
+    with torch.enable_grad():                                    # trainable embeddings + grad mode: bypass the cache
+        n0 = len(d.encoded)
+        PromptContextCache(d)([["a"], ["a1"], ["a2"]])
+        PromptContextCache(d)([["a"], ["a1"], ["a2"]])
+        assert len(d.encoded) == n0 + 2
+    d = _CountingEmbedder(deep=3).requires_grad_(False)
+    cd = PromptContextCache(d)
+    text = [["a", "b", "a"], ["a1", "b1", "a1"], ["a2", "b2", "a2"]]
+    z = cd(text)
+    assert z.shape == (3, 3, 77, 8) and d.encoded == [("a", "a1", "a2"), ("b", "b1", "b2")]
+    assert torch.equal(z[0], z[2]) and not torch.equal(z[0], z[1])
+
+    class LDM:
+        cond_stage_model = emb
+    ldm = LDM()
+    w = install_context_cache(ldm)
+    assert ldm.cond_stage_model is w and install_context_cache(ldm) is w
+    assert w.special_embeddings is emb.special_embeddings        # attributes stay reachable through the wrapper
 
 
 def test_no_cpu_fallback():

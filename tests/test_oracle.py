@@ -88,3 +88,20 @@ def test_ddim_multi_sampling_vs_reference_golden(small_sd):
                             [torch.tensor(g[f"context{v}"]) for v in range(V)], torch.tensor(g["uc_context"]), S, 1.0,
                             2.5, noises, random.Random(int(g["random_seed"])))
     _close(s.numpy(), g["samples"], tol=2e-4)
+
+
+def test_nvs_use_sep_vs_reference_golden():
+    """NVSUnetModel(use_sep=True) + c_input (inpainting_ldm/NVS_ldm.py:22-104): the oracle against the output of the
+    unmodified reference class (oracle/make_golden.py --only-nvs; full config because the reference hard-codes the
+    separator channel list for model_channels = 320), 16x32 latent -> feature widths 33 / 17 / 9 / 5."""
+    g = load_golden("nvs_full_16x32.npz")
+    cfg = O.DEFAULT_CFG
+    assert O.sep_channels(cfg) == [9, 320, 640, 1280, 2560, 1920, 960]      # NVS_ldm.py:27
+    sd = O.make_state_dict(cfg, seed=int(g["seed"]))
+    sd.update(O.make_sep_tokens(cfg, seed=int(g["seed"])))
+    x, t, ctx = torch.tensor(g["x"]), torch.tensor(g["t"]), torch.tensor(g["context"])
+    y = O.nvs_unet_forward(sd, cfg, x, t, ctx, use_sep=True, c_input=torch.tensor(g["c_input_half"]))
+    _close(y.numpy(), g["out.sep_cin_half"])
+    y = O.nvs_unet_forward(sd, cfg, x[:1], t[:1], ctx[:1], use_sep=False,
+                           c_input=torch.tensor(g["c_input_half_nosep"])[:1])
+    _close(y.numpy(), g["out.nosep_cin_half"][:1])

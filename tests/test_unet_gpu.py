@@ -373,3 +373,163 @@ def test_multiview_four_reference_stitched_full_size():
             floor = O.unet_forward(sdc, cfg, x.cuda(), t.cuda(), ctx.cuda(), view_num=5, concat_target=True).float()
         y = m(x.cuda(), t.cuda(), context=ctx.cuda())
     _assert_parity(y, ref, floor)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# round 2: parity at BASELINE sizes, NVSUnetModel variants, context-length change under the cached step graph
+# ----------------------------------------------------------------------------------------------------------------------
+TRAJ_STEPS = (1, 10, 25, 50)
+
+
+def test_sampler_full_size_50_steps_vs_oracle_trajectory(full):
+    """BASELINE config C2 through the public API: DDIMSampler.sample(50, 4, (4, 64, 128)), cfg 2.5, eta 1, the full
+    865.9 M-parameter model, injected noise - against the oracle sampler (O.ddim_sample on the GPU) in fp32 and with the
+    UNet under torch.autocast (the reference's precision recipe). The native trajectory must stay within 1.25x of the
+    autocast trajectory's distance to the fp32 trajectory at steps 1 / 10 / 25 / 50 (ddim.py:224-386)."""
+    import leftrefill_b200 as lr
+    m, sd = full
+    dev = torch.device("cuda")
+    S, B = 50, 4
+    x_T, c_cat, ctx, uc = synthetic_inputs(B, device=dev)
+    g = torch.Generator().manual_seed(2024)
+    noises = torch.randn(S, B, 4, 64, 128, generator=g).to(dev)
+    s = lr.DDIMSampler(FakeLDM(m, dev))
+    s.noise_source = lambda shape, device, i: noises[i]
+    cond = {"c_concat": [c_cat], "c_crossattn": [ctx]}
+    ucond = {"c_concat": [c_cat], "c_crossattn": [uc]}
+    samples, inter = s.sample(S, B, (4, 64, 128), cond, eta=1.0, x_T=x_T, verbose=False,
+                              unconditional_guidance_scale=2.5, unconditional_conditioning=ucond, log_every_t=1)
+    native = inter["x_inter"][1:]                      # x after every step (entry 0 is x_T)
+    assert len(native) == S and torch.equal(native[-1], samples)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    ref, floor = [], []
+    with torch.no_grad():
+        O.ddim_sample(sdc, O.DEFAULT_CFG, x_T, c_cat, ctx, uc, S, 1.0, 2.5, noises, trajectory=ref)
+        O.ddim_sample(sdc, O.DEFAULT_CFG, x_T, c_cat, ctx, uc, S, 1.0, 2.5, noises, trajectory=floor,
+                      autocast_unet=True)
+    rows = []
+    for k in TRAJ_STEPS:
+        sn, sf = err_stats(native[k - 1], ref[k - 1]), err_stats(floor[k - 1], ref[k - 1])
+        rows.append((k, sn["rel_rms"], sf["rel_rms"], sn["max_abs"], sf["max_abs"]))
+        print(f"step {k:2d}: native rel_rms {sn['rel_rms']:.3e} max {sn['max_abs']:.3e} | autocast rel_rms "
+              f"{sf['rel_rms']:.3e} max {sf['max_abs']:.3e}")
+    for k, rn, rf, _, _ in rows:
+        assert rn <= FLOOR_FACTOR * rf, rows
+    assert torch.isfinite(samples).all()
+
+
+def test_multiview_four_reference_stitched_64x128():
+    """BASELINE config C4 at its full size: view_num=5, concat_target=True on 4 stitched 64x128 latents -> self-attention
+    over 5*64*64 = 20480 tokens at the top level (multiview_attention.py:431-468), one sample, vs the fp32 oracle."""
+    cfg = O.DEFAULT_CFG
+    m, sd = _build(cfg, 2, multiview=(5, True))
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn(4, 9, 64, 128, generator=g)
+    ctx = torch.randn(4, 77, 1024, generator=g)
+    t = torch.full((4,), 601, dtype=torch.long)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = O.unet_forward(sdc, cfg, x.cuda(), t.cuda(), ctx.cuda(), view_num=5, concat_target=True)
+        with torch.autocast("cuda"):
+            floor = O.unet_forward(sdc, cfg, x.cuda(), t.cuda(), ctx.cuda(), view_num=5, concat_target=True).float()
+        y = m(x.cuda(), t.cuda(), context=ctx.cuda())
+    _assert_parity(y, ref, floor)
+
+
+@pytest.fixture(scope="module")
+def nvs_sep():
+    import leftrefill_b200 as lr
+    cfg = O.DEFAULT_CFG
+    g = load_golden("nvs_full_16x32.npz")
+    sd = O.make_state_dict(cfg, seed=int(g["seed"]))
+    sd.update(O.make_sep_tokens(cfg, seed=int(g["seed"])))
+    m = lr.NVSUnetModel(**cfg, use_sep=True)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval(), sd, g
+
+
+@pytest.mark.parametrize("tag,cin", [("sep", None), ("sep_cin_half", "c_input_half"), ("sep_cin_full", "c_input_full")])
+def test_nvs_use_sep_vs_reference_golden(nvs_sep, tag, cin):
+    """NVSUnetModel(use_sep=True) (inpainting_ldm/NVS_ldm.py:22-104): learned separator column around every non-resampling
+    block (feature widths 33 / 17 / 9 / 5), optionally with c_input added to the input conv's output; golden from the
+    unmodified reference class (oracle/make_golden.py --only-nvs)."""
+    m, sd, g = nvs_sep
+    x, t, ctx = torch.tensor(g["x"]).cuda(), torch.tensor(g["t"]).cuda(), torch.tensor(g["context"]).cuda()
+    ci = None if cin is None else torch.tensor(g[cin]).cuda()
+    with torch.no_grad():
+        y = m(x, t, context=ctx, c_input=ci)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        sdc = {k: v.cuda() for k, v in sd.items()}
+        with torch.autocast("cuda"):
+            floor = O.nvs_unet_forward(sdc, O.DEFAULT_CFG, x, t, ctx, use_sep=True, c_input=ci).float()
+    _assert_parity(y, g[f"out.{tag}"], floor)
+
+
+def test_nvs_c_input_without_sep_and_clearing(full):
+    """c_input on the plain UNet (use_sep=False): added over the right half of the input conv's output; a following call
+    WITHOUT c_input must not see the staged tensor."""
+    import leftrefill_b200 as lr
+    g = load_golden("nvs_full_16x32.npz")
+    cfg = O.DEFAULT_CFG
+    sd = {k: v for k, v in O.make_state_dict(cfg, seed=int(g["seed"])).items()}
+    m = lr.NVSUnetModel(**cfg)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    x, t, ctx = torch.tensor(g["x"]).cuda(), torch.tensor(g["t"]).cuda(), torch.tensor(g["context"]).cuda()
+    with torch.no_grad():
+        y0 = m(x, t, context=ctx)
+        y1 = m(x, t, context=ctx, c_input=torch.tensor(g["c_input_half_nosep"]).cuda())
+        y2 = m(x, t, context=ctx)
+    _assert_parity(y1, g["out.nosep_cin_half"])
+    assert torch.equal(y0, y2)
+    assert not torch.allclose(y0, y1, rtol=1e-2, atol=1e-2)
+
+
+def test_sampler_graph_survives_context_length_change(small, monkeypatch):
+    """A second sample() on the same UNet with the same batch / latent shape but another context length must not replay
+    a step graph that points at the freed cross-attention K/V buffers (round-1 advisor finding): graph == eager for
+    L = 77, then L = 50, then L = 77 again."""
+    import leftrefill_b200 as lr
+    m, _ = small
+    dev = torch.device("cuda")
+    m.__dict__.pop("_step_graphs", None)
+    for L in (77, 50, 77):
+        x_T, c_cat, ctx, uc = synthetic_inputs(2, h=16, w=32, ctx_dim=256, L=L, seed=900 + L, device=dev)
+        cond = {"c_concat": [c_cat], "c_crossattn": [ctx]}
+        ucond = {"c_concat": [c_cat], "c_crossattn": [uc]}
+        out = {}
+        for mode in ("graph", "eager"):
+            if mode == "eager":
+                monkeypatch.setenv("LR_NO_CUDA_GRAPH", "1")
+            else:
+                monkeypatch.delenv("LR_NO_CUDA_GRAPH", raising=False)
+            torch.manual_seed(11)
+            s = lr.DDIMSampler(FakeLDM(m, dev))
+            out[mode], _ = s.sample(3, 2, (4, 16, 32), cond, eta=1.0, x_T=x_T, verbose=False,
+                                    unconditional_guidance_scale=2.5, unconditional_conditioning=ucond)
+        assert torch.equal(out["graph"], out["eager"]), (L, (out["graph"] - out["eager"]).abs().max().item())
+    monkeypatch.delenv("LR_NO_CUDA_GRAPH", raising=False)
+
+
+def test_unet_deepcopy_and_invalidate(small):
+    """copy.deepcopy of a model that already owns an engine handle must work (the copy builds its own engine), and
+    invalidate_weights() must make `.data` writes (invisible to the version counter: LitEma.copy_to) take effect."""
+    import copy
+    m, _ = small
+    g = load_golden("unet_small.npz")
+    x, t, ctx = (torch.tensor(g[k]).cuda() for k in ("x", "t", "context"))
+    with torch.no_grad():
+        y0 = m(x, t, context=ctx)
+        m2 = copy.deepcopy(m)
+        assert torch.equal(m2(x, t, context=ctx), y0)
+        w = m2.out[2].weight
+        w.data.mul_(2.0)                      # does NOT bump w._version
+        m2.invalidate_weights()
+        y1 = m2(x, t, context=ctx)
+    b = m2.out[2].bias.detach()[None, :, None, None]
+    assert torch.allclose(y1 - b, 2 * (y0 - b), rtol=5e-3, atol=8e-3)
