@@ -17,7 +17,14 @@ Metric: stitched 512x1024 images/sec @ 50 DDIM steps (whole job, all ranks).
   cpu_baseline : the oracle (a port: /root/reference does not exist on the GPU box) timed on the host cores on a bounded
                  sample (one CFG step of one canvas), extrapolated to the metric's unit
 
+  gpu_reference: CONTEXT ONLY (never routed through repo kernels, never the product): the oracle (the reference's
+                 PyTorch ops) run on the same GPU under torch.autocast, once with the reference's materialised-logits
+                 attention (attention.py:168-196) and once with F.scaled_dot_product_attention swapped in - i.e. what
+                 cuDNN + cuBLAS + a library flash kernel do on this box for the same UNet batch.
+
 `--impl reference` times the reference's CPU implementation of the path (the oracle port) with all host threads.
+`--config c2|c4|c5` selects the workload (BASELINE.json configs[1] (default) / [3] multiview 4-reference stitched /
+[4] NVS 32x64 latent); the driver contract (no flag) is c2 at N = 1 and c3 = c2 per GPU at N = 8.
 """
 import argparse
 import json
@@ -39,7 +46,9 @@ def _ncu_traffic():
     """DRAM bytes (read + write) per gemm_conv_kernel launch from the committed ncu launch list of one UNet forward
     (profiles/r1_ncu_forward_launches_summary.json: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,
     dram__bytes_write.sum` over the same workload, cold cache per launch). None if the file is missing."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_forward_launches_summary.json")
+    p = os.path.join(ROOT, "profiles", "r2_ncu_forward_launches_summary.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r1_ncu_forward_launches_summary.json")
     try:
         d = json.load(open(p))
         rd = wr = n = 0
@@ -48,9 +57,9 @@ def _ncu_traffic():
                 rd += v["dram_read"]
                 wr += v["dram_write"]
                 n += v["launches"]
-        return (rd + wr) / n if n else None
+        return ((rd + wr) / n if n else None), os.path.basename(p)
     except Exception:  # noqa: BLE001
-        return None
+        return None, None
 
 
 def _peaks():
@@ -138,21 +147,94 @@ def run_reference(args):
         return
     import torch
     ddim_steps = args.ddim_steps
+    batch = args.batch if args.batch > 0 else CONFIGS["c2"]["batch"]
     times, cores = cpu_baseline(threads=os.cpu_count(), canvases=1, repeats=args.steps, warmup=max(1, min(args.warmup, 1)))
     t = sum(times) / len(times)
     value = 1.0 / (ddim_steps * t)
     sample = (f"each step = 1 CFG DDIM step (UNet batch 2, 64x128 latent, fp32) of 1 canvas on {cores} threads; "
               f"images/s = 1 / ({ddim_steps} x step time)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 * ddim_steps * args.batch,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 * ddim_steps * batch,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"batch={args.batch} ref-inpainting canvases, {ddim_steps} DDIM steps, cfg=2.5, "
+            "config": {"workload": f"batch={batch} ref-inpainting canvases, {ddim_steps} DDIM steps, cfg=2.5, "
                                    "stitched 512x1024 (64x128 latent), SD2-inpainting UNet 865.9M params, random init",
                        "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+CONFIGS = {
+    # BASELINE.json configs[1] (and configs[2] = the same per GPU on 8 GPUs)
+    "c2": dict(H=64, W=128, batch=4, view=None, rows_per_sample=1,
+               name="batch={B} ref-inpainting canvases per GPU, {S} DDIM steps, cfg=2.5, eta=1.0, stitched 512x1024 "
+                    "(64x128 latent, 9-ch input, UNet batch 2*batch), SD2-inpainting UNet 865.9M params random init "
+                    "(BASELINE.json configs[1])"),
+    # configs[3]: multiview, 4 reference views stitched with the target: MultiViewUnetModel(view_num=5, concat_target=True),
+    # every sample = 4 stitched [ref_i | target] canvases whose self-attention runs over 5*64*64 = 20480 tokens
+    "c4": dict(H=64, W=128, batch=2, view=(5, True), rows_per_sample=4,
+               name="batch={B} multiview samples per GPU x 4 stitched [ref_i | target] 512x1024 canvases (view_num=5, "
+                    "concat_target=True: self-attention over 20480 tokens), {S} DDIM steps, cfg=2.5, UNet batch "
+                    "2*4*batch (BASELINE.json configs[3])"),
+    # configs[4]: NVS config (novel_view_synthesis.yaml: the plain UNetModel at a 32x64 latent), 4 canvases per GPU
+    "c5": dict(H=32, W=64, batch=4, view=None, rows_per_sample=1,
+               name="batch={B} NVS canvases per GPU (novel_view_synthesis.yaml, 256x512 stitched = 32x64 latent), {S} DDIM "
+                    "steps, cfg=2.5, UNet batch 2*batch (BASELINE.json configs[4]: 16 canvases over 4 GPUs)"),
+}
+
+
+def device_unet(cls, cfg, dev, seed, **extra):
+    """The reference architecture with synthetic weights drawn ON THE DEVICE (no checkpoint offline): the module is
+    built on the meta device and filled in place, so a run does not spend a minute of host time initialising 866 M
+    parameters. Same scaling rules as the oracle's make_state_dict (variance preserving; norm gains around 1; the
+    reference's zero-initialised tensors drawn like the others)."""
+    import torch
+    with torch.device("meta"):
+        m = cls(**cfg, **extra)
+    m = m.to_empty(device=dev)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if p.dim() == 1:
+                p.normal_(0.0, 0.05, generator=g)
+                if name.endswith("weight"):
+                    p.mul_(2.0).add_(1.0)
+            else:
+                fan_in = p[0].numel()
+                p.normal_(0.0, 1.0 / fan_in ** 0.5, generator=g)
+    return m.eval()
+
+
+def gpu_reference(unet, cfg, xc, tt, cc, iters=3):
+    """CONTEXT ONLY - never the product, never through repo kernels: the oracle (the reference's PyTorch op sequence)
+    on this GPU under torch.autocast with the same weights and UNet batch, (a) with the reference's own attention
+    (materialised fp32 logits, attention.py:168-196), (b) with F.scaled_dot_product_attention swapped in. ms per UNet
+    forward, CUDA events. This - cuDNN + cuBLAS (+ a library flash kernel) - is what the hand-written kernels compete
+    with on the same box."""
+    import torch
+    from helpers import O
+    sd = {k: p.detach() for k, p in unet.named_parameters()}
+    out = {}
+    for impl in ("vanilla", "sdpa"):
+        O.ATTN_IMPL = impl
+        try:
+            with torch.no_grad(), torch.autocast("cuda"):
+                O.unet_forward(sd, cfg, xc, tt, cc)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    O.unet_forward(sd, cfg, xc, tt, cc)
+                e1.record()
+                torch.cuda.synchronize()
+            out[impl + "_ms_per_unet_forward"] = e0.elapsed_time(e1) / iters
+        except Exception as e:  # noqa: BLE001 - context leg: report, never fail the bench
+            out[impl + "_error"] = str(e)[:200]
+        finally:
+            O.ATTN_IMPL = "vanilla"
+        torch.cuda.empty_cache()
+    return out
 
 
 def _ensure_built():
@@ -185,16 +267,18 @@ def run_native(args):
         raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the native arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    B, S = args.batch, args.ddim_steps
+    wl = CONFIGS[args.config]
+    S = args.ddim_steps
+    nsamp = args.batch if args.batch > 0 else wl["batch"]   # samples (images) per GPU and batch
+    B = nsamp * wl["rows_per_sample"]                        # rows the sampler sees (stitched canvases)
     cfg = O.DEFAULT_CFG
-    H, W = 64, 128
+    H, W = wl["H"], wl["W"]
 
-    # ---- model: reference architecture, random init (no checkpoint offline), replicated per rank ----
-    sd = O.make_state_dict(cfg, seed=0)
-    unet = lr.UNetModel(**cfg)
-    unet.load_state_dict(sd, strict=True)
-    del sd
-    unet = unet.to(dev).eval()
+    # ---- model: reference architecture, random init on the device (no checkpoint offline), replicated per rank ----
+    if wl["view"] is None:
+        unet = device_unet(lr.UNetModel, cfg, dev, seed=0)
+    else:
+        unet = device_unet(lr.MultiViewUnetModel, cfg, dev, seed=0, view_num=wl["view"][0], concat_target=wl["view"][1])
     ldm = FakeLDM(unet, dev)
 
     # ---- synthetic inputs, rank-specific seed: weak scaling, B canvases per GPU ----
@@ -292,6 +376,16 @@ def run_native(args):
     torch.cuda.synchronize()
     unet_ms = e0.elapsed_time(e1) / 10
     unet_flops = unet.last_flops()
+    gref = None
+    if rank == 0 and world == 1 and wl["view"] is None and not args.no_gpu_reference:
+        gref = gpu_reference(unet, cfg, xc, tt, torch.cat([uc, ctx]).contiguous())
+        if "vanilla_ms_per_unet_forward" in gref:
+            gref["native_ms_per_unet_forward"] = unet_ms
+            gref["speedup_vs_vanilla"] = gref["vanilla_ms_per_unet_forward"] / unet_ms
+        if "sdpa_ms_per_unet_forward" in gref:
+            gref["speedup_vs_sdpa"] = gref["sdpa_ms_per_unet_forward"] / unet_ms
+        gref["note"] = ("context only: the oracle's PyTorch ops (cuDNN/cuBLAS, autocast fp16) on this GPU, same weights "
+                        f"and UNet batch {xc.shape[0]} at {H}x{W}; not the product path")
 
     if rank != 0:
         if world > 1:
@@ -299,6 +393,7 @@ def run_native(args):
             dist.destroy_process_group()
         return
     sustained, burst, hbm, peak_src = _peaks()
+    traffic, traffic_src = _ncu_traffic()
     names = ["gemm_conv_kernel", "attention_kernel", "groupnorm", "layernorm", "other"]
     classes = {names[c]: {"ms_per_forward": acc_ms[c] / prof_iters, "tflops": (acc_fl[c] / acc_ms[c] / 1e9) if acc_ms[c] > 0 and acc_fl[c] > 0 else None,
                           "steps_per_forward": acc_n[c] // prof_iters} for c in range(5)}
@@ -308,9 +403,9 @@ def run_native(args):
     mufu_bound = 148 * 16 * sm_mhz * 1e6 * 256 / 1e12 if sm_mhz else None
     roofline = {"kernel": "gemm_conv_kernel (tcgen05 implicit-GEMM conv3x3 + linear, all launches of a UNet forward)",
                 "bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                "frac": achieved / sustained, "traffic": _ncu_traffic(),
+                "frac": achieved / sustained, "traffic": traffic,
                 "traffic_note": "DRAM read+write bytes per launch, mean over the gemm_conv_kernel launches of one forward "
-                                "(ncu, cold cache per launch; profiles/r1_ncu_forward_launches_summary.json)",
+                                f"(ncu launch list of this build, cold cache per launch; profiles/{traffic_src})",
                 "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "flops_per_launch": acc_fl[0] / gemm_launches, "ms_per_launch": acc_ms[0] / gemm_launches,
                 "launches_timed": gemm_launches,
@@ -326,21 +421,19 @@ def run_native(args):
                 "by_class": classes}
 
     cb = None
-    if world == 1:  # the CPU baseline is reported at N = 1 only
+    if world == 1 and args.config == "c2":  # the CPU baseline is reported at N = 1 only (and for the headline config)
         cb_times, cores = cpu_baseline(threads=os.cpu_count(), canvases=1, repeats=1, warmup=1)
         cb_t = sum(cb_times) / len(cb_times)
         cb = {"value": 1.0 / (S * cb_t), "unit": UNIT, "cores": cores, "kind": "port",
               "sample": f"1 CFG DDIM step (UNet batch 2, 64x128 latent, fp32 oracle) of 1 canvas = {cb_t:.2f} s on "
                         f"{cores} threads; images/s = 1/({S} x step)"}
 
-    images = B * world * args.steps
+    images = nsamp * world * args.steps
     h2d = sum(t.numel() * t.element_size() for t in (xT_h, ccat_h, ctx_h, uc_h))
     line = {"metric": METRIC, "value": images / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": f"batch={B} ref-inpainting canvases per GPU, {S} DDIM steps, cfg=2.5, eta=1.0, stitched "
-                                   "512x1024 (64x128 latent, 9-ch input, UNet batch 2*batch), SD2-inpainting UNet 865.9M "
-                                   "params random init (BASELINE.json configs[1])",
+            "config": {"workload": wl["name"].format(B=nsamp, S=S), "name": args.config,
                        "l2": "inputs larger than L2: 1.73 GB fp16 weights + >2 GB activations per UNet forward vs 126 MB",
                        "parallelism": f"dp{world}: canvases sharded, weights replicated, 1 all-gather per batch",
                        "precision": "fp16 operands, fp32 accumulate / norm statistics / softmax / DDIM state"},
@@ -348,7 +441,8 @@ def run_native(args):
             "unet_tflop_per_forward": unet_flops / 1e12,
             "e2e": {"value": images / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": out_h.numel() * 4},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cb}
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cb,
+            "gpu_reference": gref}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -361,7 +455,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--batch", type=int, default=4, help="stitched canvases per GPU (UNet batch is 2x with CFG)")
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU (0 = the config's: 4 canvases for c2 / c5, "
+                                                         "2 multiview samples for c4); the UNet batch is 2x rows with CFG")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the PyTorch-ops-on-GPU context leg")
     ap.add_argument("--ddim-steps", type=int, default=50)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -212,6 +212,9 @@ def _resblock(sd, p, x, emb):
     return x + h
 
 
+ATTN_IMPL = "vanilla"  # "sdpa": F.scaled_dot_product_attention instead (bench.py's gpu_reference context leg only)
+
+
 def _attention(sd, p, x, context, heads):
     q = F.linear(x, sd[p + "to_q.weight"])
     k = F.linear(context, sd[p + "to_k.weight"])
@@ -223,8 +226,17 @@ def _attention(sd, p, x, context, heads):
         return t.reshape(b, t.shape[1], heads, d).permute(0, 2, 1, 3)
 
     q, k, v = split(q), split(k), split(v)
-    sim = torch.einsum("bhid,bhjd->bhij", q, k) * (d ** -0.5)
-    o = torch.einsum("bhij,bhjd->bhid", sim.softmax(dim=-1), v)
+    if ATTN_IMPL == "sdpa":
+        o = F.scaled_dot_product_attention(q, k, v)
+    else:
+        if q.is_cuda and torch.is_autocast_enabled():
+            # _ATTN_PRECISION == "fp32" (attention.py:22,175-179): under autocast the logits are computed with autocast
+            # disabled on upcast q, k; softmax in fp32; the PV product is back under autocast (fp16)
+            with torch.autocast("cuda", enabled=False):
+                sim = torch.einsum("bhid,bhjd->bhij", q.float(), k.float()) * (d ** -0.5)
+        else:
+            sim = torch.einsum("bhid,bhjd->bhij", q, k) * (d ** -0.5)
+        o = torch.einsum("bhij,bhjd->bhid", sim.softmax(dim=-1), v)
     o = o.permute(0, 2, 1, 3).reshape(b, n, c)
     return F.linear(o, sd[p + "to_out.0.weight"], sd[p + "to_out.0.bias"])
 
