@@ -142,6 +142,25 @@ int lr_linear_f16(const void* a, int lda, int M, int K, const void* w, int ldw, 
 int lr_conv3x3_f16(const void* x0, int c0, const void* x1, int c1, int n, int h, int w, int stride, const void* wt,
                    int cout, const float* bias, const float* bias_img, const void* residual, void* out,
                    int force_block_n, void* stream);
+/* ---- GroupNorm fused into its producer and its consumer (ResBlock in_layers / out_layers = GroupNorm32 -> SiLU -> conv,
+ * openaimodel.py:200-204,224-231,254-274; SpatialTransformer norm -> proj_in, attention.py:399-404) -----------------
+ * A GroupNorm is y = x * scale[n, c] + shift[n, c] once its statistics are known. The kernel that WRITES a tensor can
+ * leave per-tile (sum, sum of squares) partials per channel (stats_out, lr_conv_stats_rows() x cout float2 entries;
+ * *stats_ppi receives the table rows per image, 0 if this geometry cannot produce them); lr_gn_finalize reduces the
+ * partials of one or two (channel-concatenated) tensors in a fixed order to scale / shift [n, c0 + c1]; the kernel that
+ * READS the tensor applies them (and the SiLU) to its activation tiles in shared memory (gn_scale / gn_shift non-NULL;
+ * 3x3: stride 1 and an image of at least 16 rows x 8 columns). The normalised tensor never exists in memory. */
+long long lr_conv_stats_rows(int n, int h, int w, int stride, int taps, int rows_per_img);
+int lr_gn_conv3x3_f16(const void* x0, int c0, const void* x1, int c1, int n, int h, int w, const float* gn_scale,
+                      const float* gn_shift, int silu, const void* wt, int cout, const float* bias, const float* bias_img,
+                      const void* residual, void* out, float* stats_out, int* stats_ppi, int force_block_n, void* stream);
+/* token matrix a [M, K] whose image index is row / rows_per_img (rows_per_img = H*W) */
+int lr_gn_linear_f16(const void* a, int M, int K, int rows_per_img, const float* gn_scale, const float* gn_shift,
+                     int silu, const void* w, int n_cols, const float* bias, const void* residual, void* out,
+                     float* stats_out, int* stats_ppi, int force_block_n, void* stream);
+int lr_gn_finalize(const float* part0, int ppi0, int c0, const float* part1, int ppi1, int c1, int n, int P, int groups,
+                   float eps, const float* gamma, const float* beta, float* scale, float* shift, void* stream);
+
 /* softmax(q k^T * scale) v, d_head = 64. q [batch*tq, ldq] (head h at columns q_col0 + 64h), likewise k, v over tk
  * tokens; out [batch*tq, ld_out]. Replaces attention.py:176-195. */
 int lr_attention_f16(const void* q, int ldq, int q_col0, const void* k, int ldk, int k_col0, const void* v, int ldv,

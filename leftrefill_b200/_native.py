@@ -74,6 +74,14 @@ SIGNATURES = {
                               c_void_p, c_int, c_int, c_int, c_void_p]),
     "lr_conv3x3_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "lr_conv_stats_rows": (c_longlong, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "lr_gn_conv3x3_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                  c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int), c_int,
+                                  c_void_p]),
+    "lr_gn_linear_f16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, POINTER(c_int), c_int, c_void_p]),
+    "lr_gn_finalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p]),
     "lr_attention_f16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
                                  c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "lr_groupnorm_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,

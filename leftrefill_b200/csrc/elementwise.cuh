@@ -246,6 +246,41 @@ __global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __half* __
   gn_apply_rows(base, ld, o, C, p_begin + rsub, p_end, rpi, sc, sh, do_silu);
 }
 
+// GroupNorm apply [+ SiLU] from the per-(image, channel) coefficients gn_finalize_kernel derived from the PRODUCER's
+// statistics: y = [silu](x * scale[n, c] + shift[n, c]). One read + one write pass (the stand-alone scheme reads twice).
+// Same thread mapping and chunking as gn_apply_kernel. grid = (pixel chunks, n); block = kNormThreads.
+__global__ void __launch_bounds__(kNormThreads) gn_apply_coef_kernel(const __half* __restrict__ x0, int c0,
+                                                                     const __half* __restrict__ x1, int c1, int P,
+                                                                     int chunk, const float* __restrict__ scale,
+                                                                     const float* __restrict__ shift, int do_silu,
+                                                                     __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int C = c0 + c1;
+  const int nvec = C / 8;
+  const int n = blockIdx.y;
+  const int p_begin = blockIdx.x * chunk;
+  const int p_end = min(P, p_begin + chunk);
+  const int rpi = blockDim.x / nvec;
+  const int vec = threadIdx.x % nvec;
+  const int rsub = threadIdx.x / nvec;
+  if (rsub >= rpi) return;
+  const int ch = vec * 8;
+  float sc[8], sh[8];
+  {
+    const float4* a = reinterpret_cast<const float4*>(scale + static_cast<size_t>(n) * C + ch);
+    const float4* b = reinterpret_cast<const float4*>(shift + static_cast<size_t>(n) * C + ch);
+    const float4 a0 = __ldg(a), a1 = __ldg(a + 1), b0 = __ldg(b), b1 = __ldg(b + 1);
+    sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+    sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+  }
+  const __half* base = (ch < c0) ? x0 + ch : x1 + (ch - c0);
+  const int ld = (ch < c0) ? c0 : c1;
+  base += static_cast<size_t>(n) * P * ld;
+  __half* o = out + static_cast<size_t>(n) * P * C + ch;
+  gn_apply_rows(base, ld, o, C, p_begin + rsub, p_end, rpi, sc, sh, do_silu);
+}
+
 // Fused single-launch GroupNorm: grid = (CS, n) with cluster dims (CS, 1, 1); block = kNormThreads;
 // dynamic smem = rpi * 2 * C floats.
 __device__ __forceinline__ double ld_dsmem_f64(const double* p, uint32_t rank) {
@@ -320,6 +355,63 @@ __global__ void __launch_bounds__(kNormThreads) gn_fused_cluster_kernel(const __
     gn_apply_rows(base, ld, o, C, p_begin + rsub, p_end, rpi, sc, sh, do_silu);
   }
   cluster_wait();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GroupNorm from PRODUCER statistics (gemm_tc.cuh header): the kernel that wrote the tensor left, per 64-row tile half
+// and channel, (sum, sum of squares) of the fp16 values in part[rows][C]; the rows of image n are [n*ppi, (n+1)*ppi).
+// One CTA per (group, image) sums its group's entries in a FIXED order (thread-local sequence, then a fixed shared-memory
+// tree; fp64), and writes the affine coefficients the consumer's transform warps apply:
+//   scale[n, c] = rstd * gamma[c],  shift[n, c] = beta[c] - mean * scale[n, c]      (same formulas as gn_apply_kernel)
+// Two sources = the channel concat of the skip connection (openaimodel.py:781); their tables may have different ppi.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kGnFinalizeThreads = 128;
+__global__ void __launch_bounds__(kGnFinalizeThreads) gn_finalize_kernel(const float2* __restrict__ part0, int ppi0, int c0,
+                                                                         const float2* __restrict__ part1, int ppi1, int c1,
+                                                                         double count, float eps,
+                                                                         const float* __restrict__ gamma,
+                                                                         const float* __restrict__ beta,
+                                                                         float* __restrict__ scale,
+                                                                         float* __restrict__ shift) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ double red[2][kGnFinalizeThreads];
+  const int groups = gridDim.x, g = blockIdx.x, n = blockIdx.y;
+  const int C = c0 + c1, cpg = C / groups;
+  const int ch0 = g * cpg;
+  double s = 0.0, q = 0.0;
+  // channels of this group that live in source 0 / source 1 (a group may straddle the concat boundary)
+  const int a0 = min(max(c0 - ch0, 0), cpg);  // first a0 channels of the group are in source 0
+  for (int idx = threadIdx.x; idx < ppi0 * a0; idx += kGnFinalizeThreads) {
+    const int i = idx / a0, c = idx - i * a0;
+    const float2 v = __ldg(part0 + (static_cast<size_t>(n) * ppi0 + i) * c0 + ch0 + c);
+    s += static_cast<double>(v.x);
+    q += static_cast<double>(v.y);
+  }
+  const int a1 = cpg - a0;
+  const int ch1 = ch0 + a0 - c0;  // first channel of the group inside source 1
+  for (int idx = threadIdx.x; idx < ppi1 * a1; idx += kGnFinalizeThreads) {
+    const int i = idx / a1, c = idx - i * a1;
+    const float2 v = __ldg(part1 + (static_cast<size_t>(n) * ppi1 + i) * c1 + ch1 + c);
+    s += static_cast<double>(v.x);
+    q += static_cast<double>(v.y);
+  }
+  red[0][threadIdx.x] = s;
+  red[1][threadIdx.x] = q;
+  __syncthreads();
+  for (int o = kGnFinalizeThreads / 2; o > 0; o >>= 1) {
+    if (static_cast<int>(threadIdx.x) < o) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + o];
+      red[1][threadIdx.x] += red[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  const float2 mr = gn_finalize(red[0][0], red[1][0], count, eps);
+  for (int c = threadIdx.x; c < cpg; c += kGnFinalizeThreads) {
+    const float sc = mr.y * gamma[ch0 + c];
+    scale[static_cast<size_t>(n) * C + ch0 + c] = sc;
+    shift[static_cast<size_t>(n) * C + ch0 + c] = beta[ch0 + c] - mr.x * sc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------

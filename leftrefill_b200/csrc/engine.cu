@@ -62,6 +62,9 @@ struct Node {
 struct Act {
   __half* p = nullptr;
   int C = 0, H = 0, W = 0;
+  // GroupNorm statistics left by the producing kernel (gemm_tc.cuh header): [n * ppi][C] float2 partials, or nullptr
+  float* stats = nullptr;
+  int ppi = 0;
 };
 
 struct Pool {
@@ -456,7 +459,93 @@ struct lr_unet {
     *out = static_cast<float*>(p);
     return 0;
   }
-  int add_conv_step(const ConvSpec& s_in) {
+  // Statistics tables live exactly as long as the activation buffer they describe.
+  std::map<const void*, void*> stats_of;
+  void release(void* p) {
+    auto it = stats_of.find(p);
+    if (it != stats_of.end()) {
+      pool.release(it->second);
+      stats_of.erase(it);
+    }
+    pool.release(p);
+  }
+  // GroupNorm sites. Three implementations exist (gemm_tc.cuh header and profiles/r2_ab_gn_fusion.txt have the
+  // measurements behind the defaults):
+  //   1. consumer-fused: statistics from the producer's epilogue, gn_finalize_kernel, and the consuming GEMM applies the
+  //      affine map in shared memory (transform warps). Default for SpatialTransformer norm -> proj_in on images of at
+  //      least gn_fuse_linear_min_rows tokens (64x128 latents: +17 us on the GEMM instead of a 42 us pass); 3x3 convs
+  //      only with LR_GN_FUSE_CONV=1 (the SiLU of 11.5 K elements per k-chunk outlasts the chunk's MMAs).
+  //   2. coefficient apply (LR_GN_COEF_APPLY=1): producer statistics + ONE read / ONE write pass (gn_apply_coef_kernel);
+  //      measured 28 + 4 us against 42 us at the top level, nothing below it: off by default.
+  //   3. the stand-alone kernels (elementwise.cuh): everything else.
+  bool gn_fuse = getenv("LR_NO_GN_FUSE") == nullptr;
+  bool gn_fuse_conv = gn_fuse && getenv("LR_GN_FUSE_CONV") != nullptr && atoi(getenv("LR_GN_FUSE_CONV")) != 0;
+  bool gn_coef_apply = gn_fuse && getenv("LR_GN_COEF_APPLY") != nullptr && atoi(getenv("LR_GN_COEF_APPLY")) != 0;
+  int gn_fuse_linear_min_rows = getenv("LR_GN_FUSE_LINEAR_MIN_ROWS") ? atoi(getenv("LR_GN_FUSE_LINEAR_MIN_ROWS")) : 4096;
+  bool stats_all() const { return gn_fuse_conv || gn_coef_apply; }  // every GroupNorm input gets producer statistics
+  bool st_fused(int P) const { return gn_fuse && P >= gn_fuse_linear_min_rows; }
+  bool next_is_fused_st = false;  // set by plan_block: the ResBlock being planned feeds a consumer-fused norm
+  // GroupNorm [+ SiLU] of concat(x0, x1) into `out` by way 2 or 3
+  int add_gn_auto(const Act& x0, const Act& x1, int n, float eps, const float* g, const float* b, int silu, __half* out) {
+    float *sc = nullptr, *sh = nullptr;
+    int err = 0;
+    if (gn_coef_apply && plan_gn_coef(x0, x1, n, eps, g, b, &sc, &sh, &err)) {
+      const __half* p0 = x0.p;
+      const __half* p1 = x1.p;
+      const int c0 = x0.C, c1 = x1.C, P = x0.H * x0.W;
+      push([=](cudaStream_t st) { return launch_gn_apply_coef(p0, c0, p1, c1, n, P, sc, sh, silu, out, st); }, 2, 0.0,
+           "gn-apply n=" + std::to_string(n) + " P=" + std::to_string(P) + " c=" + std::to_string(c0) + "+" +
+               std::to_string(c1));
+      release(sc);
+      release(sh);
+      return 0;
+    }
+    LR_TRY(err);
+    return add_gn(x0.p, x0.C, x1.p, x1.C, n, x0.H * x0.W, eps, g, b, silu, out);
+  }
+  // Requests producer statistics for the output of conv spec `s` ([n_tab images] table so that a CFG-shared prefix can be
+  // replicated); call before add_conv_step, then finish_stats with the built op.
+  int want_stats(ConvSpec* s, int n_tab_factor = 1, bool needed = false) {
+    s->stats_out = nullptr;
+    if (!gn_fuse || !(needed || stats_all()) || s->ncols % 8 != 0) return 0;
+    const size_t rows = conv_stats_rows(*s) * n_tab_factor;
+    if (rows == 0) return 0;
+    float* t;
+    LR_TRY(acquire_f(rows * s->ncols * 2, &t));
+    s->stats_out = t;
+    return 0;
+  }
+  void finish_stats(const ConvSpec& s, const ConvOp* op, Act* out) {
+    if (s.stats_out == nullptr) return;
+    if (op->stats_ok) {
+      out->stats = s.stats_out;
+      out->ppi = op->stats_ppi;
+      stats_of[out->p] = s.stats_out;
+    } else {
+      pool.release(s.stats_out);
+    }
+  }
+  // GroupNorm site whose consumer applies the affine map itself: combines the producers' partials into scale / shift
+  // [n][c0 + c1]. Returns false (nothing planned) when a source has no statistics.
+  bool plan_gn_coef(const Act& x0, const Act& x1, int n, float eps, const float* g, const float* b, float** scale,
+                    float** shift, int* err) {
+    *err = 0;
+    if (!gn_fuse || x0.stats == nullptr || (x1.p != nullptr && x1.stats == nullptr)) return false;
+    const int C = x0.C + x1.C;
+    float *sc, *sh;
+    if ((*err = acquire_f(static_cast<size_t>(n) * C, &sc)) != 0) return false;
+    if ((*err = acquire_f(static_cast<size_t>(n) * C, &sh)) != 0) return false;
+    const float* p0 = x0.stats;
+    const float* p1 = x1.stats;
+    const int ppi0 = x0.ppi, ppi1 = x1.ppi, c0 = x0.C, c1 = x1.C, P = x0.H * x0.W;
+    push([=](cudaStream_t st) { return launch_gn_finalize(p0, ppi0, c0, p1, ppi1, c1, n, P, 32, eps, g, b, sc, sh, st); },
+         2, 0.0, "gn-finalize n=" + std::to_string(n) + " P=" + std::to_string(P) + " c=" + std::to_string(c0) + "+" +
+                     std::to_string(c1));
+    *scale = sc;
+    *shift = sh;
+    return true;
+  }
+  int add_conv_step(const ConvSpec& s_in, ConvOp** out_op = nullptr) {
     ConvSpec s = s_in;
     void* ws = nullptr;
     if (s.taps == 9 && s.workspace == nullptr) {
@@ -472,15 +561,17 @@ struct lr_unet {
     }
     auto op = std::make_unique<ConvOp>();
     LR_TRY(build_conv_op(op.get(), s));
-    if (ws) pool.release(ws);
+    if (ws) release(ws);
     flops += op->flops;
     ConvOp* raw = op.get();
+    if (out_op) *out_op = raw;
     conv_ops.push_back(std::move(op));
     char d[200];
-    snprintf(d, sizeof(d), "%s n=%d %dx%d s%d c=%d+%d->%d%s bn=%d st=%d tiles=%d%s",
+    snprintf(d, sizeof(d), "%s n=%d %dx%d s%d c=%d+%d->%d%s bn=%d st=%d tiles=%d%s%s%s",
              s.taps == 9 ? "conv3x3" : "linear", s.n_img, s.in_h, s.in_w, s.stride, s.c0, s.c1, s.ncols,
              s.geglu ? " geglu" : (s.residual ? " +res" : ""), raw->block_n, raw->stages, raw->tiles,
-             raw->ksplit > 1 ? " splitK3" : "");
+             raw->ksplit > 1 ? " splitK3" : "", raw->xf ? (s.xf_silu ? " gn+silu" : " gn") : "",
+             raw->stats_ok ? " stats" : "");
     push([raw](cudaStream_t st) { return launch_conv_op(*raw, st); }, 0, raw->flops, d);
     return 0;
   }
@@ -558,23 +649,38 @@ struct lr_unet {
     });
   }
 
+  // ... and its statistics table: the rows of the first `ns` images are replicated for the second half
+  void add_dup_stats(const Act& a, int ns) {
+    if (a.stats == nullptr) return;
+    float* t = a.stats;
+    const size_t half = static_cast<size_t>(ns) * a.ppi * a.C * 2;  // floats
+    push([=](cudaStream_t st) {
+      cudaError_t e = cudaMemcpyAsync(t + half, t, half * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) {
+        set_error(std::string("cudaMemcpyAsync(dup stats): ") + cudaGetErrorString(e));
+        return 1;
+      }
+      return 0;
+    });
+  }
+
   // ResBlock._forward (openaimodel.py:254-274), x = concat(x0, x1) when x1.p != nullptr
+  //
+  // GroupNorm + SiLU of both halves are fused into the convs that consume them whenever the producers left statistics
+  // and the conv runs in halo mode (gemm_tc.cuh header): no normalised tensor is written or re-read. Otherwise (the
+  // 8x16 level, whose convs run split-K on 128-pixel images, and tiny test shapes) the stand-alone kernel runs.
   int plan_res(const ResW& r, Act x0, Act x1, int n_full, Act* out) {
     const int Hh = x0.H, Ww = x0.W, P = Hh * Ww;
     // inside the shared CFG prefix only the first shared_ns images are computed (buffers stay full size)
     const int n = shared_ns > 0 ? shared_ns : n_full;
+    const int tab = n_full / n;  // statistics tables are sized for the full batch (the prefix is replicated afterwards)
     const size_t M = static_cast<size_t>(n) * P;
     const size_t Mfull = static_cast<size_t>(n_full) * P;
     LR_CHECK(x0.C + x1.C == r.cin, "resblock: channel mismatch");
-    __half *xn, *h, *hn, *o, *skip = nullptr;
-    LR_TRY(acquire_h(M * r.cin, &xn));
-    LR_TRY(add_gn(x0.p, x0.C, x1.p, x1.C, n, P, 1e-5f, F(r.gn1_g), F(r.gn1_b), 1, xn));
-    LR_TRY(acquire_h(M * r.cout, &h));
+    __half *xn = nullptr, *h, *hn = nullptr, *o, *skip = nullptr;
+    Act hact;
     {
       ConvSpec s;
-      s.a0 = xn;
-      s.c0 = r.cin;
-      s.lda0 = r.cin;
       s.n_img = n;
       s.in_h = Hh;
       s.in_w = Ww;
@@ -585,14 +691,39 @@ struct lr_unet {
       s.bias = F(r.conv1_b);
       s.bias_img = emb_all + r.emb_col0;
       s.ld_bias_img = emb_total;
-      s.out = h;
       s.ld_out = r.cout;
-      LR_TRY(add_conv_step(s));
+      float *sc = nullptr, *sh = nullptr;
+      int err = 0;
+      const bool fused = gn_fuse_conv && conv_is_halo(s) &&
+                         plan_gn_coef(x0, x1, n, 1e-5f, F(r.gn1_g), F(r.gn1_b), &sc, &sh, &err);
+      LR_TRY(err);
+      if (fused) {
+        s.a0 = x0.p;
+        s.c0 = x0.C;
+        s.lda0 = x0.C;
+        s.a1 = x1.p;
+        s.c1 = x1.C;
+        s.lda1 = x1.C;
+        s.xf_scale = sc;
+        s.xf_shift = sh;
+        s.xf_silu = 1;
+      } else {
+        LR_TRY(acquire_h(M * r.cin, &xn));
+        LR_TRY(add_gn_auto(x0, x1, n, 1e-5f, F(r.gn1_g), F(r.gn1_b), 1, xn));
+        s.a0 = xn;
+        s.c0 = r.cin;
+        s.lda0 = r.cin;
+      }
+      LR_TRY(acquire_h(M * r.cout, &h));
+      s.out = h;
+      hact = Act{h, r.cout, Hh, Ww};
+      LR_TRY(want_stats(&s));
+      ConvOp* op;
+      LR_TRY(add_conv_step(s, &op));
+      finish_stats(s, op, &hact);
+      if (xn) release(xn);
+      if (sc) { release(sc); release(sh); }
     }
-    pool.release(xn);
-    LR_TRY(acquire_h(M * r.cout, &hn));
-    LR_TRY(add_gn(h, r.cout, nullptr, 0, n, P, 1e-5f, F(r.gn2_g), F(r.gn2_b), 1, hn));
-    pool.release(h);
     const __half* resid;
     if (r.has_skip) {
       LR_TRY(acquire_h(M * r.cout, &skip));
@@ -620,9 +751,9 @@ struct lr_unet {
       resid = x0.p;
     }
     LR_TRY(acquire_h(Mfull * r.cout, &o));
+    Act oact{o, r.cout, Hh, Ww};
     {
       ConvSpec s;
-      s.a0 = hn;
       s.c0 = r.cout;
       s.lda0 = r.cout;
       s.n_img = n;
@@ -637,14 +768,31 @@ struct lr_unet {
       s.ld_res = r.cout;
       s.out = o;
       s.ld_out = r.cout;
-      LR_TRY(add_conv_step(s));
+      float *sc = nullptr, *sh = nullptr;
+      int err = 0;
+      const bool fused = gn_fuse_conv && conv_is_halo(s) &&
+                         plan_gn_coef(hact, Act{}, n, 1e-5f, F(r.gn2_g), F(r.gn2_b), &sc, &sh, &err);
+      LR_TRY(err);
+      if (fused) {
+        s.a0 = h;
+        s.xf_scale = sc;
+        s.xf_shift = sh;
+        s.xf_silu = 1;
+      } else {
+        LR_TRY(acquire_h(M * r.cout, &hn));
+        LR_TRY(add_gn_auto(hact, Act{}, n, 1e-5f, F(r.gn2_g), F(r.gn2_b), 1, hn));
+        s.a0 = hn;
+      }
+      LR_TRY(want_stats(&s, tab, next_is_fused_st));
+      ConvOp* op;
+      LR_TRY(add_conv_step(s, &op));
+      finish_stats(s, op, &oact);
+      if (hn) release(hn);
+      if (sc) { release(sc); release(sh); }
     }
-    pool.release(hn);
-    if (skip) pool.release(skip);
-    out->p = o;
-    out->C = r.cout;
-    out->H = Hh;
-    out->W = Ww;
+    release(h);
+    if (skip) release(skip);
+    *out = oact;
     return 0;
   }
 
@@ -659,11 +807,43 @@ struct lr_unet {
     int n = shared_ns > 0 ? shared_ns : n_full;
     int M = n * P;
     __half *xn, *h, *t, *qkv, *a, *g, *o;
-    LR_TRY(acquire_h(static_cast<size_t>(Mfull) * C, &xn));
-    LR_TRY(add_gn(x.p, C, nullptr, 0, n, P, 1e-6f, F(s.gn_g), F(s.gn_b), 0, xn));
     LR_TRY(acquire_h(static_cast<size_t>(Mfull) * C, &h));
-    LR_TRY(add_linear(xn, M, C, H(s.pin_w), C, F(s.pin_b), nullptr, 0, h, C, 0));
-    pool.release(xn);
+    {
+      // norm (GroupNorm eps 1e-6, no activation) -> proj_in (attention.py:399-404): the affine map is applied to the
+      // activation tiles of the proj_in GEMM in shared memory when the producer of x left statistics
+      float *sc = nullptr, *sh = nullptr;
+      int err = 0;
+      const bool fused = st_fused(P) && plan_gn_coef(x, Act{}, n, 1e-6f, F(s.gn_g), F(s.gn_b), &sc, &sh, &err);
+      LR_TRY(err);
+      if (fused) {
+        ConvSpec cs;
+        cs.a0 = x.p;
+        cs.c0 = C;
+        cs.lda0 = C;
+        cs.n_img = 1;
+        cs.in_h = 1;
+        cs.in_w = M;
+        cs.taps = 1;
+        cs.w = H(s.pin_w);
+        cs.ldw = C;
+        cs.ncols = C;
+        cs.bias = F(s.pin_b);
+        cs.out = h;
+        cs.ld_out = C;
+        cs.xf_scale = sc;
+        cs.xf_shift = sh;
+        cs.xf_silu = 0;
+        cs.xf_rows_per_img = P;
+        LR_TRY(add_conv_step(cs));
+        release(sc);
+        release(sh);
+      } else {
+        LR_TRY(acquire_h(static_cast<size_t>(Mfull) * C, &xn));
+        LR_TRY(add_gn_auto(x, Act{}, n, 1e-6f, F(s.gn_g), F(s.gn_b), 0, xn));
+        LR_TRY(add_linear(xn, M, C, H(s.pin_w), C, F(s.pin_b), nullptr, 0, h, C, 0));
+        release(xn);
+      }
+    }
     LR_TRY(acquire_h(static_cast<size_t>(Mfull) * C, &t));
     LR_TRY(acquire_h(static_cast<size_t>(Mfull) * C, &a));
     float* lnst;  // (mean, rstd) per token row for the folded LayerNorms
@@ -720,11 +900,11 @@ struct lr_unet {
           __half* hdst = h;
           push([=](cudaStream_t st) { return launch_mv_scatter(o_r, C, bs, v, hh, side, hdst, st); });
         }
-        pool.release(qkv_r);
-        pool.release(a_r);
-        pool.release(h_r);
-        pool.release(o_r);
-        pool.release(qkv);
+        release(qkv_r);
+        release(a_r);
+        release(h_r);
+        release(o_r);
+        release(qkv);
       } else {
         // multiview (multiview_attention.py:448,462, concat_target=False): '(b v) hw c -> b (v hw) c' is a pure
         // reshape of the token matrix, so only batch / sequence length change.
@@ -738,7 +918,7 @@ struct lr_unet {
         as.batch = n / v; as.heads = s.heads; as.tq = P * v; as.tk = P * v;
         as.scale = 0.125f;
         LR_TRY(add_attn(as));
-        pool.release(qkv);
+        release(qkv);
         LR_TRY(add_linear(a, M, C, H(b.out1_w), C, F(b.out1_b), h, C, h, C, 0));
       }
       if (first_block && n != n_full) {  // end of the shared prefix: replicate the residual stream and the ST input
@@ -768,7 +948,7 @@ struct lr_unet {
         as.scale = 0.125f;
         LR_TRY(add_attn(as));
       }
-      pool.release(q2);
+      release(q2);
       LR_TRY(add_linear(a, M, C, H(b.out2_w), C, F(b.out2_b), h, C, h, C, 0));
       // GEGLU feed-forward
       LR_TRY(acquire_h(static_cast<size_t>(M) * 4 * C, &g));
@@ -780,18 +960,39 @@ struct lr_unet {
         LR_TRY(add_linear(t, M, C, H(b.ff1_w), 8 * C, F(b.ff1_b), nullptr, 0, g, 4 * C, 1));
       }
       LR_TRY(add_linear(g, M, 4 * C, H(b.ff2_w), C, F(b.ff2_b), h, C, h, C, 0));
-      pool.release(g);
+      release(g);
     }
-    pool.release(t);
-    pool.release(a);
-    pool.release(lnst);
+    release(t);
+    release(a);
+    release(lnst);
     LR_TRY(acquire_h(static_cast<size_t>(M) * C, &o));
-    LR_TRY(add_linear(h, M, C, H(s.pout_w), C, F(s.pout_b), x.p, C, o, C, 0));
-    pool.release(h);
-    out->p = o;
-    out->C = C;
-    out->H = x.H;
-    out->W = x.W;
+    Act oact{o, C, x.H, x.W};
+    {
+      // proj_out (+ the transformer's input as residual): its output feeds the next ResBlock's GroupNorm
+      ConvSpec cs;
+      cs.a0 = h;
+      cs.c0 = C;
+      cs.lda0 = C;
+      cs.n_img = 1;
+      cs.in_h = 1;
+      cs.in_w = M;
+      cs.taps = 1;
+      cs.w = H(s.pout_w);
+      cs.ldw = C;
+      cs.ncols = C;
+      cs.bias = F(s.pout_b);
+      cs.residual = x.p;
+      cs.ld_res = C;
+      cs.out = o;
+      cs.ld_out = C;
+      cs.stats_rows_per_img = P;
+      LR_TRY(want_stats(&cs));
+      ConvOp* op;
+      LR_TRY(add_conv_step(cs, &op));
+      finish_stats(cs, op, &oact);
+    }
+    release(h);
+    *out = oact;
     return 0;
   }
 
@@ -814,11 +1015,12 @@ struct lr_unet {
     LR_TRY(acquire_h(static_cast<size_t>(n) * Ho * Wo * c.cout, &o));
     s.out = o;
     s.ld_out = c.cout;
-    LR_TRY(add_conv_step(s));
-    out->p = o;
-    out->C = c.cout;
-    out->H = Ho;
-    out->W = Wo;
+    Act oact{o, c.cout, Ho, Wo};
+    LR_TRY(want_stats(&s));
+    ConvOp* op;
+    LR_TRY(add_conv_step(s, &op));
+    finish_stats(s, op, &oact);
+    *out = oact;
     return 0;
   }
 
@@ -829,7 +1031,9 @@ struct lr_unet {
       Act nxt;
       const Node& nd = blk[i];
       if (nd.kind == N_RES) {
+        next_is_fused_st = i + 1 < blk.size() && blk[i + 1].kind == N_ST && st_fused(cur.H * cur.W);
         LR_TRY(plan_res(res[nd.idx], cur, (i == 0) ? skip : Act{}, n, &nxt));
+        next_is_fused_st = false;
       } else if (nd.kind == N_ST) {
         LR_TRY(plan_st(sts[nd.idx], cur, n, &nxt));
       } else if (nd.kind == N_DOWN) {
@@ -843,12 +1047,12 @@ struct lr_unet {
         push([=](cudaStream_t st) { return launch_upsample2x(src, n, hh, ww, cc, up, st); });
         Act u{up, cur.C, 2 * cur.H, 2 * cur.W};
         LR_TRY(plan_conv3(convs[nd.idx], u, n, 1, &nxt));
-        pool.release(up);
+        release(up);
       } else {
         LR_CHECK(false, "unexpected node");
       }
-      if (cur_owned || (i == 0 && release_input)) pool.release(cur.p);
-      if (i == 0 && skip.p != nullptr) pool.release(skip.p);
+      if (cur_owned || (i == 0 && release_input)) release(cur.p);
+      if (i == 0 && skip.p != nullptr) release(skip.p);
       cur = nxt;
       cur_owned = true;
     }
@@ -885,12 +1089,12 @@ struct lr_unet {
     Act hs_, ss_{};
     LR_TRY(plan_sep_insert(h, F(it->second), n, &hs_));
     if (skip.p != nullptr) LR_TRY(plan_sep_insert(skip, F(it->second) + h.C, n, &ss_));
-    if (release_input) pool.release(h.p);
-    if (skip.p != nullptr) pool.release(skip.p);
+    if (release_input) release(h.p);
+    if (skip.p != nullptr) release(skip.p);
     Act t;
     LR_TRY(plan_block(blk, hs_, ss_, n, &t, true));  // releases the two widened copies
     LR_TRY(plan_sep_remove(t, n, out));
-    pool.release(t.p);
+    release(t.p);
     return 0;
   }
 
@@ -978,6 +1182,7 @@ struct lr_unet {
     conv_ops.clear();
     attn_ops.clear();
     pool.clear();
+    stats_of.clear();
     flops = 0;
     pn = 0;
     const int mc = cfg.model_channels, temb = 4 * mc;
@@ -1037,7 +1242,7 @@ struct lr_unet {
         const float* sp = F(it->second);
         push([=](cudaStream_t st) { return launch_sep_insert_nchw_f32(this->in_x, sp, ns, cin, Hh, Ww, xsep, st); });
         push([=](cudaStream_t st) { return launch_im2col_nchw_f32(xsep, ns, cin, Hh, Wh, kp, col, st); });
-        pool.release(xsep);
+        release(xsep);
       } else {
         push(
             [=](cudaStream_t st) { return launch_im2col_nchw_f32(this->in_x, ns, cin, Hh, Ww, kp, col, st); });
@@ -1049,16 +1254,36 @@ struct lr_unet {
       LR_TRY(acquire_h(M0h * mc, &o));
       const ConvW& c = convs[conv_in_idx];
       // c_input (NVS_ldm.py:64-68) is added to the input conv's output BEFORE the separator is removed
-      LR_TRY(add_linear(col, static_cast<int>(M0hs), kpad_in, H(c.w), mc, F(c.b), cin_on ? cin_h : nullptr, mc, o, mc, 0));
+      ConvSpec cs;
+      cs.a0 = col;
+      cs.c0 = kpad_in;
+      cs.lda0 = kpad_in;
+      cs.n_img = 1;
+      cs.in_h = 1;
+      cs.in_w = static_cast<int>(M0hs);
+      cs.taps = 1;
+      cs.w = H(c.w);
+      cs.ldw = kpad_in;
+      cs.ncols = mc;
+      cs.bias = F(c.b);
+      cs.residual = cin_on ? cin_h : nullptr;
+      cs.ld_res = mc;
+      cs.out = o;
+      cs.ld_out = mc;
+      cs.stats_rows_per_img = Hh * Wh;
       h = Act{o, mc, Hh, Wh};
+      if (!cfg.use_sep) LR_TRY(want_stats(&cs, n / ns));  // (with use_sep the separator column is cut out again below)
+      ConvOp* op;
+      LR_TRY(add_conv_step(cs, &op));
+      finish_stats(cs, op, &h);
       if (cfg.use_sep) {
         Act t;
         LR_TRY(plan_sep_remove(h, n, &t));
-        pool.release(h.p);
+        release(h.p);
         h = t;
       }
     }
-    pool.release(col);
+    release(col);
     std::vector<Act> hs{h};
     for (size_t i = 1; i < input_blocks.size(); ++i) {
       Act o;
@@ -1073,8 +1298,10 @@ struct lr_unet {
           LR_TRY(plan_block(input_blocks[1], h, Act{}, n, &o, false));
           shared_ns = 0;
           add_dup_half(o.p, M0s * o.C);
+          add_dup_stats(o, ns);
         }
         add_dup_half(hs[0].p, M0s * mc);  // conv_in output: also a skip connection for both halves
+        add_dup_stats(hs[0], ns);
       } else {
         LR_TRY(plan_block_sep(input_blocks[i], h, Act{}, n, &o, false));
       }
@@ -1097,13 +1324,29 @@ struct lr_unet {
     }
     // --- head: GroupNorm32 -> SiLU -> conv3x3 (openaimodel.py:727-731,787) ---
     {
-      __half *hn, *y;
-      LR_TRY(acquire_h(M0 * mc, &hn));
-      LR_TRY(add_gn(h.p, mc, nullptr, 0, n, Hh * Ww, 1e-5f, F(head_gn_g), F(head_gn_b), 1, hn));
+      __half *hn = nullptr, *y;
       const ConvW& c = convs[head_idx];
       LR_TRY(acquire_h(M0 * c.cout, &y));
       ConvSpec s;
-      s.a0 = hn;
+      s.n_img = n;
+      s.in_h = Hh;
+      s.in_w = Ww;
+      s.taps = 9;
+      float *sc = nullptr, *sh = nullptr;
+      int err = 0;
+      const bool fused = gn_fuse_conv && conv_is_halo(s) &&
+                         plan_gn_coef(h, Act{}, n, 1e-5f, F(head_gn_g), F(head_gn_b), &sc, &sh, &err);
+      LR_TRY(err);
+      if (fused) {
+        s.a0 = h.p;
+        s.xf_scale = sc;
+        s.xf_shift = sh;
+        s.xf_silu = 1;
+      } else {
+        LR_TRY(acquire_h(M0 * mc, &hn));
+        LR_TRY(add_gn_auto(h, Act{}, n, 1e-5f, F(head_gn_g), F(head_gn_b), 1, hn));
+        s.a0 = hn;
+      }
       s.c0 = mc;
       s.lda0 = mc;
       s.n_img = n;
@@ -1424,6 +1667,101 @@ int lr_conv3x3_f16(const void* x0, int c0, const void* x1, int c1, int n, int h,
   ConvOp op;
   LR_TRY(build_conv_op(&op, s));
   return launch_conv_op(op, static_cast<cudaStream_t>(stream));
+}
+
+// ---- GroupNorm fusion, op level (gemm_tc.cuh header) -------------------------------------------------------------
+long long lr_conv_stats_rows(int n, int h, int w, int stride, int taps, int rows_per_img) {
+  ConvSpec s;
+  s.n_img = n;
+  s.in_h = h;
+  s.in_w = w;
+  s.stride = stride;
+  s.taps = taps;
+  s.stats_rows_per_img = rows_per_img;
+  return static_cast<long long>(conv_stats_rows(s));
+}
+
+int lr_gn_conv3x3_f16(const void* x0, int c0, const void* x1, int c1, int n, int h, int w, const float* gn_scale,
+                      const float* gn_shift, int silu, const void* wt, int cout, const float* bias, const float* bias_img,
+                      const void* residual, void* out, float* stats_out, int* stats_ppi, int force_block_n, void* stream) {
+  if (stats_ppi) *stats_ppi = 0;
+  if (n == 0) return 0;
+  ConvSpec s;
+  s.a0 = static_cast<const __half*>(x0);
+  s.c0 = c0;
+  s.lda0 = c0;
+  s.a1 = static_cast<const __half*>(x1);
+  s.c1 = x1 ? c1 : 0;
+  s.lda1 = c1;
+  s.n_img = n;
+  s.in_h = h;
+  s.in_w = w;
+  s.stride = 1;
+  s.taps = 9;
+  s.w = static_cast<const __half*>(wt);
+  s.ldw = 9 * (c0 + s.c1);
+  s.ncols = cout;
+  s.bias = bias;
+  s.bias_img = bias_img;
+  s.residual = static_cast<const __half*>(residual);
+  s.ld_res = cout;
+  s.out = static_cast<__half*>(out);
+  s.ld_out = cout;
+  s.force_block_n = force_block_n % 1000;
+  s.force_cg = force_block_n / 1000;
+  s.xf_scale = gn_scale;
+  s.xf_shift = gn_shift;
+  s.xf_silu = silu;
+  s.stats_out = stats_out;
+  LR_CHECK(gn_scale == nullptr || conv_is_halo(s),
+           "lr_gn_conv3x3_f16: the fused GroupNorm transform needs an image of at least 16 rows x 8 columns (halo mode)");
+  ConvOp op;
+  LR_TRY(build_conv_op(&op, s));
+  if (stats_ppi) *stats_ppi = op.stats_ok ? op.stats_ppi : 0;
+  return launch_conv_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int lr_gn_linear_f16(const void* a, int M, int K, int rows_per_img, const float* gn_scale, const float* gn_shift,
+                     int silu, const void* w, int n_cols, const float* bias, const void* residual, void* out,
+                     float* stats_out, int* stats_ppi, int force_block_n, void* stream) {
+  if (stats_ppi) *stats_ppi = 0;
+  if (M == 0) return 0;
+  ConvSpec s;
+  s.a0 = static_cast<const __half*>(a);
+  s.c0 = K;
+  s.lda0 = K;
+  s.n_img = 1;
+  s.in_h = 1;
+  s.in_w = M;
+  s.taps = 1;
+  s.w = static_cast<const __half*>(w);
+  s.ldw = K;
+  s.ncols = n_cols;
+  s.bias = bias;
+  s.residual = static_cast<const __half*>(residual);
+  s.ld_res = n_cols;
+  s.out = static_cast<__half*>(out);
+  s.ld_out = n_cols;
+  s.force_block_n = force_block_n % 1000;
+  s.force_cg = force_block_n / 1000;
+  s.xf_scale = gn_scale;
+  s.xf_shift = gn_shift;
+  s.xf_silu = silu;
+  s.xf_rows_per_img = rows_per_img;
+  s.stats_out = stats_out;
+  s.stats_rows_per_img = rows_per_img;
+  ConvOp op;
+  LR_TRY(build_conv_op(&op, s));
+  if (stats_ppi) *stats_ppi = op.stats_ok ? op.stats_ppi : 0;
+  return launch_conv_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int lr_gn_finalize(const float* part0, int ppi0, int c0, const float* part1, int ppi1, int c1, int n, int P, int groups,
+                   float eps, const float* gamma, const float* beta, float* scale, float* shift, void* stream) {
+  LR_CHECK(part0 && gamma && beta && scale && shift, "lr_gn_finalize: null argument");
+  if (n == 0) return 0;
+  return launch_gn_finalize(part0, ppi0, c0, part1, part1 ? ppi1 : 0, part1 ? c1 : 0, n, P, groups, eps, gamma, beta, scale,
+                            shift, static_cast<cudaStream_t>(stream));
 }
 
 int lr_attention_f16(const void* q, int ldq, int q_col0, const void* k, int ldk, int k_col0, const void* v, int ldv,

@@ -29,6 +29,26 @@
 //                                         residual (prefetched one chunk ahead) / GEGLU -> fp16 tile staged in
 //                                         swizzled smem -> TMA store (full 128 B lines; per-thread 16 B row-strided
 //                                         global stores made the kernel epilogue-bound for K <= ~3000)
+//
+// GroupNorm fusion (round 2; reference ResBlock in_layers / out_layers = GroupNorm32 -> SiLU -> conv, openaimodel.py:200-204,
+// 224-231,254-274, and SpatialTransformer norm -> proj_in, attention.py:399-404): a GroupNorm is an affine map per
+// (image, channel), y = x * a[n, c] + b[n, c], once its statistics are known. Neither half needs its own pass:
+//   * STATISTICS come from the PRODUCER: the epilogue that writes a tensor also sums, per output tile half (64 rows) and
+//     channel, (sum x, sum x^2) of the fp16 values it staged for the TMA store and writes them to a fixed slot of a
+//     partials table (GemmParams::stats_out). gn_finalize_kernel (elementwise.cuh) combines the slots of an image in a
+//     fixed order (bit-reproducible, batch invariant) into a[n, c], b[n, c].
+//   * APPLY (+ SiLU) can happen in the CONSUMER (template parameter XF): four extra "transform" warps apply the affine
+//     map [and the SiLU] IN PLACE in shared memory on every activation tile the TMA producer lands, before the MMA warp
+//     may read it (barrier xready). In halo mode one (8+2) x (16+2) box serves all nine taps, so every element is
+//     transformed once per output tile - not once per tap - and the out-of-image halo is re-zeroed after the affine map
+//     (the conv pads the NORMALISED tensor with zeros).
+//     Measured on B200 (profiles/r2_ab_gn_fusion.txt): for the Linear consumers (SpatialTransformer norm -> proj_in, no
+//     SiLU) this costs +13 us on a 40 us GEMM and replaces a 42 us GroupNorm pass: the engine uses it. For the 3x3
+//     convs (GroupNorm + SiLU of 180 x 64 elements per k-chunk) four transform warps run at ~0.15 IPC and take longer
+//     than the MMAs of the chunk (120 us vs 83 us at 320->320 @64x128; a variant in which these warps load the tile
+//     from global memory themselves was slower still, 184 us), which is no better than the stand-alone pass; the
+//     engine therefore applies GroupNorm + SiLU for convs with gn_apply_coef_kernel (ONE read + ONE write pass over
+//     the producers' statistics) and keeps the in-kernel conv transform as a tested op-level path (LR_GN_FUSE_CONV=1).
 #pragma once
 #include "ptx.cuh"
 
@@ -88,6 +108,15 @@ struct GemmParams {
   int geglu;               // accumulator columns are (value, gate) pairs -> out[:, j] = v * gelu(g) (attention.py:51-58)
   int n_valid;             // valid output columns (after GEGLU halving)
   float out_scale;         // multiplies the final value (1.0 normally)
+  // ---- GroupNorm fusion (see the header comment) ----
+  const float* xf_scale;   // XF kernels: a[n_img][xf_ld] (rstd * gamma) of the (concatenated) input channels
+  const float* xf_shift;   //             b[n_img][xf_ld] (beta - mean * rstd * gamma)
+  int xf_ld;               // channels of the (concatenated) input
+  int xf_silu;             // 1: SiLU after the affine map
+  int xf_rows_per_img;     // linear geometry: token rows per image (the image index of row m is m / xf_rows_per_img)
+  float2* stats_out;       // [tiles_m * 2][stats_ld] (sum, sum of squares) per tile half (64 rows) and output channel of the
+                           // fp16 values this launch writes, or nullptr. Requires the TMA-store epilogue.
+  int stats_ld;
   int dbg;                 // bring-up experiments only (LR_GEMM_DEBUG): 1 = no A loads, 2 = no B loads, 4 = no MMAs
   unsigned long long* trace;  // LR_GEMM_TRACE: CTA 0 records clock64() per role / tile / phase ([3][16][8]); else null
 };
@@ -114,6 +143,9 @@ struct GemmParams {
 #define LR_STORE_WARP 0
 #endif
 constexpr int kGemmThreads = LR_STORE_WARP ? 352 : 320;
+constexpr int kXfWarps = 4;                                 // transform warps of the XF instantiation (warps 10..13)
+constexpr int kGemmThreadsXf = 320 + kXfWarps * 32;
+static_assert(!LR_STORE_WARP, "the store-warp experiment shares warp 10 with the transform warps");
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kBlockM = 128;
@@ -121,10 +153,11 @@ constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kMaxStages = 8;
 constexpr int kMaxAStages = 4;
+constexpr int kHaloBoxRows = (8 + 2) * (16 + 2);  // pixels of one halo box
 constexpr int kHaloBW = 8, kHaloBH = 16;  // halo-mode output tile: 8 pixels wide x 16 rows
 constexpr int kBarBytes = 512;
 constexpr int kGemmAuxBytes = kBarBytes /*barriers*/ + 4 * 256 * 4 /*bias + LayerNorm column-sum staging, double buffered*/;
-static_assert((2 * kMaxStages + 4 + 2 * kMaxAStages + 6) * 8 + 4 <= kBarBytes, "barrier block overflows");
+static_assert((5 * kMaxStages + 4 + 6) * 8 + 4 <= kBarBytes, "barrier block overflows");
 
 // bytes of one pipeline stage in ONE CTA (cg = CTAs cooperating on a tile: each holds block_n / cg weight rows)
 __host__ __device__ inline int gemm_stage_bytes(int block_n, int cg = 1) {
@@ -153,8 +186,39 @@ struct IntTag {
   static constexpr int value = V;
 };
 
-template <int CG>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid_constant__ GemmParams p) {
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// y = [silu](x * sc + sh) on 8 packed fp16 channels; the result is ANDed with `keep` (all ones / zero). Branch free on
+// purpose: the transform warps have one warp per scheduler, their throughput comes from instruction-level parallelism
+// across the 32 independent elements of four unrolled rows, which per-row branches (reconvergence points) destroy.
+template <bool kSilu>
+__device__ __forceinline__ uint4 xf_apply8(const uint4 v, const float (&sc)[8], const float (&sh)[8], const uint32_t keep) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack_half2(w[i]);
+    float y0 = fmaf(t.x, sc[2 * i], sh[2 * i]);
+    float y1 = fmaf(t.y, sc[2 * i + 1], sh[2 * i + 1]);
+    if (kSilu) {  // x * sigmoid(x) = x * rcp(1 + 2^(-x log2 e)): one MUFU.EX2 + one MUFU.RCP, flush-to-zero forms
+      y0 *= fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * y0));
+      y1 *= fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * y1));
+    }
+    o[i] = pack_half2(y0, y1) & keep;
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+template <int CG, bool XF>
+__global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_conv_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // identical smem offsets in both CTAs of a pair are required (UMMA descriptors / multicast commits use offsets)
   uint8_t* smem = smem_raw;
@@ -166,9 +230,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   uint64_t* empty = bars + kMaxStages;     // [kMaxStages]
   uint64_t* tfull = bars + 2 * kMaxStages; // [2]
   uint64_t* tempty = tfull + 2;            // [2]
-  uint64_t* a_full = tempty + 2;           // [kMaxAStages]  (halo mode)
-  uint64_t* a_empty = a_full + kMaxAStages;  // [kMaxAStages]
-  uint64_t* cfull = a_empty + kMaxAStages;   // [2] staged output tile complete (all epilogue threads arrived)
+  uint64_t* a_full = tempty + 2;           // [kMaxStages]  activation tile landed (halo mode; XF: also the plain mode)
+  uint64_t* a_empty = a_full + kMaxStages;   // [kMaxStages]
+  uint64_t* xready = a_empty + kMaxStages;   // [kMaxStages]  XF: the transform warps (of both CTAs) are done with the tile
+  uint64_t* cfull = xready + kMaxStages;     // [2] staged output tile complete (all epilogue threads arrived)
   uint64_t* cfree = cfull + 2;               // [2] its TMA stores have finished reading the staging buffer
   uint64_t* rfull = cfree + 2;               // [2] residual tile has landed in staging buffer b (res_tma)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2);
@@ -200,9 +265,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kEpiWarps * CG);  // the leader's MMA thread waits for the epilogues of BOTH CTAs
     }
-    for (int i = 0; i < kMaxAStages; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
+      mbar_init(&xready[i], kXfWarps * CG);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&cfull[i], kEpiThreads);
@@ -262,10 +328,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         mbar_wait(&a_empty[sa], pha ^ 1);
         if (elect_one()) {
           uint8_t* a_s = smem + sa * p.a_slot_bytes;
-          if (CG == 2) {
+          if (CG == 2 && !XF) {
             if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * a_tx);
             tma_load_4d_2sm(a_s, ta, &a_full[sa], kch, x0 - 1, y0 - 1, n0);
-          } else {
+          } else {  // XF: every CTA's transform warps wait for their OWN box, so it is credited to the local barrier
             mbar_arrive_expect_tx(&a_full[sa], a_tx);
             tma_load_4d(a_s, ta, &a_full[sa], kch, x0 - 1, y0 - 1, n0);
           }
@@ -326,7 +392,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
             const int kb = tap * p.ctot + (src0 ? 0 : p.c0) + kch;
             const CUtensorMap* ta = src0 ? &p.tmA0 : &p.tmA1;
             const int tx_bytes = ((p.dbg & 1) ? 0 : kATileBytes) + ((p.dbg & 2) ? 0 : stage_bytes - kATileBytes);
-            if (CG == 2) {
+            if (XF) {
+              // activation tile -> this CTA's a_full (its transform warps wait on it); weight tile -> full (leader's)
+              mbar_arrive_expect_tx(&a_full[s], kATileBytes);
+              tma_load_4d(a_s, ta, &a_full[s], kch, x0 + dx, y0 + dy, n0);
+              if (CG == 2) {
+                if (leader) mbar_arrive_expect_tx(&full[s], 2 * (stage_bytes - kATileBytes));
+                tma_load_2d_2sm(b_s, &p.tmB, &full[s], kb, ncol0);
+              } else {
+                mbar_arrive_expect_tx(&full[s], stage_bytes - kATileBytes);
+                tma_load_2d(b_s, &p.tmB, &full[s], kb, ncol0);
+              }
+            } else if (CG == 2) {
               // the leader's barrier collects the bytes of both CTAs
               if (leader) mbar_arrive_expect_tx(&full[s], 2 * tx_bytes);
               if (!(p.dbg & 1)) tma_load_4d_2sm(a_s, ta, &full[s], kch, x0 + dx, y0 + dy, n0);
@@ -368,7 +445,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         const uint32_t d_tmem = tmem_base + as * 256;
         uint32_t started = 0;
         for (int kc = 0; kc < p.kc0 + p.kc1; ++kc) {
-          mbar_wait(&a_full[sa], pha);
+          if (XF) { if (p.dbg & 128) mbar_wait_cluster(&xready[sa], pha); else mbar_wait(&xready[sa], pha); }
+          else mbar_wait(&a_full[sa], pha);
           tc_fence_after();
           if (kc == 0) LR_GEMM_TR(1, tcount, 2);
           for (int tap0 = 0; tap0 < 9; tap0 += kG) {
@@ -434,6 +512,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         const int kiters = ((sp + 1) * p.taps / p.ksplit - sp * p.taps / p.ksplit) * (p.kc0 + p.kc1);
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(&full[s], ph);
+          if (XF) { if (p.dbg & 128) mbar_wait_cluster(&xready[s], ph); else mbar_wait(&xready[s], ph); }
           tc_fence_after();
           if (it == 0) LR_GEMM_TR(1, tcount, 2);
           if (elect_one()) {
@@ -461,9 +540,150 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
+  } else if (XF && warp >= 2 + kEpiWarps) {
+    // ------------------------------- transform warps (GroupNorm apply [+ SiLU] in shared memory) -------------
+    // 128 threads; thread -> (physical 16-byte chunk q of a 128-byte row, rows prow0, prow0 + 16, ...). With the 128B
+    // swizzle the LOGICAL channel chunk of physical chunk q in row r is q ^ (r & 7); rows advance by 16, so it is the
+    // same for all rows of a thread: its 8 scale / shift values are loaded once per 64-channel chunk, before the tile
+    // has landed.
+    const int tt = static_cast<int>(threadIdx.x) - (2 + kEpiWarps) * 32;
+    const int q = tt & 7, prow0 = tt >> 3;
+    const int j8 = (q ^ (prow0 & 7)) * 8;
+    const bool xf_skip = (p.dbg & 64) != 0;  // timing experiment: barrier hand-offs only, no transform work
+    auto load_coef = [&](int img, int kc, float (&sc)[8], float (&sh)[8]) {
+      const bool src0 = kc < p.kc0;
+      const int kch = (src0 ? kc : kc - p.kc0) * kBlockK + j8;       // channel inside its source
+      const int climit = src0 ? p.c0 : p.ctot - p.c0;
+      if (kch + 8 <= climit) {  // channels beyond the source are TMA zero fill and meet zero weights: leave them zero
+        const float* a = p.xf_scale + static_cast<size_t>(img) * p.xf_ld + (src0 ? 0 : p.c0) + kch;
+        const float* b = p.xf_shift + static_cast<size_t>(img) * p.xf_ld + (src0 ? 0 : p.c0) + kch;
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(a)), a1 = __ldg(reinterpret_cast<const float4*>(a) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b)), b1 = __ldg(reinterpret_cast<const float4*>(b) + 1);
+        sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+        sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sc[i] = sh[i] = 0.f;
+      }
+    };
+    auto signal = [&](uint64_t* bar) {
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+      __syncwarp();
+      if (lane == 0) {
+        // the peer CTA's warps arrive on the leader's barrier (the leader issues the cta_group::2 MMA for both). Plain
+        // arrives, like the accumulator-empty handshake; cluster-scope release / acquire on this barrier measured
+        // +15 % on the 3x3 convs (LR_GEMM_DEBUG bit 128 selects them for A/B runs).
+        if (CG == 2 && (p.dbg & 128)) {
+          if (leader) mbar_arrive_release_cluster(bar); else mbar_arrive_leader_release_cluster(bar);
+        } else if (CG == 2 && !leader) {
+          mbar_arrive_leader(bar);
+        } else {
+          mbar_arrive(bar);
+        }
+      }
+    };
+    if (p.halo) {
+      int sa = 0;
+      uint32_t pha = 0;
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+        int tm = min((tile / p.tiles_n) * CG + static_cast<int>(rank), tiles_m - 1);
+        const int tx = tm % p.tiles_x;
+        tm /= p.tiles_x;
+        const int ty = tm % p.tiles_y;
+        const int n0 = tm / p.tiles_y;
+        const int gx0 = tx * kHaloBW - 1, gy0 = ty * kHaloBH - 1;
+        for (int kc = 0; kc < p.kc0 + p.kc1; ++kc) {
+          float sc[8], sh[8];
+          load_coef(n0, kc, sc, sh);
+          mbar_wait(&a_full[sa], pha);
+          uint8_t* slot = smem + sa * p.a_slot_bytes + q * 16;
+          // 12 row slots per thread (rows >= 180 do not exist: the 12th slot of threads with prow0 >= 4), in three
+          // straight-line groups of four. Pixels outside the image stay / become ZERO: the conv pads the NORMALISED
+          // tensor (keep mask), so the out-of-bounds zero fill of the TMA box is re-established after the affine map.
+          auto rows = [&](auto silu_tag) {
+            constexpr bool kSilu = decltype(silu_tag)::value != 0;
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+              uint4 v[4];
+              uint32_t keep[4];
+              int off[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int pr = prow0 + (g * 4 + k) * 16;
+                const int prc = min(pr, kHaloBoxRows - 1);
+                const int yl = prc / (kHaloBW + 2), xl = prc - yl * (kHaloBW + 2);
+                const bool inb = static_cast<unsigned>(gx0 + xl) < static_cast<unsigned>(p.W) &&
+                                 static_cast<unsigned>(gy0 + yl) < static_cast<unsigned>(p.H);
+                keep[k] = inb ? 0xffffffffu : 0u;
+                off[k] = pr < kHaloBoxRows ? prc * 128 : -1;
+                v[k] = *reinterpret_cast<const uint4*>(slot + prc * 128);
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[k] = xf_apply8<kSilu>(v[k], sc, sh, keep[k]);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (off[k] >= 0) *reinterpret_cast<uint4*>(slot + off[k]) = v[k];
+            }
+          };
+          if (!xf_skip) {
+            if (p.xf_silu) rows(IntTag<1>{}); else rows(IntTag<0>{});
+          }
+          signal(&xready[sa]);
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+        }
+      }
+    } else {
+      // plain (Linear / 1x1) mode: one 128-row x 64-channel tile per stage. The host guarantees a token-matrix geometry
+      // (H == 1, one "image", tiles of 128 consecutive rows): row r of M-tile tm is token row tm * 128 + r, its image
+      // is row / xf_rows_per_img. Tiles inside one image (the normal case: rows per image a multiple of 128) take
+      // their coefficients once per chunk.
+      int s = 0;
+      uint32_t ph = 0;
+      const int M = p.W;
+      for (int u = unit0; u < num_units; u += unit_step) {
+        const int tile = u / p.ksplit;
+        const int tm = min((tile / p.tiles_n) * CG + static_cast<int>(rank), tiles_m - 1);
+        const int m0 = tm * kBlockM;
+        const int img_first = m0 / p.xf_rows_per_img;
+        const int img_last = min(m0 + kBlockM - 1, M - 1) / p.xf_rows_per_img;
+        for (int kc = 0; kc < p.kc0 + p.kc1; ++kc) {  // taps == 1 (checked on the host)
+          float sc[8], sh[8];
+          load_coef(img_first, kc, sc, sh);
+          mbar_wait(&a_full[s], ph);
+          uint8_t* slot = smem + s * stage_bytes + q * 16;
+          if (xf_skip) {
+          } else if (img_first == img_last) {
+#pragma unroll
+            for (int it = 0; it < kBlockM / 16; ++it) {
+              uint4* ptr = reinterpret_cast<uint4*>(slot + (prow0 + it * 16) * 128);
+              *ptr = p.xf_silu ? xf_apply8<true>(*ptr, sc, sh, 0xffffffffu)   // rows beyond M are zero fill and are
+                               : xf_apply8<false>(*ptr, sc, sh, 0xffffffffu);  // never stored
+            }
+          } else {
+            int cur_img = img_first;
+            for (int r = prow0; r < kBlockM; r += 16) {
+              const int img = min(m0 + r, M - 1) / p.xf_rows_per_img;
+              if (img != cur_img) {
+                cur_img = img;
+                load_coef(img, kc, sc, sh);
+              }
+              uint4* ptr = reinterpret_cast<uint4*>(slot + r * 128);
+              *ptr = p.xf_silu ? xf_apply8<true>(*ptr, sc, sh, 0xffffffffu) : xf_apply8<false>(*ptr, sc, sh, 0xffffffffu);
+            }
+          }
+          signal(&xready[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
   } else if (warp < 2 + kEpiWarps) {
     // ------------------------------- epilogue warps -----------------------------
     // 8 warps: warp (2+w) reads TMEM lane quarter (w & 3); the two warps of a quarter interleave 32-column chunks.
+    // The XF instantiation (GroupNorm-consuming convs / proj_in) never runs GEGLU, a folded LayerNorm or split-K: pruning
+    // those paths at compile time keeps it inside the 128 registers that 448 threads leave per thread.
+    const bool k_geglu = !XF && p.geglu != 0;
+    const bool k_ln = !XF && p.ln_stats != nullptr;
+    const bool k_partial = !XF && p.partial != nullptr;
     const int ew = warp - 2;
     const int q = hw_warp & 3;  // TMEM lane quarter this warp may access (hardware: warp id % 4)
     const int half = ew >> 2;
@@ -472,7 +692,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     int as = 0;
     uint32_t aph = 0;
     const bool vec_ok = (p.ld_out % 8 == 0) && (p.residual == nullptr || p.ld_res % 8 == 0);
-    const int ocols_tile = p.geglu ? p.block_n / 2 : p.block_n;  // output columns of one tile
+    const int ocols_tile = k_geglu ? p.block_n / 2 : p.block_n;  // output columns of one tile
     const int full_slabs = ocols_tile >> 6;                      // 64-column slabs [128 rows][128 B], swizzled
     bool stores_pending = false;
     // bias: one column per epilogue thread (block_n <= 256 = kEpiThreads), fetched ONE TILE AHEAD into a register
@@ -482,7 +702,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       return col < p.ncols ? __ldg(p.bias + col) : 0.f;
     };
     auto fetch_lns = [&](int tile) -> float {
-      if (tile >= num_tiles || p.ln_stats == nullptr || etid >= p.block_n) return 0.f;
+      if (!k_ln || tile >= num_tiles || etid >= p.block_n) return 0.f;
       const int col = (tile % p.tiles_n) * p.block_n + etid;
       return col < p.ncols ? __ldg(p.ln_s + col) : 0.f;
     };
@@ -522,6 +742,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       int tm = (tile / p.tiles_n) * CG + static_cast<int>(rank);
       const bool tile_ok = tm < tiles_m;
       tm = min(tm, tiles_m - 1);
+      const int tm_idx = tm;  // linear M-tile index: the row pair of this tile in the statistics table
       const int tx = tm % p.tiles_x;
       tm /= p.tiles_x;
       const int ty = tm % p.tiles_y;
@@ -555,14 +776,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       lns_next = fetch_lns((u + unit_step) < num_units ? (u + unit_step) / p.ksplit : num_tiles);
       // folded LayerNorm: this thread's row statistics (they do not depend on the MMA either)
       float ln_rstd = 1.f, ln_nrm = 0.f;
-      if (p.ln_stats != nullptr && row_ok) {
+      if (k_ln && row_ok) {
         const float2 st = __ldg(p.ln_stats + grow);
         ln_rstd = st.y;
         ln_nrm = -st.x * st.y;
       }
 
       // residual of the first chunk is fetched before the accumulator is ready (it does not depend on the MMA)
-      const bool fast = vec_ok && row_ok && !p.geglu && !p.res_tma;
+      const bool fast = vec_ok && row_ok && !k_geglu && !p.res_tma;
       const __half* res_row = (p.residual != nullptr) ? p.residual + grow * p.ld_res : nullptr;
       uint4 rnext[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
       int c = half * 32;
@@ -607,7 +828,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         }
         tmem_ld_wait();
         const int col0 = ncol0 + c;
-        if (p.partial != nullptr) {
+        if (k_partial) {
           // split-K unit: raw fp32 partial sums; bias / residual / fp16 conversion happen in splitk_reduce_kernel
           if (row_ok && col0 < p.ncols) {
             float* po = p.partial + (static_cast<size_t>(sp) * m_total + grow) * p.ncols + col0;
@@ -624,7 +845,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         }
         if (row_ok && col0 < p.ncols) {
           float f[32];
-          if (p.ln_stats != nullptr) {
+          if (k_ln) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b4 = *reinterpret_cast<const float4*>(sb + c + j);
@@ -650,7 +871,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.ncols) f[j] += __ldg(bi + j);
           }
-          if (p.geglu) {
+          if (k_geglu) {
             const int oc0 = col0 >> 1;
             __half* o = p.out + grow * p.ld_out + oc0;
             float g[16];
@@ -748,7 +969,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
         if (ew == 0) LR_GEMM_TR(2, tcount, 4);
         if (etid == 0 && tile_ok && !(p.dbg & 8)) {
-          const int oc_tile0 = p.geglu ? (ncol0 >> 1) : ncol0;
+          const int oc_tile0 = k_geglu ? (ncol0 >> 1) : ncol0;
           const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tb * p.bn;
           for (int sl = 0; sl < full_slabs; ++sl)
             if (oc_tile0 + sl * 64 < p.n_valid)
@@ -760,6 +981,57 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         }
         // the other staging buffer is free (its last store was confirmed above): fetch the next tile's residual into it
         if (p.res_tma && etid == 0 && u + unit_step < num_units) issue_res(u + unit_step, (tcount + 1) & 1);
+        if (p.stats_out != nullptr && tile_ok) {
+          // GroupNorm statistics of the tile just staged (the fp16 values the TMA store is writing): thread -> (pair of
+          // output columns, half of the rows). 32 consecutive threads read 128 contiguous bytes of one row: no bank
+          // conflicts, the swizzle only permutes 16-byte chunks inside a row. The staging buffer is not rewritten before
+          // every epilogue thread has passed the bias barrier of the next tile.
+          const int cpair = etid & 127, rh = etid >> 7;
+          const int col = 2 * cpair;  // output column inside the tile
+          const int oc_tile0 = k_geglu ? (ncol0 >> 1) : ncol0;
+          if (col < ocols_tile && oc_tile0 + col < p.n_valid) {
+            const int slab = col >> 6, cin = col & 63;
+            const bool in_slab = slab < full_slabs;
+            const uint8_t* base = in_slab ? cstage + slab * (kBlockM * 128) + (cin & 7) * 2
+                                          : cstage + full_slabs * (kBlockM * 128) + cin * 2;
+            const int cp0 = cin >> 3;
+            const int xlim = p.W - tx * p.bw, ylim = p.H - ty * p.bh, nlim = p.n_img - tb * p.bn;
+            const bool full_tile = xlim >= p.bw && ylim >= p.bh && nlim >= p.bn;
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            auto acc = [&](uint32_t w) {
+              const float2 t = unpack_half2(w);
+              s0 += t.x;
+              q0 = fmaf(t.x, t.x, q0);
+              s1 += t.y;
+              q1 = fmaf(t.y, t.y, q1);
+            };
+            const uint8_t* hbase = base + rh * 64 * (in_slab ? 128 : 64);
+            if (full_tile) {
+              // straight-line: 8 independent loads in flight; (row & 7) is the unrolled index k
+#pragma unroll
+              for (int i8 = 0; i8 < 8; ++i8) {
+                uint32_t w[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                  w[k] = in_slab ? *reinterpret_cast<const uint32_t*>(hbase + (i8 * 8 + k) * 128 + ((cp0 ^ k) << 4))
+                                 : *reinterpret_cast<const uint32_t*>(hbase + (i8 * 8 + k) * 64);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc(w[k]);
+              }
+            } else {
+              for (int i = 0; i < 64; ++i) {  // tiles that stick out of the image: rows outside hold stale data
+                const int rr = rh * 64 + i;
+                const int xi2 = rr % p.bw, yi2 = (rr / p.bw) % p.bh, ni2 = rr / (p.bw * p.bh);
+                if (xi2 >= xlim || yi2 >= ylim || ni2 >= nlim) continue;
+                acc(in_slab ? *reinterpret_cast<const uint32_t*>(hbase + i * 128 + ((cp0 ^ (rr & 7)) << 4))
+                            : *reinterpret_cast<const uint32_t*>(hbase + i * 64));
+              }
+            }
+            float4* dst = reinterpret_cast<float4*>(p.stats_out + (static_cast<size_t>(tm_idx) * 2 + rh) * p.stats_ld +
+                                                    oc_tile0 + col);
+            *dst = make_float4(s0, q0, s1, q1);
+          }
+        }
         if (ew == 0) LR_GEMM_TR(2, tcount, 5);
       }
 #endif

@@ -158,6 +158,66 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+namespace {
+struct Tiling {
+  int Ho, Wo, bw, bh, bn, tiles_x, tiles_y, tiles_b;
+  bool halo;
+};
+Tiling conv_tiling(const ConvSpec& s) {
+  Tiling t;
+  t.Ho = (s.stride == 1) ? s.in_h : (s.in_h - 1) / 2 + 1;
+  t.Wo = (s.stride == 1) ? s.in_w : (s.in_w - 1) / 2 + 1;
+  // halo mode (gemm_tc.cuh): stride-1 3x3 convs on images at least one halo tile high
+  static const bool halo_enabled = getenv("LR_NO_HALO") == nullptr;
+  t.halo = halo_enabled && s.taps == 9 && s.stride == 1 && s.in_h >= kHaloBH && s.in_w >= kHaloBW;
+  // tile box: power-of-two (bw, bh, bn) with product 128 minimising the number of (partially empty) tiles
+  int best_tiles = INT32_MAX;
+  t.bw = 128;
+  t.bh = 1;
+  t.bn = 1;
+  if (t.halo) {
+    t.bw = kHaloBW;
+    t.bh = kHaloBH;
+    t.bn = 1;
+  }
+  for (int w = 128; w >= 1 && !t.halo; w >>= 1) {
+    for (int h = 128 / w; h >= 1; h >>= 1) {
+      const int n = 128 / (w * h);
+      const long long nt = 1LL * cdiv(t.Wo, w) * cdiv(t.Ho, h) * cdiv(s.n_img, n);
+      if (nt < best_tiles) {
+        best_tiles = static_cast<int>(nt);
+        t.bw = w;
+        t.bh = h;
+        t.bn = n;
+      }
+    }
+  }
+  t.tiles_x = cdiv(t.Wo, t.bw);
+  t.tiles_y = cdiv(t.Ho, t.bh);
+  t.tiles_b = cdiv(s.n_img, t.bn);
+  return t;
+}
+// every 128-row output tile lies inside one image, and the tiles of an image are consecutive
+bool tiles_per_image(const ConvSpec& s, const Tiling& t, int* ppi) {
+  if (s.stats_rows_per_img > 0) {  // token matrix [M, C]: in_h == 1, n_img == 1, tiles of 128 consecutive rows
+    if (s.n_img != 1 || s.in_h != 1 || t.bw != 128 || s.stats_rows_per_img % 128 != 0) return false;
+    *ppi = 2 * (s.stats_rows_per_img / 128);
+    return true;
+  }
+  if (t.bn != 1) return false;
+  *ppi = 2 * t.tiles_x * t.tiles_y;
+  return true;
+}
+}  // namespace
+
+size_t conv_stats_rows(const ConvSpec& s) {
+  const Tiling t = conv_tiling(s);
+  int ppi = 0;
+  if (!tiles_per_image(s, t, &ppi)) return 0;
+  return static_cast<size_t>(2) * t.tiles_x * t.tiles_y * t.tiles_b;
+}
+bool conv_is_halo(const ConvSpec& s) { return conv_tiling(s).halo; }
+
 int build_conv_op(ConvOp* op, const ConvSpec& s) {
   LR_CHECK(s.a0 && s.w && s.out, "conv: null pointer");
   LR_CHECK(s.taps == 1 || s.taps == 9, "conv: taps must be 1 or 9");
@@ -169,32 +229,15 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   LR_CHECK(s.a1 == nullptr || s.c0 % 64 == 0, "conv: two-source K split requires c0 % 64 == 0");
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  const int Ho = (s.stride == 1) ? s.in_h : (s.in_h - 1) / 2 + 1;
-  const int Wo = (s.stride == 1) ? s.in_w : (s.in_w - 1) / 2 + 1;
+  const Tiling tl = conv_tiling(s);
+  const int Ho = tl.Ho, Wo = tl.Wo;
   op->out_h = Ho;
   op->out_w = Wo;
-  // halo mode (gemm_tc.cuh): stride-1 3x3 convs on images at least one halo tile high
-  static const bool halo_enabled = getenv("LR_NO_HALO") == nullptr;
-  const bool halo = halo_enabled && s.taps == 9 && s.stride == 1 && s.in_h >= kHaloBH && s.in_w >= kHaloBW;
-  // tile box: power-of-two (bw, bh, bn) with product 128 minimising the number of (partially empty) tiles
-  int best_tiles = INT32_MAX, bw = 128, bh = 1, bn = 1;
-  if (halo) {
-    bw = kHaloBW;
-    bh = kHaloBH;
-    bn = 1;
-  }
-  for (int w = 128; w >= 1 && !halo; w >>= 1) {
-    for (int h = 128 / w; h >= 1; h >>= 1) {
-      const int n = 128 / (w * h);
-      const long long t = 1LL * cdiv(Wo, w) * cdiv(Ho, h) * cdiv(s.n_img, n);
-      if (t < best_tiles) {
-        best_tiles = static_cast<int>(t);
-        bw = w;
-        bh = h;
-        bn = n;
-      }
-    }
-  }
+  const bool halo = tl.halo;
+  const int bw = tl.bw, bh = tl.bh, bn = tl.bn;
+  const bool xf = s.xf_scale != nullptr;
+  LR_CHECK(!xf || (s.xf_shift != nullptr && (halo || s.taps == 1) && !s.geglu && s.ln_stats == nullptr),
+           "conv: the fused GroupNorm transform needs a halo-mode 3x3 conv or a Linear, without GEGLU / folded LayerNorm");
   p.n_img = s.n_img;
   p.H = Ho;
   p.W = Wo;
@@ -394,6 +437,32 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
     box[0] = 32;
     LR_TRY(make_tmap(&p.tmC2, s.out, 4, dims, str, box, es, false));
   }
+  // ---- GroupNorm fusion ----
+  LR_CHECK(!xf || ksplit == 1, "conv: the fused GroupNorm transform cannot be combined with split-K");
+  LR_CHECK(!xf || halo || (s.n_img == 1 && s.in_h == 1 && bw == 128 && s.xf_rows_per_img > 0),
+           "conv: the fused GroupNorm transform of a Linear needs a token matrix (n_img = in_h = 1) and xf_rows_per_img");
+  p.xf_scale = s.xf_scale;
+  p.xf_shift = s.xf_shift;
+  p.xf_ld = s.c0 + s.c1;
+  p.xf_silu = s.xf_silu;
+  p.xf_rows_per_img = s.xf_rows_per_img;
+
+  LR_CHECK(!xf || (s.c0 + s.c1) % 8 == 0, "conv: fused GroupNorm needs channel counts that are multiples of 8");
+  op->xf = xf ? 1 : 0;
+  op->stats_ok = 0;
+  op->stats_ppi = 0;
+  p.stats_out = nullptr;
+  p.stats_ld = s.ncols;
+  {
+    int ppi = 0;
+    if (s.stats_out != nullptr && tma_store && ksplit == 1 && !s.geglu && s.ncols % 2 == 0 &&
+        tiles_per_image(s, tl, &ppi)) {
+      LR_CHECK((reinterpret_cast<uintptr_t>(s.stats_out) & 15) == 0, "conv: statistics table must be 16-byte aligned");
+      p.stats_out = reinterpret_cast<float2*>(s.stats_out);
+      op->stats_ok = 1;
+      op->stats_ppi = ppi;
+    }
+  }
   const int num_units = cdiv(tiles_m, cg) * p.tiles_n * ksplit;
   op->ksplit = ksplit;
   op->ncols = s.ncols;
@@ -417,18 +486,26 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   op->flops = 2.0 * s.n_img * Ho * Wo * static_cast<double>(s.ncols) * s.taps * (s.c0 + s.c1);
   memcpy(op->params, &p, sizeof(p));
   if (first_use_on_device(0)) {
-    LR_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    LR_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    LR_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    LR_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    LR_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    LR_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   }
   return 0;
 }
 
 int launch_conv_op(const ConvOp& op, cudaStream_t st) {
   const GemmParams* p = reinterpret_cast<const GemmParams*>(op.params);
-  if (op.cg == 2) {
-    LR_CUDA(launch_pdl(gemm_conv_kernel<2>, dim3(op.grid), dim3(kGemmThreads), op.smem, st, 2, *p));
+  if (op.xf) {
+    if (op.cg == 2) {
+      LR_CUDA(launch_pdl(gemm_conv_kernel<2, true>, dim3(op.grid), dim3(kGemmThreadsXf), op.smem, st, 2, *p));
+    } else {
+      LR_CUDA(launch_pdl(gemm_conv_kernel<1, true>, dim3(op.grid), dim3(kGemmThreadsXf), op.smem, st, 1, *p));
+    }
+  } else if (op.cg == 2) {
+    LR_CUDA(launch_pdl(gemm_conv_kernel<2, false>, dim3(op.grid), dim3(kGemmThreads), op.smem, st, 2, *p));
   } else {
-    LR_CUDA(launch_pdl(gemm_conv_kernel<1>, dim3(op.grid), dim3(kGemmThreads), op.smem, st, 1, *p));
+    LR_CUDA(launch_pdl(gemm_conv_kernel<1, false>, dim3(op.grid), dim3(kGemmThreads), op.smem, st, 1, *p));
   }
   LR_LAUNCHED();
   if (op.ksplit > 1) {
@@ -561,6 +638,32 @@ int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_i
   LR_LAUNCHED();
   LR_CUDA(launch_pdl(gn_apply_kernel, grid, dim3(kNormThreads), 0, st, 1, x0, c0, x1, c1, P, chunk,
                      static_cast<const unsigned char*>(scratch), gamma, beta, groups, do_silu, out));
+  LR_LAUNCHED();
+  return 0;
+}
+
+int launch_gn_finalize(const float* part0, int ppi0, int c0, const float* part1, int ppi1, int c1, int n_img, int P,
+                       int groups, float eps, const float* gamma, const float* beta, float* scale, float* shift,
+                       cudaStream_t st) {
+  LR_CHECK(part0 != nullptr && (part1 != nullptr || c1 == 0), "gn_finalize: null statistics table");
+  LR_CHECK((c0 + c1) % groups == 0, "gn_finalize: channels not divisible by groups");
+  LR_CUDA(launch_pdl(gn_finalize_kernel, dim3(groups, n_img), dim3(kGnFinalizeThreads), 0, st, 1,
+                     reinterpret_cast<const float2*>(part0), ppi0, c0, reinterpret_cast<const float2*>(part1), ppi1, c1,
+                     static_cast<double>(P) * ((c0 + c1) / groups), eps, gamma, beta, scale, shift));
+  LR_LAUNCHED();
+  return 0;
+}
+
+int launch_gn_apply_coef(const __half* x0, int c0, const __half* x1, int c1, int n_img, int P, const float* scale,
+                         const float* shift, int do_silu, __half* out, cudaStream_t st) {
+  const int C = c0 + c1;
+  LR_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C / 8 <= kNormThreads, "gn_apply_coef: bad channel counts");
+  static const int chunk_div = env_int("LR_GN_APPLY_CHUNK_DIV", 32);
+  int chunk = P / chunk_div;
+  if (chunk < 16) chunk = 16;
+  if (chunk > 512) chunk = 512;
+  LR_CUDA(launch_pdl(gn_apply_coef_kernel, dim3(cdiv(P, chunk), n_img), dim3(kNormThreads), 0, st, 1, x0, c0, x1, c1, P,
+                     chunk, scale, shift, do_silu, out));
   LR_LAUNCHED();
   return 0;
 }

@@ -55,6 +55,17 @@ struct ConvSpec {
   int geglu = 0;
   const float* ln_stats = nullptr;  // folded LayerNorm: [M] float2 (mean, rstd) of the input rows, or nullptr
   const float* ln_s = nullptr;      //                   [ncols] column sums of the gamma-folded weight
+  // GroupNorm fusion (gemm_tc.cuh header): the input is x * xf_scale[n, c] + xf_shift[n, c] (+ SiLU), applied in shared
+  // memory by the transform warps. Needs a halo-mode 3x3 conv (stride 1, image >= 16 rows x 8 columns) or taps == 1.
+  const float* xf_scale = nullptr;  // [n_img (or M / xf_rows_per_img), c0 + c1]
+  const float* xf_shift = nullptr;
+  int xf_silu = 0;
+  int xf_rows_per_img = 0;  // taps == 1 on a token matrix: rows per image
+  // per-tile-half (sum, sum of squares) of the fp16 output per channel -> stats_out [conv_stats_rows()][ncols] float2;
+  // written only when the op ends up eligible (ConvOp::stats_ok), i.e. TMA-store epilogue, no split-K, every 128-row tile
+  // inside one image (stats_rows_per_img: rows per image of a token-matrix output, 0 = conv geometry)
+  float* stats_out = nullptr;
+  int stats_rows_per_img = 0;
   float* workspace = nullptr;  // optional split-K scratch (fp32 partial tiles), workspace_bytes >= 3 * M_out * ncols * 4
   size_t workspace_bytes = 0;
   int force_block_n = 0;  // testing hook: 0 = heuristic
@@ -74,9 +85,16 @@ struct ConvOp {
   const __half* residual = nullptr;
   __half* out = nullptr;
   double flops = 0;
+  int xf = 0;         // launches the transform-warp instantiation
+  int stats_ok = 0;   // stats_out is written by this op
+  int stats_ppi = 0;  // statistics rows per image (2 per 128-row tile)
 };
 // 3x3 convs with at most this many OUTPUT pixels per image run split-K over the taps when scratch is provided
 constexpr int kSplitKMaxPixels = 256;
+// rows of the statistics table a conv / linear with this geometry needs (2 per M-tile); 0 if it can never produce them
+size_t conv_stats_rows(const ConvSpec& s);
+// true if build_conv_op will run this 3x3 conv in halo mode (the only 3x3 mode the transform warps support)
+bool conv_is_halo(const ConvSpec& s);
 int build_conv_op(ConvOp* op, const ConvSpec& s);
 int launch_conv_op(const ConvOp& op, cudaStream_t st);
 float* op_level_workspace(size_t bytes);
@@ -105,6 +123,13 @@ size_t groupnorm_scratch_bytes(int n_img, int groups);
 int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_img, int P, int groups, float eps,
                      const float* gamma, const float* beta, int do_silu, void* scratch, int scratch_is_zero,
                      __half* out, cudaStream_t st);
+// GroupNorm statistics from producer partials -> per-(image, channel) affine coefficients (elementwise.cuh)
+int launch_gn_finalize(const float* part0, int ppi0, int c0, const float* part1, int ppi1, int c1, int n_img, int P,
+                       int groups, float eps, const float* gamma, const float* beta, float* scale, float* shift,
+                       cudaStream_t st);
+// y = [silu](x * scale[n, c] + shift[n, c]) over concat(x0, x1): GroupNorm apply from finalized producer statistics
+int launch_gn_apply_coef(const __half* x0, int c0, const __half* x1, int c1, int n_img, int P, const float* scale,
+                         const float* shift, int do_silu, __half* out, cudaStream_t st);
 int launch_layernorm(const __half* x, int M, int C, const float* gamma, const float* beta, float eps, __half* out,
                      cudaStream_t st);
 // (mean, rstd) per row -> stats [M] float2; the normalisation itself is folded into the consuming GEMM

@@ -65,6 +65,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Cluster-scope variants: a barrier in the leader CTA of a pair that threads of BOTH CTAs arrive on after writing shared
+// memory the leader's tcgen05.mma.cta_group::2 will read (gemm_tc.cuh transform warps).
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("lr_b200: mbarrier (cluster) timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint64_t* bar) {  // local barrier, cluster-scope release
+  asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // One lane of a converged warp. Issue loops are executed by the WHOLE warp with warp-uniform operands and only the
 // tcgen05 / TMA instruction itself is predicated on this: operands then stay in uniform registers. (Running the loop
 // inside `if (lane == 0)` made ptxas emit ELECT + 5 x R2UR.BROADCAST + descriptor re-computation per MMA, ~130 issue
@@ -254,6 +282,10 @@ __device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* m,
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_leader_release_cluster(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+               : "memory");
+}
 __device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -310,6 +342,14 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t M, uint32_t
 // ----------------------------------------------------------------------------------------------
 // misc
 // ----------------------------------------------------------------------------------------------
+// 16-byte read-only load that does not allocate in L1 (streamed once: activation tiles of the transform warps)
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

@@ -98,6 +98,78 @@ def groupnorm(x0, gamma, beta, eps, silu=False, x1=None, groups=32):
     return out
 
 
+class GNStats:
+    """Per-tile (sum, sum of squares) partials a conv / linear left for its OUTPUT (lr_gn_conv3x3_f16 / lr_gn_linear_f16):
+    table fp32 [rows, C, 2], `ppi` rows per image, `P` pixels per image. Feeds gn_finalize."""
+
+    def __init__(self, table, ppi, C, P):
+        self.table, self.ppi, self.C, self.P = table, ppi, C, P
+
+
+def gn_finalize(stats0, gamma, beta, eps, n, stats1=None, groups=32):
+    """GroupNorm statistics from producer partials -> (scale, shift) fp32 [n, c0 + c1] with
+    y = x * scale + shift == GroupNorm(x) (elementwise.cuh gn_finalize_kernel)."""
+    C = stats0.C + (stats1.C if stats1 is not None else 0)
+    scale = torch.empty(n, C, dtype=torch.float32, device=stats0.table.device)
+    shift = torch.empty_like(scale)
+    N.check(N.lib().lr_gn_finalize(N.ptr(stats0.table), stats0.ppi, stats0.C,
+                                   N.ptr(stats1.table) if stats1 is not None else None,
+                                   stats1.ppi if stats1 is not None else 0, stats1.C if stats1 is not None else 0, n,
+                                   stats0.P, groups, float(eps), N.ptr(_chk(gamma, torch.float32)),
+                                   N.ptr(_chk(beta, torch.float32)), N.ptr(scale), N.ptr(shift), N.current_stream()),
+            "gn_finalize")
+    return scale, shift
+
+
+def gn_conv3x3(x0, wt, gn=None, silu=True, bias=None, x1=None, bias_img=None, residual=None, want_stats=False,
+               force_block_n=0):
+    """3x3 conv (stride 1, pad 1) whose input is GroupNorm(+SiLU) of concat(x0, x1) given as gn = (scale, shift) fp32
+    [n, c0 + c1] - applied to the activation tiles in shared memory - and/or whose epilogue leaves GroupNorm partials
+    of its output. Returns out, or (out, GNStats | None) when want_stats."""
+    import ctypes
+    _chk(x0, torch.float16)
+    n, h, w, c0 = x0.shape
+    c1 = x1.shape[3] if x1 is not None else 0
+    cout = wt.shape[0]
+    out = torch.empty(n, h, w, cout, dtype=torch.float16, device=x0.device)
+    table = None
+    if want_stats:
+        rows = N.lib().lr_conv_stats_rows(n, h, w, 1, 9, 0)
+        if rows > 0:
+            table = torch.zeros(rows, cout, 2, dtype=torch.float32, device=x0.device)
+    ppi = ctypes.c_int(0)
+    sc, sh = gn if gn is not None else (None, None)
+    N.check(N.lib().lr_gn_conv3x3_f16(N.ptr(x0), c0, N.ptr(x1), c1, n, h, w, N.ptr(sc), N.ptr(sh), int(silu),
+                                      N.ptr(_chk(wt, torch.float16)), cout, N.ptr(bias), N.ptr(bias_img), N.ptr(residual),
+                                      N.ptr(out), N.ptr(table), ctypes.byref(ppi), force_block_n, N.current_stream()),
+            "gn_conv3x3")
+    if not want_stats:
+        return out
+    return out, (GNStats(table, ppi.value, cout, h * w) if ppi.value > 0 else None)
+
+
+def gn_linear(a, w, rows_per_img, gn=None, silu=False, bias=None, residual=None, want_stats=False, force_block_n=0):
+    """Linear on a token matrix a [M, K] (image of row m = m // rows_per_img) with the same two fusions as gn_conv3x3."""
+    import ctypes
+    _chk(a, torch.float16)
+    M, K = a.shape
+    n_out = w.shape[0]
+    out = torch.empty(M, n_out, dtype=torch.float16, device=a.device)
+    table = None
+    if want_stats:
+        rows = N.lib().lr_conv_stats_rows(1, 1, M, 1, 1, rows_per_img)
+        if rows > 0:
+            table = torch.zeros(rows, n_out, 2, dtype=torch.float32, device=a.device)
+    ppi = ctypes.c_int(0)
+    sc, sh = gn if gn is not None else (None, None)
+    N.check(N.lib().lr_gn_linear_f16(N.ptr(a), M, K, rows_per_img, N.ptr(sc), N.ptr(sh), int(silu),
+                                     N.ptr(_chk(w, torch.float16)), n_out, N.ptr(bias), N.ptr(residual), N.ptr(out),
+                                     N.ptr(table), ctypes.byref(ppi), force_block_n, N.current_stream()), "gn_linear")
+    if not want_stats:
+        return out
+    return out, (GNStats(table, ppi.value, n_out, rows_per_img) if ppi.value > 0 else None)
+
+
 def layernorm(x, gamma, beta, eps=1e-5):
     _chk(x, torch.float16)
     C = x.shape[-1]

@@ -267,6 +267,59 @@ def _ref_nvs_class():
     return ns["NVSUnetModel"]
 
 
+def golden_vae():
+    """First-stage decode: the unmodified reference Decoder (ldm/modules/diffusionmodules/model.py:547-653) + the
+    post_quant_conv of AutoencoderKL.decode (autoencoder.py:87-90; that class itself needs pytorch_lightning, its decode
+    is `decoder(post_quant_conv(z))`), small config (ch = 32), latent 2x4x16x32 -> image 2x3x128x256."""
+    from oracle import vae_oracle as V
+    from ldm.modules.diffusionmodules.model import Decoder
+    cfg = V.SMALL_CFG
+    sd = V.make_state_dict(cfg, seed=0)
+    dd = {k: v for k, v in cfg.items() if k != "embed_dim"}
+    dec = Decoder(**dd)
+    keys = ["decoder." + k for k in dec.state_dict().keys()]
+    spec = V.decoder_spec(cfg)
+    assert keys == [n for n, _ in spec if n.startswith("decoder.")], "oracle decoder walk differs from the reference"
+    for n, shp in spec:
+        if n.startswith("decoder."):
+            assert tuple(dec.state_dict()[n[len("decoder."):]].shape) == tuple(shp), n
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}, strict=True)
+    dec.eval()
+    pq = torch.nn.Conv2d(cfg["embed_dim"], cfg["z_channels"], 1)
+    pq.load_state_dict({"weight": sd["post_quant_conv.weight"], "bias": sd["post_quant_conv.bias"]})
+    g = torch.Generator(device="cpu").manual_seed(71)
+    z = torch.randn(2, 4, 16, 32, generator=g) * V.SCALE_FACTOR * 4.0     # latents as the sampler returns them
+    taps_ref = {}
+    hooks = [dec.mid.block_2.register_forward_hook(lambda m, a, o: taps_ref.__setitem__("mid", o))]
+    with torch.no_grad():
+        y_ref = dec(pq(z / V.SCALE_FACTOR))
+        taps = {}
+        y_or = V.decode(sd, cfg, z, scale_factor=V.SCALE_FACTOR, taps=taps)
+    print("Decoder + post_quant_conv (small config, 2x4x16x32 -> 2x3x128x256):")
+    check("image", y_or, y_ref)
+    check("mid", taps["mid"], taps_ref["mid"])
+    for h in hooks:
+        h.remove()
+    np.savez_compressed(os.path.join(GOLD, "vae_small.npz"), z=z.numpy(), out=y_ref.numpy(),
+                        mid=taps_ref["mid"].numpy(), scale_factor=V.SCALE_FACTOR)
+    # the full SD2 decoder (ch = 128, 49.5 M parameters) at a small latent: walk + numerics
+    cfg = V.DEFAULT_CFG
+    sd = V.make_state_dict(cfg, seed=0)
+    dec = Decoder(**{k: v for k, v in cfg.items() if k != "embed_dim"})
+    assert ["decoder." + k for k in dec.state_dict().keys()] == [n for n, _ in V.decoder_spec(cfg) if n.startswith("decoder.")]
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}, strict=True)
+    dec.eval()
+    z = torch.randn(1, 4, 8, 16, generator=g) * V.SCALE_FACTOR * 4.0
+    with torch.no_grad():
+        zq = torch.nn.functional.conv2d(z / V.SCALE_FACTOR, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
+        y_ref = dec(zq)
+        y_or = V.decode(sd, cfg, z, scale_factor=V.SCALE_FACTOR)
+    print("Decoder (full SD2 VAE config, 1x4x8x16 -> 1x3x64x128):")
+    check("image", y_or, y_ref)
+    np.savez_compressed(os.path.join(GOLD, "vae_full_8x16.npz"), z=z.numpy(), out=y_ref.numpy(),
+                        scale_factor=V.SCALE_FACTOR)
+
+
 def golden_nvs():
     """NVSUnetModel(use_sep=True) with and without c_input, full config (the reference hard-codes the separator channel
     list for model_channels = 320) at a 16x32 latent."""
@@ -314,12 +367,16 @@ if __name__ == "__main__":
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--only-multi", action="store_true", help="regenerate only tests/golden/ddim_multi_small.npz")
     ap.add_argument("--only-nvs", action="store_true", help="regenerate only tests/golden/nvs_full_16x32.npz")
+    ap.add_argument("--only-vae", action="store_true", help="regenerate only tests/golden/vae_*.npz")
     args = ap.parse_args()
     assert os.path.isdir(REF), "the reference tree is only available in the build container"
     os.makedirs(GOLD, exist_ok=True)
     torch.set_grad_enabled(False)
     if args.only_nvs:
         golden_nvs()
+        sys.exit(0)
+    if args.only_vae:
+        golden_vae()
         sys.exit(0)
     if args.only_multi:
         cfg = O.SMALL_CFG
@@ -330,6 +387,7 @@ if __name__ == "__main__":
     golden_multiview()
     golden_ddim(cfg, sd, m)
     golden_ddim_multi(cfg, sd, m)
+    golden_vae()
     if args.full:
         validate_full()
         golden_nvs()

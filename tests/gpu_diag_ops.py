@@ -210,6 +210,99 @@ def case_gn(n, h, w, c0, c1=0, silu=True, eps=1e-5, seed=0):
                   ref.permute(0, 2, 3, 1).reshape(-1, C))
 
 
+def case_gn_fused_conv(n, h, w, c0, cout, c1=0, silu=True, eps=1e-5, residual=False, force=0, bigmean=False, seed=0):
+    """The fused GroupNorm path end to end at op level: a producer conv leaves statistics partials for its output(s),
+    lr_gn_finalize turns them into (scale, shift), and the consumer conv applies GroupNorm + SiLU to its activation tiles
+    in shared memory. Reference: F.group_norm + F.silu + F.conv2d on the producers' fp16 outputs."""
+    import torch
+    import torch.nn.functional as F
+    from leftrefill_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    C = c0 + c1
+
+    def producer(cin, co):
+        x = torch.randn(n, cin, h, w, generator=g).cuda()
+        wt = (torch.randn(co, cin, 3, 3, generator=g) / (9 * cin) ** 0.5).cuda()
+        b = torch.randn(co, generator=g).cuda() * (6.0 if bigmean else 1.0)
+        y, st = ops.gn_conv3x3(ops.to_nhwc_f16(x), ops.repack_conv3x3(wt), bias=b, want_stats=True)
+        return y, st
+
+    y0, st0 = producer(64, c0)
+    y1, st1 = producer(64, c1) if c1 else (None, None)
+    assert st0 is not None and (c1 == 0 or st1 is not None), "producer did not leave statistics"
+    gamma = torch.randn(C, generator=g).cuda()
+    beta = torch.randn(C, generator=g).cuda()
+    scale, shift = ops.gn_finalize(st0, gamma, beta, eps, n, stats1=st1)
+    xcat = torch.cat([y0, y1], dim=3) if c1 else y0
+    xf = xcat.float().permute(0, 3, 1, 2).double()
+    # statistics check: scale / shift against fp64 group statistics of the fp16 producer outputs
+    xg = xf.reshape(n, 32, C // 32, h, w)
+    mean = xg.mean(dim=(2, 3, 4))
+    rstd = 1.0 / (xg.var(dim=(2, 3, 4), unbiased=False) + eps).sqrt()
+    sc_ref = (rstd.repeat_interleave(C // 32, dim=1) * gamma.double()[None]).float()
+    sh_ref = (beta.double()[None] - mean.repeat_interleave(C // 32, dim=1) * sc_ref.double()).float()
+    ok = report(f"gn-finalize scale n={n} {h}x{w} c={c0}+{c1}", scale, sc_ref, rtol=2e-4 if bigmean else 2e-5, atol_scale=1e-6)
+    ok &= report(f"gn-finalize shift n={n} {h}x{w} c={c0}+{c1}", shift, sh_ref, rtol=2e-4 if bigmean else 2e-5,
+                 atol_scale=2e-4 if bigmean else 2e-6)
+    wt = (torch.randn(cout, C, 3, 3, generator=g) / (9 * C) ** 0.5).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    r = torch.randn(n, h, w, cout, generator=g).cuda().half() if residual else None
+    out, st_out = ops.gn_conv3x3(y0, ops.repack_conv3x3(wt), gn=(scale, shift), silu=silu, bias=b, x1=y1, residual=r,
+                                 want_stats=True, force_block_n=force)
+    torch.cuda.synchronize()
+    # reference with the SAME coefficients (isolates the transform + conv) ...
+    xn = xf.float() * scale[:, :, None, None] + shift[:, :, None, None]
+    if silu:
+        xn = F.silu(xn)
+    xn = xn.half().float()                       # the transform rounds to fp16 before the MMA
+    ref = F.conv2d(xn, wt.half().float(), b, padding=1).permute(0, 2, 3, 1)
+    if r is not None:
+        ref = ref + r.float()
+    ok &= report(f"gn-fused conv n={n} {h}x{w} c={c0}+{c1}->{cout} silu={silu} res={residual} bn={force}",
+                 out.reshape(-1, cout), ref.reshape(-1, cout))
+    # ... and the statistics the consumer left for ITS output
+    if st_out is not None:
+        s2, h2 = ops.gn_finalize(st_out, torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda"), eps, n)
+        og = out.float().permute(0, 3, 1, 2).double().reshape(n, 32, cout // 32, h, w)
+        rstd2 = (1.0 / (og.var(dim=(2, 3, 4), unbiased=False) + eps).sqrt()).repeat_interleave(cout // 32, dim=1).float()
+        ok &= report("gn-fused conv: statistics of its own output (rstd)", s2, rstd2, rtol=5e-5, atol_scale=1e-6)
+    return ok
+
+
+def case_gn_fused_linear(n, P, C, cout, silu=False, eps=1e-6, force=0, seed=0):
+    """SpatialTransformer norm -> proj_in (attention.py:399-404) fused: token-matrix producer (a Linear with residual, like
+    proj_out) leaves statistics, the consumer Linear applies the GroupNorm in shared memory."""
+    import torch
+    from leftrefill_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    M = n * P
+    a = torch.randn(M, 64, generator=g).cuda().half()
+    w0 = (torch.randn(C, 64, generator=g) / 8.0).cuda()
+    r0 = torch.randn(M, C, generator=g).cuda().half()
+    y, st = ops.gn_linear(a, ops.repack_linear(w0), P, bias=torch.randn(C, generator=g).cuda(), residual=r0,
+                          want_stats=True)
+    assert st is not None, "producer did not leave statistics"
+    gamma = torch.randn(C, generator=g).cuda()
+    beta = torch.randn(C, generator=g).cuda()
+    scale, shift = ops.gn_finalize(st, gamma, beta, eps, n)
+    yg = y.double().reshape(n, P, 32, C // 32)
+    mean = yg.mean(dim=(1, 3))
+    rstd = 1.0 / (yg.var(dim=(1, 3), unbiased=False) + eps).sqrt()
+    sc_ref = (rstd.repeat_interleave(C // 32, dim=1) * gamma.double()[None]).float()
+    ok = report(f"gn-finalize (token matrix) scale n={n} P={P} C={C}", scale, sc_ref, rtol=2e-5, atol_scale=1e-6)
+    w1 = (torch.randn(cout, C, generator=g) / C ** 0.5).cuda()
+    b1 = torch.randn(cout, generator=g).cuda()
+    out = ops.gn_linear(y, ops.repack_linear(w1), P, gn=(scale, shift), silu=silu, bias=b1, force_block_n=force)
+    torch.cuda.synchronize()
+    xn = y.float().reshape(n, P, C) * scale[:, None, :] + shift[:, None, :]
+    if silu:
+        xn = torch.nn.functional.silu(xn)
+    ref = xn.half().float().reshape(M, C) @ w1.half().float().t() + b1
+    ok &= report(f"gn-fused linear n={n} P={P} C={C}->{cout} silu={silu} bn={force}", out, ref)
+    return ok
+
+
 def case_ln(M, C, seed=0):
     import torch
     import torch.nn.functional as F
@@ -323,6 +416,18 @@ CASES = {
     "gn_bigmean": lambda: case_gn_bigmean(2, 16, 32, 320),
     "gn_bigmean_twopass": lambda: case_gn_bigmean(1, 64, 128, 320, ratio=60.0),
     "geglu_big": lambda: case_geglu_big(512, 320, 640),
+    "gnf_conv": lambda: case_gn_fused_conv(2, 16, 32, 64, 96),
+    "gnf_conv_big": lambda: case_gn_fused_conv(2, 64, 128, 320, 320, residual=True),
+    "gnf_conv_concat": lambda: case_gn_fused_conv(2, 32, 64, 128, 160, c1=192, force=2160),
+    "gnf_conv_1cta": lambda: case_gn_fused_conv(3, 40, 24, 64, 64, residual=True, force=1064),
+    "gnf_conv_ragged": lambda: case_gn_fused_conv(2, 17, 33, 64, 96),
+    "gnf_conv_nosilu": lambda: case_gn_fused_conv(1, 16, 8, 64, 64, silu=False, eps=1e-6),
+    "gnf_conv_bigmean": lambda: case_gn_fused_conv(2, 32, 32, 320, 64, bigmean=True),
+    "gnf_conv_cout4": lambda: case_gn_fused_conv(2, 16, 32, 320, 4),
+    "gnf_linear": lambda: case_gn_fused_linear(2, 512, 320, 320),
+    "gnf_linear_1cta": lambda: case_gn_fused_linear(3, 128, 64, 96, force=1096),
+    "gnf_linear_2sm": lambda: case_gn_fused_linear(2, 2048, 640, 640, force=2000),
+    "gnf_linear_silu": lambda: case_gn_fused_linear(1, 256, 128, 64, silu=True, eps=1e-5),
     "gn": lambda: case_gn(2, 16, 32, 320),
     "gn_concat": lambda: case_gn(2, 8, 16, 1280, c1=640),
     "gn_nosilu": lambda: case_gn(3, 8, 8, 64, silu=False, eps=1e-6),

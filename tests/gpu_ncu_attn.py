@@ -20,6 +20,27 @@ elif kind == "conv":
     b = torch.zeros(320, device="cuda")
     for _ in range(3):
         ops.conv3x3(x, w, bias=b)
+elif kind == "gnconv":      # fused GroupNorm + SiLU conv (transform warps), preceded by the plain conv for comparison
+    x = torch.randn(8, 64, 128, 320, device="cuda").half()
+    w = torch.randn(320, 2880, device="cuda").half() * 0.02
+    b = torch.zeros(320, device="cuda")
+    r = torch.randn(8, 64, 128, 320, device="cuda").half()
+    sc = torch.rand(8, 320, device="cuda") + 0.5
+    sh = torch.randn(8, 320, device="cuda") * 0.1
+    for _ in range(3):
+        ops.conv3x3(x, w, bias=b, residual=r)
+    for _ in range(3):
+        ops.gn_conv3x3(x, w, gn=(sc, sh), silu=True, bias=b, residual=r, want_stats=True)
+elif kind == "gnlin":
+    a = torch.randn(65536, 320, device="cuda").half()
+    w = torch.randn(320, 320, device="cuda").half() * 0.05
+    b = torch.zeros(320, device="cuda")
+    sc = torch.rand(8, 320, device="cuda") + 0.5
+    sh = torch.randn(8, 320, device="cuda") * 0.1
+    for _ in range(3):
+        ops.linear(a, w, bias=b)
+    for _ in range(3):
+        ops.gn_linear(a, w, 8192, gn=(sc, sh), silu=False, bias=b)
 elif kind == "conv1280":
     x = torch.randn(8, 32, 64, 1280, device="cuda").half()
     w = torch.randn(1280, 11520, device="cuda").half() * 0.01

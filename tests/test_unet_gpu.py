@@ -516,7 +516,7 @@ def test_sampler_graph_survives_context_length_change(small, monkeypatch):
                 monkeypatch.delenv("LR_NO_CUDA_GRAPH", raising=False)
             torch.manual_seed(11)
             s = lr.DDIMSampler(FakeLDM(m, dev))
-            out[mode], _ = s.sample(3, 2, (4, 16, 32), cond, eta=1.0, x_T=x_T, verbose=False,
+            out[mode], _ = s.sample(4, 2, (4, 16, 32), cond, eta=1.0, x_T=x_T, verbose=False,
                                     unconditional_guidance_scale=2.5, unconditional_conditioning=ucond)
         assert torch.equal(out["graph"], out["eager"]), (L, (out["graph"] - out["eager"]).abs().max().item())
     monkeypatch.delenv("LR_NO_CUDA_GRAPH", raising=False)
