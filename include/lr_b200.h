@@ -114,6 +114,36 @@ double lr_unet_last_flops(const lr_unet* h);
 /* Bytes of device memory held by the engine (weights + activation plan). */
 long long lr_unet_device_bytes(const lr_unet* h);
 
+/* ---- first-stage decoder: replaces AutoencoderKL.decode (ldm/models/autoencoder.py:87-90: decoder(post_quant_conv(z)))
+ * with the Decoder of ldm/modules/diffusionmodules/model.py:547-653, as called by LatentDiffusion.decode_first_stage
+ * (ldm/models/diffusion/ddpm.py:835-843, which first multiplies z by 1 / scale_factor = z_scale here). ----------- */
+typedef struct lr_vae lr_vae;
+/* first_stage_config.params of configs/ref_inpainting.yaml:38-58 (ddconfig + embed_dim); attn_resolutions must be
+ * empty (only the mid-block attention of the SD VAE exists), resamp_with_conv true, tanh_out / give_pre_end false. */
+typedef struct lr_vae_cfg {
+  int ch;              /* 128 */
+  int out_ch;          /* 3 */
+  int num_levels;      /* len(ch_mult) */
+  int ch_mult[8];      /* 1,2,4,4 */
+  int num_res_blocks;  /* 2 */
+  int z_channels;      /* 4 */
+  int embed_dim;       /* 4 */
+} lr_vae_cfg;
+int lr_vae_create(const lr_vae_cfg* cfg, lr_vae** out);
+void lr_vae_destroy(lr_vae* h);
+/* weight table = AutoencoderKL state-dict keys "decoder.*" and "post_quant_conv.*" (SD checkpoints:
+ * first_stage_model.<name>), fp32 PyTorch layouts, same protocol as lr_unet_set_weight */
+int lr_vae_num_weights(const lr_vae* h);
+const char* lr_vae_weight_name(const lr_vae* h, int index);
+int lr_vae_weight_shape(const lr_vae* h, int index, int64_t shape_out[4]);
+int lr_vae_set_weight(lr_vae* h, const char* name, const float* data, const int64_t* shape, int ndim, void* stream);
+int lr_vae_missing_weights(const lr_vae* h);
+/* z [n, embed_dim, H, W] fp32 NCHW -> out [n, out_ch, 8H, 8W] fp32 NCHW (2^(num_levels-1) = 8 for the SD VAE) */
+int lr_vae_decode(lr_vae* h, const float* z, float z_scale, float* out, int n, int H, int W, void* stream);
+double lr_vae_last_flops(const lr_vae* h);
+long long lr_vae_device_bytes(const lr_vae* h);
+int lr_vae_num_steps(const lr_vae* h);
+
 /* ---- fused CFG + DDIM update: replaces p_sample_ddim's tail (ldm/models/diffusion/ddim.py:343,359-381) ----------
  * eps_uncond/eps_cond: the two halves of the CFG-doubled UNet output (eps_cond may be NULL: no guidance).
  * noise may be NULL when sigma == 0. All tensors fp32 with `numel` elements. */

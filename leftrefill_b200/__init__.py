@@ -4,6 +4,8 @@ Public surface (mirrors the reference class surface):
     UNetModel, MultiViewUnetModel, NVSUnetModel, ResBlock, Upsample, Downsample, TimestepEmbedSequential   (openaimodel.py)
     CrossAttention, BasicTransformerBlock, SpatialTransformer, FeedForward, GEGLU            (attention.py)
     DDIMSampler                                                                              (ddim.py)
+    AutoencoderKL (decode), Decoder              first-stage decoder on the same kernels (autoencoder.py:87-90,
+                                                 model.py:547-653)
     PromptContextCache, install_context_cache    memoised prompt contexts for the learned-prompt text encoders
                                                  (Refill_modules.py:160-191)
     install()  -> makes `ldm.modules.diffusionmodules.openaimodel.UNetModel`, `ldm.modules.attention.CrossAttention`
@@ -23,6 +25,7 @@ _LAZY = {
     "SpatialTransformer": "attention", "FeedForward": "attention", "GEGLU": "attention",
     "DDIMSampler": "ddim",
     "PromptContextCache": "context_cache", "install_context_cache": "context_cache",
+    "AutoencoderKL": "vae", "Decoder": "vae",
 }
 
 

@@ -38,6 +38,18 @@ class UNetCfg(Structure):
     ]
 
 
+class VaeCfg(Structure):
+    _fields_ = [
+        ("ch", c_int),
+        ("out_ch", c_int),
+        ("num_levels", c_int),
+        ("ch_mult", c_int * 8),
+        ("num_res_blocks", c_int),
+        ("z_channels", c_int),
+        ("embed_dim", c_int),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/lr_b200.h declares
 SIGNATURES = {
     "lr_abi_version": (c_int, []),
@@ -64,6 +76,17 @@ SIGNATURES = {
     "lr_unet_step_info": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_double), POINTER(c_int), c_char_p,
                                   c_int]),
     "lr_unet_plan_generation": (c_longlong, [c_void_p]),
+    "lr_vae_create": (c_int, [POINTER(VaeCfg), POINTER(c_void_p)]),
+    "lr_vae_destroy": (None, [c_void_p]),
+    "lr_vae_num_weights": (c_int, [c_void_p]),
+    "lr_vae_weight_name": (c_char_p, [c_void_p, c_int]),
+    "lr_vae_weight_shape": (c_int, [c_void_p, c_int, POINTER(c_int64)]),
+    "lr_vae_set_weight": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int, c_void_p]),
+    "lr_vae_missing_weights": (c_int, [c_void_p]),
+    "lr_vae_decode": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "lr_vae_last_flops": (c_double, [c_void_p]),
+    "lr_vae_device_bytes": (c_longlong, [c_void_p]),
+    "lr_vae_num_steps": (c_int, [c_void_p]),
     "lr_ddim_update_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int64, c_void_p,
                                    c_void_p, c_void_p]),
     "lr_unet_last_flops": (c_double, [c_void_p]),

@@ -852,6 +852,125 @@ __global__ void cinput_nchw_to_nhwc_kernel(const float* __restrict__ x, int n_im
   out[idx] = __float2half_rn(v);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// First-stage decoder helpers (AutoencoderKL.decode: ldm/models/autoencoder.py:87-90; Decoder / AttnBlock:
+// ldm/modules/diffusionmodules/model.py:153-204,547-653)
+// ------------------------------------------------------------------------------------------------------------
+// z [n, zc, H, W] fp32 NCHW (the sampler's latent) -> z * z_scale (decode_first_stage divides by scale_factor,
+// ddpm.py:842) -> post_quant_conv (1x1, zc x e, fp32) -> im2col rows [n*H*W, kpad] fp16 of the 3x3 conv_in
+// (k = tap * zc + c, zero outside the image: the conv pads post_quant_conv's OUTPUT with zeros).
+constexpr int kVaeMaxZ = 8;
+__global__ void vae_in_kernel(const float* __restrict__ z, int n_img, int e, int zc, int H, int W, float z_scale,
+                              const float* __restrict__ pq_w, const float* __restrict__ pq_b, int kpad,
+                              __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (pixel, tap)
+  const size_t total = static_cast<size_t>(n_img) * H * W * 9;
+  if (idx >= total) return;
+  const int tap = static_cast<int>(idx % 9);
+  const size_t m = idx / 9;
+  const int xw = static_cast<int>(m % W);
+  const int yh = static_cast<int>((m / W) % H);
+  const int n = static_cast<int>(m / (static_cast<size_t>(W) * H));
+  const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+  __half* o = out + m * kpad + tap * zc;
+  if (yy < 0 || yy >= H || xx < 0 || xx >= W) {
+    for (int c = 0; c < zc; ++c) o[c] = __float2half_rn(0.f);
+  } else {
+    float zin[kVaeMaxZ];
+    for (int i = 0; i < e; ++i) zin[i] = z[((static_cast<size_t>(n) * e + i) * H + yy) * W + xx] * z_scale;
+    for (int c = 0; c < zc; ++c) {
+      float acc = pq_b[c];
+      for (int i = 0; i < e; ++i) acc = fmaf(pq_w[c * e + i], zin[i], acc);
+      o[c] = __float2half_rn(acc);
+    }
+  }
+  if (tap == 8)
+    for (int k = 9 * zc; k < kpad; ++k) out[m * kpad + k] = __float2half_rn(0.f);
+}
+
+// Row softmax of an fp16 matrix in place (AttnBlock: softmax over the key axis of the scaled logits, model.py:185),
+// fp32 statistics. One CTA of 256 threads per row; the row is read once into registers (T <= 256 * 8 * kSoftmaxVecs).
+constexpr int kSoftmaxVecs = 8;  // rows of up to 16384 elements
+__global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ x, int T, size_t ld) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[8];
+  __half* row = x + static_cast<size_t>(blockIdx.x) * ld;
+  const int nvec = T / 8;
+  uint4 raw[kSoftmaxVecs];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int v = 0; v < kSoftmaxVecs; ++v) {
+    const int vi = threadIdx.x + v * 256;
+    raw[v] = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);  // -inf
+    if (vi < nvec) {
+      raw[v] = *reinterpret_cast<const uint4*>(row + vi * 8);
+      float f[8];
+      unpack8(raw[v], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx = fmaxf(mx, f[j]);
+    }
+  }
+  auto block_reduce = [&](float v, bool is_max) -> float {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float t = __shfl_xor_sync(0xffffffffu, v, o);
+      v = is_max ? fmaxf(v, t) : v + t;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];  // fixed order
+    return r;
+  };
+  mx = block_reduce(mx, true);
+  float sum = 0.f;
+#pragma unroll
+  for (int v = 0; v < kSoftmaxVecs; ++v) {
+    if (threadIdx.x + v * 256 < nvec) {
+      float f[8];
+      unpack8(raw[v], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += __expf(f[j] - mx);
+    }
+  }
+  sum = block_reduce(sum, false);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int v = 0; v < kSoftmaxVecs; ++v) {
+    const int vi = threadIdx.x + v * 256;
+    if (vi < nvec) {
+      float f[8];
+      unpack8(raw[v], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __expf(f[j] - mx) * inv;
+      store8(row + vi * 8, f);
+    }
+  }
+}
+
+// out [C, T] = in [T, C]^T (fp16, in has row stride ld_in): the value matrix of the AttnBlock as the K-major "weight"
+// operand of the P V GEMM. 32 x 32 tiles through shared memory.
+__global__ void transpose_f16_kernel(const __half* __restrict__ in, int T, int C, size_t ld_in, __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ __half tile[32][33];
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < T && c < C) ? in[static_cast<size_t>(t) * ld_in + c] : __float2half_rn(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (c < C && t < T) out[static_cast<size_t>(c) * T + t] = tile[threadIdx.x][i];
+  }
+}
+
 // fp32 -> fp16 cast (context tokens)
 __global__ void cast_f32_f16_kernel(const float* __restrict__ x, size_t n, __half* __restrict__ out) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;

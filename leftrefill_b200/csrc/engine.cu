@@ -15,7 +15,7 @@
 
 namespace lr {
 
-enum WKind { K_CONV3, K_LINEAR, K_LINEAR_GEGLU, K_VEC, K_VEC_GEGLU };
+enum WKind { K_CONV3, K_LINEAR, K_LINEAR_GEGLU, K_VEC, K_VEC_GEGLU, K_F32 /* all elements, fp32, as is */ };
 
 struct Weight {
   std::string name;
@@ -33,6 +33,8 @@ struct ResW {
   int cin = 0, cout = 0;
   size_t gn1_g, gn1_b, conv1_w, conv1_b, emb_w, emb_b, gn2_g, gn2_b, conv2_w, conv2_b, skip_w, skip_b;
   bool has_skip = false;
+  bool has_emb = true;  // UNet ResBlock: + Linear(SiLU(emb)) per image (openaimodel.py:263-272); VAE ResnetBlock: none
+  float eps = 1e-5f;    // GroupNorm32 (util.py:208) 1e-5; the VAE's Normalize (model.py:45) 1e-6
   int emb_col0 = 0;  // column offset of this block's emb_layers output inside the batched [n, emb_total] buffer
 };
 struct TBlockW {
@@ -108,7 +110,9 @@ struct Pool {
 
 using namespace lr;
 
-struct lr_unet {
+// Shared machinery of the two engines (UNet forward, first-stage decoder): weight table + fp16 / fp32 arenas, the
+// activation pool, the static plan (list of launches) and the planners of the blocks both networks are made of.
+struct lr_engine {
   lr_unet_cfg cfg;
   std::vector<Weight> weights;
   std::map<std::string, int> windex;
@@ -168,7 +172,7 @@ struct lr_unet {
   bool ctx_valid = false;
   size_t persistent_bytes = 0;
 
-  ~lr_unet() {
+  virtual ~lr_engine() {
     for (auto e : prof_events) cudaEventDestroy(e);
     pool.clear();
     if (harena) cudaFree(harena);
@@ -689,13 +693,13 @@ struct lr_unet {
       s.ldw = 9 * r.cin;
       s.ncols = r.cout;
       s.bias = F(r.conv1_b);
-      s.bias_img = emb_all + r.emb_col0;
+      s.bias_img = r.has_emb ? emb_all + r.emb_col0 : nullptr;
       s.ld_bias_img = emb_total;
       s.ld_out = r.cout;
       float *sc = nullptr, *sh = nullptr;
       int err = 0;
       const bool fused = gn_fuse_conv && conv_is_halo(s) &&
-                         plan_gn_coef(x0, x1, n, 1e-5f, F(r.gn1_g), F(r.gn1_b), &sc, &sh, &err);
+                         plan_gn_coef(x0, x1, n, r.eps, F(r.gn1_g), F(r.gn1_b), &sc, &sh, &err);
       LR_TRY(err);
       if (fused) {
         s.a0 = x0.p;
@@ -709,7 +713,7 @@ struct lr_unet {
         s.xf_silu = 1;
       } else {
         LR_TRY(acquire_h(M * r.cin, &xn));
-        LR_TRY(add_gn_auto(x0, x1, n, 1e-5f, F(r.gn1_g), F(r.gn1_b), 1, xn));
+        LR_TRY(add_gn_auto(x0, x1, n, r.eps, F(r.gn1_g), F(r.gn1_b), 1, xn));
         s.a0 = xn;
         s.c0 = r.cin;
         s.lda0 = r.cin;
@@ -771,7 +775,7 @@ struct lr_unet {
       float *sc = nullptr, *sh = nullptr;
       int err = 0;
       const bool fused = gn_fuse_conv && conv_is_halo(s) &&
-                         plan_gn_coef(hact, Act{}, n, 1e-5f, F(r.gn2_g), F(r.gn2_b), &sc, &sh, &err);
+                         plan_gn_coef(hact, Act{}, n, r.eps, F(r.gn2_g), F(r.gn2_b), &sc, &sh, &err);
       LR_TRY(err);
       if (fused) {
         s.a0 = h;
@@ -780,7 +784,7 @@ struct lr_unet {
         s.xf_silu = 1;
       } else {
         LR_TRY(acquire_h(M * r.cout, &hn));
-        LR_TRY(add_gn_auto(hact, Act{}, n, 1e-5f, F(r.gn2_g), F(r.gn2_b), 1, hn));
+        LR_TRY(add_gn_auto(hact, Act{}, n, r.eps, F(r.gn2_g), F(r.gn2_b), 1, hn));
         s.a0 = hn;
       }
       LR_TRY(want_stats(&s, tab, next_is_fused_st));
@@ -1374,9 +1378,357 @@ struct lr_unet {
   }
 };
 
+struct lr_unet : lr_engine {};
+
 // ==============================================================================================================
 // C ABI
 // ==============================================================================================================
+// ==============================================================================================================
+// First-stage decoder engine: AutoencoderKL.decode = decoder(post_quant_conv(z)) (ldm/models/autoencoder.py:87-90) with
+// the Decoder of ldm/modules/diffusionmodules/model.py:547-653, as a static plan of the same kernels the UNet uses:
+// ResnetBlock (model.py:82-150) = plan_res without the time-embedding term (GroupNorm eps 1e-6 + swish + tcgen05
+// conv3x3, nin_shortcut as a 1x1 GEMM, the skip added in the conv2 epilogue); Upsample (model.py:51-66) = nearest x2
+// + conv3x3; AttnBlock (model.py:153-204) = one fused QKV GEMM, then per image the single-head d = C attention as two
+// tcgen05 GEMMs around a row-softmax kernel (logits [T, T] fp16 with the 1/sqrt(C) scale applied to the fp32
+// accumulator - under torch.autocast the reference materialises the same fp16 logits with torch.bmm), proj_out with the
+// residual in its epilogue. The d_head = 64 flash kernel does not apply (d = 512); this runs once per batch, not per step.
+// ==============================================================================================================
+struct VaeAttnW {
+  int C = 0;
+  size_t gn_g, gn_b, qkv_w, qkv_b, out_w, out_b;
+};
+struct VaeLevel {
+  std::vector<int> blocks;  // indices into res
+  int up_conv = -1;         // index into convs, -1: no upsample
+};
+
+struct lr_vae : lr_engine {
+  lr_vae_cfg vcfg;
+  int top = 0, last = 0, kpad = 0;
+  size_t conv_in_w = 0, conv_in_b = 0, pq_w = 0, pq_b = 0, no_g = 0, no_b = 0;
+  int mid1 = 0, mid2 = 0, out_conv = 0;
+  VaeAttnW attn;
+  std::vector<VaeLevel> levels;  // from the lowest resolution up
+  const float* in_z = nullptr;
+  float* out_img = nullptr;
+  float z_scale = 1.0f;
+  float pz_scale = 0.f;  // planned
+
+  int add_vres(const std::string& pfx, int cin, int cout) {
+    ResW r;
+    r.cin = cin;
+    r.cout = cout;
+    r.has_emb = false;
+    r.eps = 1e-6f;
+    r.gn1_g = reg_vec(pfx + "norm1.weight", cin);
+    r.gn1_b = reg_vec(pfx + "norm1.bias", cin);
+    r.conv1_w = reg_conv3(pfx + "conv1.weight", cout, cin, 9 * cin);
+    r.conv1_b = reg_vec(pfx + "conv1.bias", cout);
+    r.gn2_g = reg_vec(pfx + "norm2.weight", cout);
+    r.gn2_b = reg_vec(pfx + "norm2.bias", cout);
+    r.conv2_w = reg_conv3(pfx + "conv2.weight", cout, cout, 9 * cout);
+    r.conv2_b = reg_vec(pfx + "conv2.bias", cout);
+    r.has_skip = cin != cout;
+    if (r.has_skip) {
+      r.skip_w = reg(pfx + "nin_shortcut.weight", {cout, cin, 1, 1}, K_LINEAR, halloc(static_cast<size_t>(cout) * cin), 0, cin);
+      r.skip_b = reg_vec(pfx + "nin_shortcut.bias", cout);
+    }
+    res.push_back(r);
+    return static_cast<int>(res.size()) - 1;
+  }
+
+  // registration order = the reference state dict (decoder.*, then post_quant_conv.*)
+  int build_graph_vae() {
+    const lr_vae_cfg& c = vcfg;
+    LR_CHECK(c.num_levels >= 1 && c.num_levels <= 8, "vae: num_levels out of range");
+    LR_CHECK(c.z_channels >= 1 && c.z_channels <= 7 && c.embed_dim >= 1 && c.embed_dim <= 8, "vae: z_channels / embed_dim out of range");
+    LR_CHECK(c.ch % 32 == 0, "vae: ch must be a multiple of 32 (GroupNorm groups)");
+    top = c.ch * c.ch_mult[c.num_levels - 1];
+    kpad = ((9 * c.z_channels + 63) / 64) * 64;
+    const std::string d = "decoder.";
+    conv_in_w = reg_conv3(d + "conv_in.weight", top, c.z_channels, kpad);
+    conv_in_b = reg_vec(d + "conv_in.bias", top);
+    mid1 = add_vres(d + "mid.block_1.", top, top);
+    {
+      const std::string a = d + "mid.attn_1.";
+      attn.C = top;
+      attn.gn_g = reg_vec(a + "norm.weight", top);
+      attn.gn_b = reg_vec(a + "norm.bias", top);
+      attn.qkv_w = halloc(static_cast<size_t>(3) * top * top);
+      attn.qkv_b = falloc(3 * top);
+      const char* nm[3] = {"q", "k", "v"};
+      for (int i = 0; i < 3; ++i) {
+        reg(a + nm[i] + ".weight", {top, top, 1, 1}, K_LINEAR, attn.qkv_w, i * top, top);
+        reg(a + nm[i] + ".bias", {top}, K_VEC, attn.qkv_b + static_cast<size_t>(i) * top, 0, 0);
+      }
+      attn.out_w = reg(a + "proj_out.weight", {top, top, 1, 1}, K_LINEAR, halloc(static_cast<size_t>(top) * top), 0, top);
+      attn.out_b = reg_vec(a + "proj_out.bias", top);
+    }
+    mid2 = add_vres(d + "mid.block_2.", top, top);
+    // the ModuleList order is up.0 .. up.N-1 (model.py:606 prepends) while execution runs from level N-1 down
+    std::vector<VaeLevel> by_level(c.num_levels);
+    std::vector<int> in_ch(c.num_levels);
+    {
+      int block_in = top;
+      for (int lvl = c.num_levels - 1; lvl >= 0; --lvl) {
+        in_ch[lvl] = block_in;
+        block_in = c.ch * c.ch_mult[lvl];
+      }
+      last = block_in;
+    }
+    for (int lvl = 0; lvl < c.num_levels; ++lvl) {
+      int block_in = in_ch[lvl];
+      const int block_out = c.ch * c.ch_mult[lvl];
+      for (int i = 0; i <= c.num_res_blocks; ++i) {
+        by_level[lvl].blocks.push_back(add_vres(d + "up." + std::to_string(lvl) + ".block." + std::to_string(i) + ".",
+                                                block_in, block_out));
+        block_in = block_out;
+      }
+      if (lvl != 0) by_level[lvl].up_conv = add_conv(d + "up." + std::to_string(lvl) + ".upsample.conv.", block_out, block_out,
+                                                     9 * block_out);
+    }
+    for (int lvl = c.num_levels - 1; lvl >= 0; --lvl) levels.push_back(by_level[lvl]);
+    no_g = reg_vec(d + "norm_out.weight", last);
+    no_b = reg_vec(d + "norm_out.bias", last);
+    out_conv = add_conv(d + "conv_out.", last, c.out_ch, 9 * last);
+    pq_w = reg("post_quant_conv.weight", {c.z_channels, c.embed_dim, 1, 1}, K_F32,
+               falloc(static_cast<size_t>(c.z_channels) * c.embed_dim), 0, 0);
+    pq_b = reg_vec("post_quant_conv.bias", c.z_channels);
+    return 0;
+  }
+
+  // AttnBlock (model.py:153-204) on x [n, P, C]
+  int plan_attn(Act x, int n, Act* out) {
+    const int C = attn.C, P = x.H * x.W, M = n * P;
+    LR_CHECK(P % 8 == 0 && C % 8 == 0, "vae attention: H*W and C must be multiples of 8");
+    __half *xn, *qkv, *S, *vt, *att, *o;
+    LR_TRY(acquire_h(static_cast<size_t>(M) * C, &xn));
+    LR_TRY(add_gn_auto(x, Act{}, n, 1e-6f, F(attn.gn_g), F(attn.gn_b), 0, xn));
+    LR_TRY(acquire_h(static_cast<size_t>(M) * 3 * C, &qkv));
+    LR_TRY(add_linear(xn, M, C, H(attn.qkv_w), 3 * C, F(attn.qkv_b), nullptr, 0, qkv, 3 * C, 0));
+    release(xn);
+    LR_TRY(acquire_h(static_cast<size_t>(P) * P, &S));
+    LR_TRY(acquire_h(static_cast<size_t>(C) * P, &vt));
+    LR_TRY(acquire_h(static_cast<size_t>(M) * C, &att));
+    for (int b = 0; b < n; ++b) {
+      const __half* qb = qkv + static_cast<size_t>(b) * P * 3 * C;
+      {  // S = (Q K^T) / sqrt(C): "weights" = the K rows of this image
+        ConvSpec cs;
+        cs.a0 = qb;
+        cs.c0 = C;
+        cs.lda0 = 3 * C;
+        cs.n_img = 1;
+        cs.in_h = 1;
+        cs.in_w = P;
+        cs.taps = 1;
+        cs.w = qb + C;
+        cs.ldw = 3 * C;
+        cs.ncols = P;
+        cs.out = S;
+        cs.ld_out = P;
+        cs.out_scale = 1.0f / sqrtf(static_cast<float>(C));
+        LR_TRY(add_conv_step(cs));
+      }
+      {
+        __half* Sb = S;
+        push([=](cudaStream_t st) { return launch_softmax_rows(Sb, P, P, static_cast<size_t>(P), st); }, 4, 0.0,
+             "vae softmax rows=" + std::to_string(P));
+        const __half* vb = qb + 2 * C;
+        push([=](cudaStream_t st) { return launch_transpose_f16(vb, P, C, static_cast<size_t>(3) * C, vt, st); }, 4, 0.0,
+             "vae V^T");
+      }
+      {  // O = P V: "weights" = V^T [C, T]
+        ConvSpec cs;
+        cs.a0 = S;
+        cs.c0 = P;
+        cs.lda0 = P;
+        cs.n_img = 1;
+        cs.in_h = 1;
+        cs.in_w = P;
+        cs.taps = 1;
+        cs.w = vt;
+        cs.ldw = P;
+        cs.ncols = C;
+        cs.out = att + static_cast<size_t>(b) * P * C;
+        cs.ld_out = C;
+        LR_TRY(add_conv_step(cs));
+      }
+    }
+    release(S);
+    release(vt);
+    release(qkv);
+    LR_TRY(acquire_h(static_cast<size_t>(M) * C, &o));
+    LR_TRY(add_linear(att, M, C, H(attn.out_w), C, F(attn.out_b), x.p, C, o, C, 0));
+    release(att);
+    *out = Act{o, C, x.H, x.W};
+    return 0;
+  }
+
+  int build_plan_vae(int n, int Hh, int Ww) {
+    if (pn == n && ph == Hh && pw == Ww && pz_scale == z_scale) return 0;
+    steps.clear();
+    conv_ops.clear();
+    attn_ops.clear();
+    pool.clear();
+    stats_of.clear();
+    flops = 0;
+    pn = 0;
+    {
+      gn_sites_cap = 2 * static_cast<int>(res.size()) + 2;
+      gn_sites_planned = 0;
+      gn_site_bytes = groupnorm_scratch_bytes(n, 32);
+      const size_t bytes = gn_site_bytes * gn_sites_cap;
+      void* p;
+      LR_TRY(pool.acquire(bytes, &p));
+      gn_stats = static_cast<unsigned char*>(p);
+      unsigned char* gs = gn_stats;
+      push([=](cudaStream_t st) {
+        cudaError_t e = cudaMemsetAsync(gs, 0, bytes, st);
+        if (e != cudaSuccess) {
+          set_error(std::string("cudaMemsetAsync(gn stats): ") + cudaGetErrorString(e));
+          return 1;
+        }
+        return 0;
+      });
+    }
+    const lr_vae_cfg& c = vcfg;
+    const size_t M0 = static_cast<size_t>(n) * Hh * Ww;
+    __half* col;
+    LR_TRY(acquire_h(M0 * kpad, &col));
+    {
+      const float zs = z_scale;
+      const int e = c.embed_dim, zc = c.z_channels, kp = kpad;
+      const float* pw_ = F(pq_w);
+      const float* pb_ = F(pq_b);
+      push([=](cudaStream_t st) { return launch_vae_in(this->in_z, n, e, zc, Hh, Ww, zs, pw_, pb_, kp, col, st); });
+    }
+    Act h;
+    {
+      __half* o;
+      LR_TRY(acquire_h(M0 * top, &o));
+      LR_TRY(add_linear(col, static_cast<int>(M0), kpad, H(conv_in_w), top, F(conv_in_b), nullptr, 0, o, top, 0));
+      h = Act{o, top, Hh, Ww};
+    }
+    release(col);
+    auto step_res = [&](int idx) -> int {
+      Act o;
+      LR_TRY(plan_res(res[idx], h, Act{}, n, &o));
+      release(h.p);
+      h = o;
+      return 0;
+    };
+    LR_TRY(step_res(mid1));
+    {
+      Act o;
+      LR_TRY(plan_attn(h, n, &o));
+      release(h.p);
+      h = o;
+    }
+    LR_TRY(step_res(mid2));
+    for (const VaeLevel& lv : levels) {
+      for (int idx : lv.blocks) LR_TRY(step_res(idx));
+      if (lv.up_conv >= 0) {
+        // Upsample (model.py:62-66): nearest x2, then conv3x3
+        __half* up;
+        LR_TRY(acquire_h(static_cast<size_t>(n) * 4 * h.H * h.W * h.C, &up));
+        const __half* src = h.p;
+        const int hh = h.H, ww = h.W, cc = h.C;
+        push([=](cudaStream_t st) { return launch_upsample2x(src, n, hh, ww, cc, up, st); });
+        release(h.p);
+        Act u{up, cc, 2 * hh, 2 * ww};
+        Act o;
+        LR_TRY(plan_conv3(convs[lv.up_conv], u, n, 1, &o));
+        release(up);
+        h = o;
+      }
+    }
+    {
+      // norm_out -> swish -> conv_out (model.py:645-650); out_ch (3) columns, rows padded to 4 halves
+      const ConvW& cw = convs[out_conv];
+      const size_t Mo = static_cast<size_t>(n) * h.H * h.W;
+      __half *hn, *y;
+      LR_TRY(acquire_h(Mo * h.C, &hn));
+      LR_TRY(add_gn_auto(h, Act{}, n, 1e-6f, F(no_g), F(no_b), 1, hn));
+      release(h.p);
+      const int ldy = 4;
+      LR_CHECK(cw.cout <= ldy, "vae: out_ch > 4 is not supported");
+      LR_TRY(acquire_h(Mo * ldy, &y));
+      ConvSpec s;
+      s.a0 = hn;
+      s.c0 = h.C;
+      s.lda0 = h.C;
+      s.n_img = n;
+      s.in_h = h.H;
+      s.in_w = h.W;
+      s.taps = 9;
+      s.w = H(cw.w);
+      s.ldw = 9 * h.C;
+      s.ncols = cw.cout;
+      s.bias = F(cw.b);
+      s.out = y;
+      s.ld_out = ldy;
+      LR_TRY(add_conv_step(s));
+      release(hn);
+      const int co = cw.cout, oh = h.H, ow = h.W;
+      push([=](cudaStream_t st) { return launch_nhwc_to_nchw_f32(y, ldy, n, co, oh, ow, this->out_img, st); });
+    }
+    pn = n;
+    ph = Hh;
+    pw = Ww;
+    pz_scale = z_scale;
+    ++plan_generation;
+    return 0;
+  }
+};
+
+
+static int engine_set_weight(lr_engine* h, const char* name, const float* data, const int64_t* shape, int ndim,
+                             void* stream) {
+  LR_CHECK(h && name && data && shape, "set_weight: null argument");
+  auto it = h->windex.find(name);
+  LR_CHECK(it != h->windex.end(), std::string("set_weight: unknown weight '") + name + "'");
+  Weight& w = h->weights[it->second];
+  bool ok = (ndim == w.ndim);
+  for (int i = 0; ok && i < ndim; ++i) ok = (shape[i] == w.shape[i]);
+  // a Linear registered as [O, I] also accepts the 1x1-conv form [O, I, 1, 1] and vice versa
+  if (!ok && w.kind == K_LINEAR) {
+    ok = (ndim == 2 || ndim == 4) && shape[0] == w.shape[0] && shape[1] == w.shape[1] &&
+         (ndim == 2 || (shape[2] == 1 && shape[3] == 1));
+  }
+  LR_CHECK(ok, std::string("set_weight: shape mismatch for '") + name + "'");
+  LR_TRY(h->ensure_arenas());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int O = static_cast<int>(w.shape[0]);
+  switch (w.kind) {
+    case K_CONV3:
+      LR_TRY(launch_repack_conv(data, O, static_cast<int>(w.shape[1]), w.ld, h->H(w.off), st));
+      break;
+    case K_LINEAR:
+      LR_TRY(launch_repack_linear(data, O, static_cast<int>(w.shape[1]), 0, w.dst_row0, h->H(w.off), st));
+      break;
+    case K_LINEAR_GEGLU:
+      LR_TRY(launch_repack_linear(data, O, static_cast<int>(w.shape[1]), 1, 0, h->H(w.off), st));
+      break;
+    case K_VEC:
+      LR_TRY(launch_repack_bias(data, O, 0, h->F(w.off), st));
+      break;
+    case K_VEC_GEGLU:
+      LR_TRY(launch_repack_bias(data, O, 1, h->F(w.off), st));
+      break;
+    case K_F32: {
+      size_t numel = 1;
+      for (int i = 0; i < w.ndim; ++i) numel *= static_cast<size_t>(w.shape[i]);
+      LR_CUDA(cudaMemcpyAsync(h->F(w.off), data, numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      break;
+    }
+  }
+  w.loaded = true;
+  h->fold_dirty = true;  // LayerNorm-folded weight copies depend on norm{1,2,3} and their consuming Linears
+  h->ctx_valid = false;  // cached K/V depend on attn2.to_k / to_v
+  return 0;
+}
+
+
 extern "C" {
 
 int lr_abi_version(void) { return LR_B200_ABI_VERSION; }
@@ -1401,59 +1753,28 @@ int lr_unet_create(const lr_unet_cfg* cfg, lr_unet** out) {
 }
 void lr_unet_destroy(lr_unet* h) { delete h; }
 
-int lr_unet_num_weights(const lr_unet* h) { return h ? static_cast<int>(h->weights.size()) : 0; }
-const char* lr_unet_weight_name(const lr_unet* h, int i) {
+static int engine_num_weights(const lr_engine* h) { return h ? static_cast<int>(h->weights.size()) : 0; }
+static const char* engine_weight_name(const lr_engine* h, int i) {
   if (!h || i < 0 || i >= static_cast<int>(h->weights.size())) return nullptr;
   return h->weights[i].name.c_str();
 }
-int lr_unet_weight_shape(const lr_unet* h, int i, int64_t shape_out[4]) {
+static int engine_weight_shape(const lr_engine* h, int i, int64_t shape_out[4]) {
   if (!h || i < 0 || i >= static_cast<int>(h->weights.size())) return -1;
   for (int d = 0; d < 4; ++d) shape_out[d] = h->weights[i].shape[d];
   return h->weights[i].ndim;
 }
-int lr_unet_missing_weights(const lr_unet* h) {
+static int engine_missing_weights(const lr_engine* h) {
   int m = 0;
   for (const auto& w : h->weights) m += w.loaded ? 0 : 1;
   return m;
 }
+int lr_unet_num_weights(const lr_unet* h) { return engine_num_weights(h); }
+const char* lr_unet_weight_name(const lr_unet* h, int i) { return engine_weight_name(h, i); }
+int lr_unet_weight_shape(const lr_unet* h, int i, int64_t shape_out[4]) { return engine_weight_shape(h, i, shape_out); }
+int lr_unet_missing_weights(const lr_unet* h) { return engine_missing_weights(h); }
 
 int lr_unet_set_weight(lr_unet* h, const char* name, const float* data, const int64_t* shape, int ndim, void* stream) {
-  LR_CHECK(h && name && data && shape, "lr_unet_set_weight: null argument");
-  auto it = h->windex.find(name);
-  LR_CHECK(it != h->windex.end(), std::string("lr_unet_set_weight: unknown weight '") + name + "'");
-  Weight& w = h->weights[it->second];
-  bool ok = (ndim == w.ndim);
-  for (int i = 0; ok && i < ndim; ++i) ok = (shape[i] == w.shape[i]);
-  // a Linear registered as [O, I] also accepts the 1x1-conv form [O, I, 1, 1] and vice versa
-  if (!ok && w.kind == K_LINEAR) {
-    ok = (ndim == 2 || ndim == 4) && shape[0] == w.shape[0] && shape[1] == w.shape[1] &&
-         (ndim == 2 || (shape[2] == 1 && shape[3] == 1));
-  }
-  LR_CHECK(ok, std::string("lr_unet_set_weight: shape mismatch for '") + name + "'");
-  LR_TRY(h->ensure_arenas());
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int O = static_cast<int>(w.shape[0]);
-  switch (w.kind) {
-    case K_CONV3:
-      LR_TRY(launch_repack_conv(data, O, static_cast<int>(w.shape[1]), w.ld, h->H(w.off), st));
-      break;
-    case K_LINEAR:
-      LR_TRY(launch_repack_linear(data, O, static_cast<int>(w.shape[1]), 0, w.dst_row0, h->H(w.off), st));
-      break;
-    case K_LINEAR_GEGLU:
-      LR_TRY(launch_repack_linear(data, O, static_cast<int>(w.shape[1]), 1, 0, h->H(w.off), st));
-      break;
-    case K_VEC:
-      LR_TRY(launch_repack_bias(data, O, 0, h->F(w.off), st));
-      break;
-    case K_VEC_GEGLU:
-      LR_TRY(launch_repack_bias(data, O, 1, h->F(w.off), st));
-      break;
-  }
-  w.loaded = true;
-  h->fold_dirty = true;  // LayerNorm-folded weight copies depend on norm{1,2,3} and their consuming Linears
-  h->ctx_valid = false;  // cached K/V depend on attn2.to_k / to_v
-  return 0;
+  return engine_set_weight(h, name, data, shape, ndim, stream);
 }
 
 int lr_unet_set_context(lr_unet* h, const float* context, int n, int L, void* stream) {
@@ -1599,6 +1920,45 @@ int lr_ddim_update(const float* x, const float* eps_uncond, const float* eps_con
                             temperature, static_cast<size_t>(numel), x_prev, pred_x0,
                             static_cast<cudaStream_t>(stream));
 }
+
+// ---- first-stage decoder -------------------------------------------------------------------------------------
+int lr_vae_create(const lr_vae_cfg* cfg, lr_vae** out) {
+  LR_CHECK(cfg != nullptr && out != nullptr, "lr_vae_create: null argument");
+  auto h = std::make_unique<lr_vae>();
+  h->vcfg = *cfg;
+  memset(&h->cfg, 0, sizeof(h->cfg));
+  h->cfg.view_num = 1;
+  LR_TRY(h->build_graph_vae());
+  *out = h.release();
+  return 0;
+}
+void lr_vae_destroy(lr_vae* h) { delete h; }
+int lr_vae_num_weights(const lr_vae* h) { return engine_num_weights(h); }
+const char* lr_vae_weight_name(const lr_vae* h, int i) { return engine_weight_name(h, i); }
+int lr_vae_weight_shape(const lr_vae* h, int i, int64_t shape_out[4]) { return engine_weight_shape(h, i, shape_out); }
+int lr_vae_missing_weights(const lr_vae* h) { return engine_missing_weights(h); }
+int lr_vae_set_weight(lr_vae* h, const char* name, const float* data, const int64_t* shape, int ndim, void* stream) {
+  return engine_set_weight(h, name, data, shape, ndim, stream);
+}
+int lr_vae_decode(lr_vae* h, const float* z, float z_scale, float* out, int n, int H, int W, void* stream) {
+  LR_CHECK(h && z && out, "lr_vae_decode: null argument");
+  LR_CHECK(n > 0 && H > 0 && W > 0, "lr_vae_decode: empty input");
+  const int missing = engine_missing_weights(h);
+  LR_CHECK(missing == 0, "lr_vae_decode: " + std::to_string(missing) + " weights not uploaded");
+  LR_TRY(h->ensure_arenas());
+  h->z_scale = z_scale;
+  LR_TRY(h->build_plan_vae(n, H, W));
+  h->in_z = z;
+  h->out_img = out;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (auto& s : h->steps) LR_TRY(s.fn(st));
+  return 0;
+}
+double lr_vae_last_flops(const lr_vae* h) { return h ? h->flops : 0.0; }
+long long lr_vae_device_bytes(const lr_vae* h) {
+  return h ? static_cast<long long>(h->persistent_bytes + h->pool.total) : 0;
+}
+int lr_vae_num_steps(const lr_vae* h) { return h ? static_cast<int>(h->steps.size()) : 0; }
 
 // ---- op level ----------------------------------------------------------------------------------------------
 int lr_linear_f16(const void* a, int lda, int M, int K, const void* w, int ldw, int n_cols, const float* bias,

@@ -374,7 +374,7 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   p.ld_out = s.ld_out;
   p.geglu = s.geglu;
   p.n_valid = s.geglu ? s.ncols / 2 : s.ncols;
-  p.out_scale = 1.0f;
+  p.out_scale = s.out_scale;
   {
     const char* e = getenv("LR_GEMM_DEBUG");
     p.dbg = e ? atoi(e) : 0;
@@ -814,6 +814,26 @@ int launch_cinput_to_nhwc(const float* x, int n_img, int C, int H, int Wc, int x
   const size_t total = static_cast<size_t>(n_img) * H * Wh * C;
   cinput_nchw_to_nhwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, n_img, C, H, Wc, x_off, Wh,
                                                                                           out);
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_vae_in(const float* z, int n_img, int e, int zc, int H, int W, float z_scale, const float* pq_w,
+                  const float* pq_b, int kpad, __half* out, cudaStream_t st) {
+  LR_CHECK(e <= kVaeMaxZ && zc <= kVaeMaxZ && 9 * zc <= kpad, "vae_in: latent channel count out of range");
+  const size_t total = static_cast<size_t>(n_img) * H * W * 9;
+  LR_CUDA(launch_pdl(vae_in_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, 1, z, n_img, e, zc,
+                     H, W, z_scale, pq_w, pq_b, kpad, out));
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_softmax_rows(__half* x, int rows, int T, size_t ld, cudaStream_t st) {
+  LR_CHECK(T % 8 == 0 && ld % 8 == 0 && T <= 256 * 8 * kSoftmaxVecs, "softmax_rows: unsupported row length");
+  LR_CUDA(launch_pdl(softmax_rows_kernel, dim3(rows), dim3(256), 0, st, 1, x, T, ld));
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_transpose_f16(const __half* in, int T, int C, size_t ld_in, __half* out, cudaStream_t st) {
+  LR_CUDA(launch_pdl(transpose_f16_kernel, dim3(cdiv(T, 32), cdiv(C, 32)), dim3(32, 8), 0, st, 1, in, T, C, ld_in, out));
   LR_LAUNCHED();
   return 0;
 }

@@ -53,6 +53,7 @@ struct ConvSpec {
   __half* out = nullptr;
   int ld_out = 0;
   int geglu = 0;
+  float out_scale = 1.0f;  // multiplies the final value (softmax scale of the VAE AttnBlock logits)
   const float* ln_stats = nullptr;  // folded LayerNorm: [M] float2 (mean, rstd) of the input rows, or nullptr
   const float* ln_s = nullptr;      //                   [ncols] column sums of the gamma-folded weight
   // GroupNorm fusion (gemm_tc.cuh header): the input is x * xf_scale[n, c] + xf_shift[n, c] (+ SiLU), applied in shared
@@ -148,6 +149,11 @@ int launch_sep_insert_nchw_f32(const float* x, const float* sep, int n_img, int 
                                cudaStream_t st);
 int launch_cinput_to_nhwc(const float* x, int n_img, int C, int H, int Wc, int x_off, int Wh, __half* out,
                           cudaStream_t st);
+// first-stage decoder helpers (elementwise.cuh)
+int launch_vae_in(const float* z, int n_img, int e, int zc, int H, int W, float z_scale, const float* pq_w,
+                  const float* pq_b, int kpad, __half* out, cudaStream_t st);
+int launch_softmax_rows(__half* x, int rows, int T, size_t ld, cudaStream_t st);
+int launch_transpose_f16(const __half* in, int T, int C, size_t ld_in, __half* out, cudaStream_t st);
 int launch_cast_f32_f16(const float* x, size_t n, __half* out, cudaStream_t st);
 int launch_nhwc_to_nchw_f32(const __half* x, int ld, int n_img, int cout, int H, int W, float* out, cudaStream_t st);
 int launch_nchw_f32_to_nhwc(const float* x, int n_img, int C, int H, int W, __half* out, cudaStream_t st);

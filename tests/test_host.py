@@ -169,6 +169,25 @@ def test_prompt_context_cache():
     assert w.special_embeddings is emb.special_embeddings        # attributes stay reachable through the wrapper
 
 
+def test_vae_decoder_weight_table_matches_the_reference_layout():
+    """N2: AutoencoderKL (decode half) owns the reference's parameter names / shapes (autoencoder.py:33-35,
+    model.py:547-606) and the native decoder's weight table is the same list, in the same order."""
+    from oracle import vae_oracle as V
+    for cfg in (V.SMALL_CFG, V.DEFAULT_CFG):
+        m = leftrefill_b200.AutoencoderKL(ddconfig={k: v for k, v in cfg.items() if k != "embed_dim"},
+                                          embed_dim=cfg["embed_dim"])
+        spec = V.decoder_spec(cfg)
+        assert list(m.state_dict().keys()) == [n for n, _ in spec]
+        assert all(tuple(m.state_dict()[n].shape) == tuple(s) for n, s in spec)
+        assert m.engine_weight_names() == [n for n, _ in spec]
+        assert N.lib().lr_vae_missing_weights(m.engine()) == len(spec)
+    with pytest.raises(N.LRError):
+        m.decode(torch.zeros(1, 4, 8, 8))
+    with pytest.raises(NotImplementedError):
+        leftrefill_b200.Decoder(ch=32, out_ch=3, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=[16], in_channels=3,
+                                resolution=64, z_channels=4)
+
+
 def test_no_cpu_fallback():
     m = leftrefill_b200.UNetModel(**O.SMALL_CFG)
     with pytest.raises(N.LRError):

@@ -105,3 +105,21 @@ def test_nvs_use_sep_vs_reference_golden():
     y = O.nvs_unet_forward(sd, cfg, x[:1], t[:1], ctx[:1], use_sep=False,
                            c_input=torch.tensor(g["c_input_half_nosep"])[:1])
     _close(y.numpy(), g["out.nosep_cin_half"][:1])
+
+
+def test_vae_decoder_vs_reference_golden():
+    """First-stage decode (autoencoder.py:87-90, model.py:547-653): the oracle against the unmodified reference Decoder's
+    output (oracle/make_golden.py --only-vae), incl. the state-dict walk of the full SD2 VAE."""
+    from oracle import vae_oracle as V
+    g = load_golden("vae_small.npz")
+    sd = V.make_state_dict(V.SMALL_CFG, seed=0)
+    taps = {}
+    y = V.decode(sd, V.SMALL_CFG, torch.tensor(g["z"])[:1], scale_factor=float(g["scale_factor"]), taps=taps)
+    _close(y.numpy(), g["out"][:1])
+    _close(taps["mid"].numpy(), g["mid"][:1])
+    spec = V.decoder_spec(V.DEFAULT_CFG)
+    assert len(spec) == 140 and sum(int(np.prod(s)) for _, s in spec) == 49_490_199
+    g = load_golden("vae_full_8x16.npz")
+    y = V.decode(V.make_state_dict(V.DEFAULT_CFG, seed=0), V.DEFAULT_CFG, torch.tensor(g["z"]),
+                 scale_factor=float(g["scale_factor"]))
+    _close(y.numpy(), g["out"])
