@@ -114,11 +114,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(threads=None, canvases=1, repeats=1, warmup=1):
-    """Oracle (CPU fp32 restatement of the reference UNet + DDIM step) on the host cores, bounded sample:
-    one CFG step (UNet batch 2) of `canvases` canvas at 64x128 latent, extrapolated: images/s = canvases/(50*t)."""
+def cpu_baseline(threads=None, canvases=1, repeats=1, warmup=1, decode=True):
+    """Oracle (CPU fp32 restatement of the reference UNet + DDIM step [+ first-stage decoder]) on the host cores, bounded
+    sample: one CFG step (UNet batch 2) of `canvases` canvas at 64x128 latent [+ one decode of that canvas], extrapolated:
+    images/s = canvases / (50 * t_step + t_decode). Returns (step times, decode seconds or 0, threads)."""
     import torch
     from helpers import O, synthetic_inputs
+    from oracle import vae_oracle as V
     if threads:
         torch.set_num_threads(threads)
     cfg = O.DEFAULT_CFG
@@ -137,7 +139,14 @@ def cpu_baseline(threads=None, canvases=1, repeats=1, warmup=1):
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
-    return times, torch.get_num_threads()
+        t_dec = 0.0
+        if decode:
+            del sd
+            vsd = V.make_state_dict(V.DEFAULT_CFG, seed=0)
+            t0 = time.perf_counter()
+            V.decode(vsd, V.DEFAULT_CFG, xT * 0.7, scale_factor=V.SCALE_FACTOR)
+            t_dec = time.perf_counter() - t0
+    return times, t_dec, torch.get_num_threads()
 
 
 def run_reference(args):
@@ -148,13 +157,15 @@ def run_reference(args):
     import torch
     ddim_steps = args.ddim_steps
     batch = args.batch if args.batch > 0 else CONFIGS["c2"]["batch"]
-    times, cores = cpu_baseline(threads=os.cpu_count(), canvases=1, repeats=args.steps, warmup=max(1, min(args.warmup, 1)))
+    times, t_dec, cores = cpu_baseline(threads=os.cpu_count(), canvases=1, repeats=args.steps,
+                                       warmup=max(1, min(args.warmup, 1)), decode=not args.no_decode)
     t = sum(times) / len(times)
-    value = 1.0 / (ddim_steps * t)
-    sample = (f"each step = 1 CFG DDIM step (UNet batch 2, 64x128 latent, fp32) of 1 canvas on {cores} threads; "
-              f"images/s = 1 / ({ddim_steps} x step time)")
+    value = 1.0 / (ddim_steps * t + t_dec)
+    sample = (f"each step = 1 CFG DDIM step (UNet batch 2, 64x128 latent, fp32) of 1 canvas on {cores} threads = {t:.2f} s"
+              f"{'' if args.no_decode else f'; + one first-stage decode of that canvas = {t_dec:.1f} s'}; "
+              f"images/s = 1 / ({ddim_steps} x step time + decode time)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 * ddim_steps * batch,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": (t * ddim_steps + t_dec) * 1e3 * batch,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"batch={batch} ref-inpainting canvases, {ddim_steps} DDIM steps, cfg=2.5, "
                                    "stitched 512x1024 (64x128 latent), SD2-inpainting UNet 865.9M params, random init",
@@ -280,18 +291,29 @@ def run_native(args):
     else:
         unet = device_unet(lr.MultiViewUnetModel, cfg, dev, seed=0, view_num=wl["view"][0], concat_target=wl["view"][1])
     ldm = FakeLDM(unet, dev)
+    # first-stage decoder (SD2 VAE, configs/ref_inpainting.yaml:38-58), native: the reference's log_images ends with
+    # decode_first_stage (inpainting_ldm/ref_inpainting_ldm.py:57), the metric counts decoded 512x1024 images
+    from oracle import vae_oracle as V  # config constants only (ch, ch_mult, scale_factor); weights are drawn on device
+    vae = None
+    if not args.no_decode:
+        vcfg = V.DEFAULT_CFG
+        vae = device_unet(lr.AutoencoderKL, {}, dev, seed=1, ddconfig={k: v for k, v in vcfg.items() if k != "embed_dim"},
+                          embed_dim=vcfg["embed_dim"])
+    z_scale = 1.0 / V.SCALE_FACTOR
 
     # ---- synthetic inputs, rank-specific seed: weak scaling, B canvases per GPU ----
     xT_h, ccat_h, ctx_h, uc_h = [t.pin_memory() for t in synthetic_inputs(B, h=H, w=W, seed=1234 + rank)]
     xT, ccat, ctx, uc = [t.to(dev) for t in (xT_h, ccat_h, ctx_h, uc_h)]
-    out_h = torch.empty(B, 4, H, W).pin_memory()
+    out_h = (torch.empty(B, 3, 8 * H, 8 * W) if vae is not None else torch.empty(B, 4, H, W)).pin_memory()
 
-    def one_batch(x_T, c_cat, c_ctx, c_uc):
+    def one_batch(x_T, c_cat, c_ctx, c_uc, decode=True):
         sampler = lr.DDIMSampler(ldm)
         cond = {"c_concat": [c_cat], "c_crossattn": [c_ctx]}
         ucond = {"c_concat": [c_cat], "c_crossattn": [c_uc]}
         samples, _ = sampler.sample(S, B, (4, H, W), cond, eta=1.0, x_T=x_T, verbose=False,
                                     unconditional_guidance_scale=2.5, unconditional_conditioning=ucond)
+        if vae is not None and decode:
+            return vae.decode(samples, z_scale=z_scale)          # [B, 3, 8H, 8W] images
         return samples
 
     def step_resident():
@@ -331,7 +353,25 @@ def run_native(args):
     N.lib().lr_launch_count_reset()
     t_res = timed(step_resident, args.steps)
     launches = N.lib().lr_launch_count()
+    # the same batch without the decode (latents gathered instead of images): the UNet / sampler share of the metric
+    t_nodec = None
+    if vae is not None:
+        t_nodec = timed(lambda: P.gather_outputs(one_batch(xT, ccat, ctx, uc, decode=False), B * world, rank, world),
+                        max(1, args.steps // 2))
+        t_nodec /= max(1, args.steps // 2)
     clk = clocks.stop() if rank == 0 else None
+    dec_ms = None
+    if vae is not None:
+        zz = torch.randn(B, 4, H, W, device=dev) * 0.7
+        vae.decode(zz, z_scale=z_scale)
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(5):
+            vae.decode(zz, z_scale=z_scale)
+        d1.record()
+        torch.cuda.synchronize()
+        dec_ms = d0.elapsed_time(d1) / 5
 
     # ---- per-kernel-class profile of the UNet forward (CUDA events between plan steps, same process) ----
     import ctypes
@@ -422,11 +462,13 @@ def run_native(args):
 
     cb = None
     if world == 1 and args.config == "c2":  # the CPU baseline is reported at N = 1 only (and for the headline config)
-        cb_times, cores = cpu_baseline(threads=os.cpu_count(), canvases=1, repeats=1, warmup=1)
+        cb_times, cb_dec, cores = cpu_baseline(threads=os.cpu_count(), canvases=1, repeats=1, warmup=1,
+                                               decode=vae is not None)
         cb_t = sum(cb_times) / len(cb_times)
-        cb = {"value": 1.0 / (S * cb_t), "unit": UNIT, "cores": cores, "kind": "port",
+        cb = {"value": 1.0 / (S * cb_t + cb_dec), "unit": UNIT, "cores": cores, "kind": "port",
               "sample": f"1 CFG DDIM step (UNet batch 2, 64x128 latent, fp32 oracle) of 1 canvas = {cb_t:.2f} s on "
-                        f"{cores} threads; images/s = 1/({S} x step)"}
+                        f"{cores} threads, first-stage decode of 1 canvas = {cb_dec:.1f} s; images/s = 1/({S} x step + "
+                        "decode)"}
 
     images = nsamp * world * args.steps
     h2d = sum(t.numel() * t.element_size() for t in (xT_h, ccat_h, ctx_h, uc_h))
@@ -435,12 +477,20 @@ def run_native(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": wl["name"].format(B=nsamp, S=S), "name": args.config,
                        "l2": "inputs larger than L2: 1.73 GB fp16 weights + >2 GB activations per UNet forward vs 126 MB",
-                       "parallelism": f"dp{world}: canvases sharded, weights replicated, 1 all-gather per batch",
+                       "parallelism": f"dp{world}: canvases sharded, weights replicated, 1 all-gather of the decoded "
+                                      "images per batch",
                        "precision": "fp16 operands, fp32 accumulate / norm statistics / softmax / DDIM state"},
+            "decode": None if vae is None else {
+                "included_in_value_and_e2e": True, "ms_per_batch": dec_ms, "tflop_per_batch": vae.last_flops() / 1e12,
+                "tflops": vae.last_flops() / dec_ms / 1e9,
+                "value_without_decode": nsamp * world / t_nodec, "unit": UNIT,
+                "note": "native first-stage decoder (lr_vae_decode) after the 50 DDIM steps; value_without_decode "
+                        "gathers the latents instead (the round-1 definition of the metric)"},
             "unet_ms_per_ddim_step": unet_ms, "unet_tflops": unet_flops / unet_ms / 1e9,
             "unet_tflop_per_forward": unet_flops / 1e12,
             "e2e": {"value": images / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": out_h.numel() * 4},
+                    "d2h_bytes_per_step": out_h.numel() * 4,
+                    "result": "decoded fp32 images" if vae is not None else "fp32 latents"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cb,
             "gpu_reference": gref}
     print(json.dumps(line), flush=True)
@@ -459,6 +509,7 @@ def main():
                                                          "2 multiview samples for c4); the UNet batch is 2x rows with CFG")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the PyTorch-ops-on-GPU context leg")
+    ap.add_argument("--no-decode", action="store_true", help="stop at the latents (no first-stage decode)")
     ap.add_argument("--ddim-steps", type=int, default=50)
     args = ap.parse_args()
     if args.impl == "reference":

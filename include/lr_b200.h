@@ -191,6 +191,12 @@ int lr_gn_linear_f16(const void* a, int M, int K, int rows_per_img, const float*
 int lr_gn_finalize(const float* part0, int ppi0, int c0, const float* part1, int ppi1, int c1, int n, int P, int groups,
                    float eps, const float* gamma, const float* beta, float* scale, float* shift, void* stream);
 
+/* Upsample.forward (openaimodel.py:108-116; model.py:62-66) = F.interpolate(x, scale_factor=2, mode="nearest") + 3x3 conv,
+ * without materialising the upsampled tensor: four 2x2-tap convs on x [n, h, w, cin], one per output phase, with the 3x3
+ * taps that read the same source pixel pre-summed (4/9 of the FLOPs). wt [cout, 9*cin] as for lr_conv3x3_f16;
+ * wfold_scratch: 16*cout*cin fp16 elements; out [n, 2h, 2w, cout]. cout % 32 == 0. */
+int lr_upsample2x_conv3x3_f16(const void* x, int n, int h, int w, int cin, const void* wt, int cout, const float* bias,
+                              void* wfold_scratch, void* out, void* stream);
 /* softmax(q k^T * scale) v, d_head = 64. q [batch*tq, ldq] (head h at columns q_col0 + 64h), likewise k, v over tk
  * tokens; out [batch*tq, ld_out]. Replaces attention.py:176-195. */
 int lr_attention_f16(const void* q, int ldq, int q_col0, const void* k, int ldk, int k_col0, const void* v, int ldv,

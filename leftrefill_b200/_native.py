@@ -105,6 +105,8 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, POINTER(c_int), c_int, c_void_p]),
     "lr_gn_finalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lr_upsample2x_conv3x3_f16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                          c_void_p, c_void_p]),
     "lr_attention_f16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
                                  c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "lr_groupnorm_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,

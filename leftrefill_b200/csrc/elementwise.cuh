@@ -726,6 +726,34 @@ __global__ void upsample2x_nhwc_kernel(const __half* __restrict__ x, int n_img, 
   *reinterpret_cast<uint4*>(out + m * C + v * 8) = val;
 }
 
+// Upsample folded into its conv (gemm_tc.cuh header): w [O, 9*I] fp16 (k = (ky*3 + kx)*I + i) -> out [4][O][4*I],
+// phase = py*2 + px, k = (a*2 + b)*I + i. Output row 2y + py of the upsampled image reads, through tap ky, upsampled row
+// 2y + py + ky - 1 = source row y + floor((py + ky - 1) / 2):
+//   py = 0: y - 1 (tap ky = 0) and y (taps ky = 1, 2);   py = 1: y (taps ky = 0, 1) and y + 1 (tap ky = 2)
+// so source offset index a in {0, 1} (offset py - 1 + a) collects the taps with floor((py + ky - 1) / 2) == py - 1 + a;
+// columns alike. The fp16 tap weights are summed in fp32 and rounded to fp16 once.
+__global__ void upfold_weights_kernel(const __half* __restrict__ w, int O, int I, __half* __restrict__ out) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(4) * O * 4 * I;
+  if (idx >= total) return;
+  const int i = static_cast<int>(idx % I);
+  const int ab = static_cast<int>((idx / I) % 4);
+  const int o = static_cast<int>((idx / (static_cast<size_t>(4) * I)) % O);
+  const int phase = static_cast<int>(idx / (static_cast<size_t>(4) * I * O));
+  const int py = phase >> 1, px = phase & 1, a = ab >> 1, b = ab & 1;
+  float acc = 0.f;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int sy = (py + ky - 1 + 2) / 2 - 1;  // floor((py + ky - 1) / 2) for arguments >= -2
+    if (sy != py - 1 + a) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int sx = (px + kx - 1 + 2) / 2 - 1;
+      if (sx != px - 1 + b) continue;
+      acc += __half2float(w[static_cast<size_t>(o) * 9 * I + (ky * 3 + kx) * I + i]);
+    }
+  }
+  out[idx] = __float2half_rn(acc);
+}
+
 // Multiview re-arranged self-attention (ldm/modules/multiview_attention.py:436-462, concat_target=True): every UNet
 // batch row is a stitched [ref_i | target] canvas of hh x (2*side) tokens. The attention sequence of sample b is
 // [target (taken from row 0), ref_1 .. ref_v], each block hh*side tokens. gather: dst[b, k, y, x] <- src; scatter:

@@ -54,6 +54,10 @@ struct STW {
 struct ConvW {
   int cin = 0, cout = 0;
   size_t w, b;
+  // Upsample convs: the four 2x2 phase matrices [4][cout][4 * cin] of the folded nearest-x2 + 3x3 conv (gemm_tc.cuh
+  // header), rebuilt by run_folds() whenever a weight changes
+  bool is_up = false;
+  size_t wfold = 0;
 };
 enum NodeKind { N_CONV_IN, N_RES, N_ST, N_DOWN, N_UP };
 struct Node {
@@ -379,6 +383,7 @@ struct lr_engine {
         }
         if (level > 0 && i == cfg.num_res_blocks[level]) {
           blk.push_back({N_UP, add_conv(p + std::to_string(sub) + ".conv.", ch, ch, 9 * ch)});
+          mark_up_conv(blk.back().idx);
           ds /= 2;
         }
         output_blocks.push_back(blk);
@@ -421,8 +426,22 @@ struct lr_engine {
 
   bool fold_dirty = true;
   bool ln_fold = getenv("LR_NO_LN_FOLD") == nullptr;
+  bool up_fold = getenv("LR_NO_UPFOLD") == nullptr;
+  // marks conv `idx` as the conv of an Upsample and reserves its folded weights
+  void mark_up_conv(int idx) {
+    ConvW& c = convs[idx];
+    c.is_up = true;
+    c.wfold = halloc(static_cast<size_t>(16) * c.cout * c.cin);
+  }
   int run_folds(cudaStream_t st) {
-    if (!fold_dirty || !ln_fold) return 0;
+    if (!fold_dirty) return 0;
+    if (up_fold)
+      for (const ConvW& c : convs)
+        if (c.is_up) LR_TRY(launch_upfold_weights(H(c.w), c.cout, c.cin, H(c.wfold), st));
+    if (!ln_fold) {
+      fold_dirty = false;
+      return 0;
+    }
     for (const STW& s : sts) {
       const int C = s.C;
       for (const TBlockW& b : s.blocks) {
@@ -1028,6 +1047,55 @@ struct lr_engine {
     return 0;
   }
 
+  // Upsample.forward (openaimodel.py:108-116; model.py:62-66): nearest x2 then conv3x3. Large images run the FOLDED
+  // form (four 2x2-tap convs on the low-resolution input, each writing one output phase through a strided TMA store:
+  // 4/9 of the FLOPs, no 4x tensor); below kUpFoldMinPixels low-resolution pixels PER IMAGE four quarter-size launches
+  // cannot fill the GPU and the upsampled tensor is materialised instead. The choice must not depend on the batch size:
+  // the folded weights round differently, and results are batch / world-size invariant by contract.
+  static constexpr int kUpFoldMinPixels = 512;
+  int plan_upsample(const ConvW& c, Act x, int n, Act* out) {
+    const int hh = x.H, ww = x.W, cc = x.C;
+    const bool fold = up_fold && c.is_up && hh * ww >= kUpFoldMinPixels && c.cout % 32 == 0;
+    if (!fold) {
+      __half* up;
+      LR_TRY(acquire_h(static_cast<size_t>(n) * 4 * hh * ww * cc, &up));
+      const __half* src = x.p;
+      push([=](cudaStream_t st) { return launch_upsample2x(src, n, hh, ww, cc, up, st); });
+      Act u{up, cc, 2 * hh, 2 * ww};
+      LR_TRY(plan_conv3(c, u, n, 1, out));
+      release(up);
+      return 0;
+    }
+    __half* o;
+    const size_t co = c.cout;
+    LR_TRY(acquire_h(static_cast<size_t>(n) * 4 * hh * ww * co, &o));
+    for (int phase = 0; phase < 4; ++phase) {
+      const int py = phase >> 1, px = phase & 1;
+      ConvSpec s;
+      s.a0 = x.p;
+      s.c0 = cc;
+      s.lda0 = cc;
+      s.n_img = n;
+      s.in_h = hh;
+      s.in_w = ww;
+      s.taps = 4;
+      s.up_oy = py - 1;
+      s.up_ox = px - 1;
+      s.w = H(c.wfold) + static_cast<size_t>(phase) * co * 4 * cc;
+      s.ldw = 4 * cc;
+      s.ncols = c.cout;
+      s.bias = F(c.b);
+      s.out = o + (static_cast<size_t>(py) * 2 * ww + px) * co;
+      s.ld_out = c.cout;
+      s.out_sx = 2 * co;
+      s.out_sy = 2 * (2 * static_cast<size_t>(ww)) * co;
+      s.out_sn = static_cast<size_t>(4) * hh * ww * co;
+      LR_TRY(add_conv_step(s));
+    }
+    *out = Act{o, c.cout, 2 * hh, 2 * ww};
+    return 0;
+  }
+
   int plan_block(const std::vector<Node>& blk, Act h, Act skip, int n, Act* out, bool release_input) {
     Act cur = h;
     bool cur_owned = false;  // whether `cur` is a temporary we may release
@@ -1043,15 +1111,7 @@ struct lr_engine {
       } else if (nd.kind == N_DOWN) {
         LR_TRY(plan_conv3(convs[nd.idx], cur, n, 2, &nxt));
       } else if (nd.kind == N_UP) {
-        // Upsample.forward (openaimodel.py:108-116): nearest x2 then conv3x3
-        __half* up;
-        LR_TRY(acquire_h(static_cast<size_t>(n) * 4 * cur.H * cur.W * cur.C, &up));
-        const __half* src = cur.p;
-        const int hh = cur.H, ww = cur.W, cc = cur.C;
-        push([=](cudaStream_t st) { return launch_upsample2x(src, n, hh, ww, cc, up, st); });
-        Act u{up, cur.C, 2 * cur.H, 2 * cur.W};
-        LR_TRY(plan_conv3(convs[nd.idx], u, n, 1, &nxt));
-        release(up);
+        LR_TRY(plan_upsample(convs[nd.idx], cur, n, &nxt));
       } else {
         LR_CHECK(false, "unexpected node");
       }
@@ -1484,8 +1544,11 @@ struct lr_vae : lr_engine {
                                                 block_in, block_out));
         block_in = block_out;
       }
-      if (lvl != 0) by_level[lvl].up_conv = add_conv(d + "up." + std::to_string(lvl) + ".upsample.conv.", block_out, block_out,
-                                                     9 * block_out);
+      if (lvl != 0) {
+        by_level[lvl].up_conv = add_conv(d + "up." + std::to_string(lvl) + ".upsample.conv.", block_out, block_out,
+                                         9 * block_out);
+        mark_up_conv(by_level[lvl].up_conv);
+      }
     }
     for (int lvl = c.num_levels - 1; lvl >= 0; --lvl) levels.push_back(by_level[lvl]);
     no_g = reg_vec(d + "norm_out.weight", last);
@@ -1628,17 +1691,10 @@ struct lr_vae : lr_engine {
     for (const VaeLevel& lv : levels) {
       for (int idx : lv.blocks) LR_TRY(step_res(idx));
       if (lv.up_conv >= 0) {
-        // Upsample (model.py:62-66): nearest x2, then conv3x3
-        __half* up;
-        LR_TRY(acquire_h(static_cast<size_t>(n) * 4 * h.H * h.W * h.C, &up));
-        const __half* src = h.p;
-        const int hh = h.H, ww = h.W, cc = h.C;
-        push([=](cudaStream_t st) { return launch_upsample2x(src, n, hh, ww, cc, up, st); });
-        release(h.p);
-        Act u{up, cc, 2 * hh, 2 * ww};
+        // Upsample (model.py:62-66): nearest x2, then conv3x3 (folded: plan_upsample)
         Act o;
-        LR_TRY(plan_conv3(convs[lv.up_conv], u, n, 1, &o));
-        release(up);
+        LR_TRY(plan_upsample(convs[lv.up_conv], h, n, &o));
+        release(h.p);
         h = o;
       }
     }
@@ -1946,6 +2002,7 @@ int lr_vae_decode(lr_vae* h, const float* z, float z_scale, float* out, int n, i
   const int missing = engine_missing_weights(h);
   LR_CHECK(missing == 0, "lr_vae_decode: " + std::to_string(missing) + " weights not uploaded");
   LR_TRY(h->ensure_arenas());
+  LR_TRY(h->run_folds(static_cast<cudaStream_t>(stream)));
   h->z_scale = z_scale;
   LR_TRY(h->build_plan_vae(n, H, W));
   h->in_z = z;
@@ -2122,6 +2179,44 @@ int lr_gn_finalize(const float* part0, int ppi0, int c0, const float* part1, int
   if (n == 0) return 0;
   return launch_gn_finalize(part0, ppi0, c0, part1, part1 ? ppi1 : 0, part1 ? c1 : 0, n, P, groups, eps, gamma, beta, scale,
                             shift, static_cast<cudaStream_t>(stream));
+}
+
+int lr_upsample2x_conv3x3_f16(const void* x, int n, int h, int w, int cin, const void* wt, int cout, const float* bias,
+                              void* wfold_scratch, void* out, void* stream) {
+  LR_CHECK(x && wt && wfold_scratch && out, "lr_upsample2x_conv3x3_f16: null argument");
+  LR_CHECK(cout % 32 == 0 && cin % 8 == 0, "lr_upsample2x_conv3x3_f16: cout must be a multiple of 32, cin of 8");
+  if (n == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __half* wf = static_cast<__half*>(wfold_scratch);
+  LR_TRY(launch_upfold_weights(static_cast<const __half*>(wt), cout, cin, wf, st));
+  __half* o = static_cast<__half*>(out);
+  const size_t co = cout;
+  for (int phase = 0; phase < 4; ++phase) {
+    const int py = phase >> 1, px = phase & 1;
+    ConvSpec s;
+    s.a0 = static_cast<const __half*>(x);
+    s.c0 = cin;
+    s.lda0 = cin;
+    s.n_img = n;
+    s.in_h = h;
+    s.in_w = w;
+    s.taps = 4;
+    s.up_oy = py - 1;
+    s.up_ox = px - 1;
+    s.w = wf + static_cast<size_t>(phase) * co * 4 * cin;
+    s.ldw = 4 * cin;
+    s.ncols = cout;
+    s.bias = bias;
+    s.out = o + (static_cast<size_t>(py) * 2 * w + px) * co;
+    s.ld_out = cout;
+    s.out_sx = 2 * co;
+    s.out_sy = 2 * (2 * static_cast<size_t>(w)) * co;
+    s.out_sn = static_cast<size_t>(4) * h * w * co;
+    ConvOp op;
+    LR_TRY(build_conv_op(&op, s));
+    LR_TRY(launch_conv_op(op, st));
+  }
+  return 0;
 }
 
 int lr_attention_f16(const void* q, int ldq, int q_col0, const void* k, int ldk, int k_col0, const void* v, int ldv,

@@ -10,6 +10,11 @@
 //     conv padding, and the tensor map's element strides implement stride 2.
 //   * the skip concat `th.cat([h, hs.pop()], 1)` (openaimodel.py:781) is never materialised: the K loop walks two
 //     tensor maps (source 0 = h, source 1 = skip) back to back.
+//   * Upsample (openaimodel.py:108-116, model.py:62-66) = nearest x2 followed by a 3x3 conv is never materialised
+//     either: output pixel (2y + py, 2x + px) only sees the 2 x 2 source pixels (y + py - 1 + a, x + px - 1 + b), so
+//     each of the four output phases (py, px) is a 4-tap conv on the LOW-resolution input with pre-summed weights
+//     (upfold_weights_kernel) whose TMA store walks the output with a pixel stride of 2: 4/9 of the FLOPs and no 4x
+//     tensor.
 //   * HALO mode (stride-1 3x3 convs on images at least 16 rows high): the output tile is 8 pixels wide x 16 rows, and
 //     for every 64-channel chunk ONE TMA box of (8+2) x (16+2) input pixels is loaded and re-used by all nine taps: the
 //     A descriptor of tap (dy, dx) simply starts ((dy+1)*10 + (dx+1)) rows further into that box, with a stride of
@@ -92,7 +97,8 @@ struct GemmParams {
   int bw, bh, bn;    // tile box: bw*bh*bn == 128 output pixels
   int tiles_x, tiles_y, tiles_b, tiles_n;
   int stride;        // 1 or 2 (input coordinate = stride * output coordinate + tap offset)
-  int taps;          // 1 or 9
+  int taps;          // 1, 9 (3x3) or 4 (one 2x2 phase of a nearest-x2 upsample folded into the following 3x3 conv)
+  signed char tap_dy[9], tap_dx[9];  // input offset of every tap (plain mode)
   int kc0, kc1;      // 64-channel chunks per tap in source 0 / source 1
   int c0, ctot;      // channels of source 0, total channels (K extent of one tap in B)
   int ncols;         // GEMM N
@@ -380,8 +386,7 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
       const int x0 = tx * p.bw * p.stride, y0 = ty * p.bh * p.stride, n0 = tb * p.bn;
       const int ncol0 = tn * p.block_n + static_cast<int>(rank) * b_rows;  // this CTA's share of the weight rows
       for (int tap = tap_b; tap < tap_e; ++tap) {
-        const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
-        const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+        const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
         for (int kc = 0; kc < p.kc0 + p.kc1; ++kc) {
           mbar_wait(&empty[s], ph ^ 1);
           if (elect_one()) {
@@ -876,7 +881,7 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
             __half* o = p.out + grow * p.ld_out + oc0;
             float g[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = f[2 * j] * gelu_erf(f[2 * j + 1]) * p.out_scale;
+            for (int j = 0; j < 16; ++j) g[j] = f[2 * j] * gelu_erf(f[2 * j + 1]);  // (out_scale is never used with GEGLU)
             if (p.tma_store) {
               const uint4 w0 = make_uint4(pack_half2(g[0], g[1]), pack_half2(g[2], g[3]), pack_half2(g[4], g[5]),
                                           pack_half2(g[6], g[7]));
@@ -922,12 +927,14 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
               const int slab = c >> 6, cp0 = (c & 63) >> 3;
               uint8_t* rowp = (slab < full_slabs) ? cstage + slab * (kBlockM * 128) + r * 128
                                                   : cstage + full_slabs * (kBlockM * 128) + r * 64;
+              if (p.out_scale != 1.0f) {  // only the VAE attention logits carry a scale: keep the multiply off the common path
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+              }
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                uint4 w = make_uint4(pack_half2(f[k * 8 + 0] * p.out_scale, f[k * 8 + 1] * p.out_scale),
-                                     pack_half2(f[k * 8 + 2] * p.out_scale, f[k * 8 + 3] * p.out_scale),
-                                     pack_half2(f[k * 8 + 4] * p.out_scale, f[k * 8 + 5] * p.out_scale),
-                                     pack_half2(f[k * 8 + 6] * p.out_scale, f[k * 8 + 7] * p.out_scale));
+                uint4 w = make_uint4(pack_half2(f[k * 8 + 0], f[k * 8 + 1]), pack_half2(f[k * 8 + 2], f[k * 8 + 3]),
+                                     pack_half2(f[k * 8 + 4], f[k * 8 + 5]), pack_half2(f[k * 8 + 6], f[k * 8 + 7]));
                 if (!p.tma_store) reinterpret_cast<uint4*>(o)[k] = w;
                 else if (slab < full_slabs) *reinterpret_cast<uint4*>(rowp + (((cp0 + k) ^ (r & 7)) << 4)) = w;
                 else *reinterpret_cast<uint4*>(rowp + ((cp0 + k) << 4)) = w;

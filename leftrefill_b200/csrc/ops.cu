@@ -220,7 +220,9 @@ bool conv_is_halo(const ConvSpec& s) { return conv_tiling(s).halo; }
 
 int build_conv_op(ConvOp* op, const ConvSpec& s) {
   LR_CHECK(s.a0 && s.w && s.out, "conv: null pointer");
-  LR_CHECK(s.taps == 1 || s.taps == 9, "conv: taps must be 1 or 9");
+  LR_CHECK(s.taps == 1 || s.taps == 9 || s.taps == 4, "conv: taps must be 1, 9 or 4 (folded upsample phase)");
+  LR_CHECK(s.taps != 4 || (s.stride == 1 && s.out_sx > 0 && !s.geglu && s.residual == nullptr && s.xf_scale == nullptr),
+           "conv: a folded-upsample phase needs stride 1, explicit output strides and a plain epilogue");
   LR_CHECK(s.stride == 1 || s.stride == 2, "conv: stride must be 1 or 2");
   LR_CHECK(s.c0 % 8 == 0 && s.c1 % 8 == 0 && s.lda0 % 8 == 0 && (s.a1 == nullptr || s.lda1 % 8 == 0),
            "conv: channel counts / leading dims must be multiples of 8 (use the im2col path otherwise)");
@@ -249,6 +251,10 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   p.tiles_b = cdiv(s.n_img, bn);
   p.stride = s.stride;
   p.taps = s.taps;
+  for (int t = 0; t < 9; ++t) {
+    p.tap_dy[t] = static_cast<signed char>(s.taps == 9 ? t / 3 - 1 : (s.taps == 4 ? s.up_oy + t / 2 : 0));
+    p.tap_dx[t] = static_cast<signed char>(s.taps == 9 ? t % 3 - 1 : (s.taps == 4 ? s.up_ox + t % 2 : 0));
+  }
   p.kc0 = cdiv(s.c0, kBlockK);
   p.kc1 = cdiv(s.c1, kBlockK);
   p.c0 = s.c0;
@@ -381,6 +387,7 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   }
   p.trace = debug_trace_buffer();
   LR_CHECK(!(s.geglu && s.residual), "conv: GEGLU + residual not supported");
+  LR_CHECK(!(s.geglu && s.out_scale != 1.0f), "conv: GEGLU + out_scale not supported");
 
   // activations: [C, W, H, N]
   {
@@ -431,6 +438,11 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
                         static_cast<uint64_t>(s.n_img)};
     uint64_t str[3] = {static_cast<uint64_t>(s.ld_out) * 2, static_cast<uint64_t>(s.ld_out) * 2 * Wo,
                        static_cast<uint64_t>(s.ld_out) * 2 * Wo * Ho};
+    if (s.out_sx > 0) {  // strided output (folded upsample phase: every other pixel of the high-resolution tensor)
+      str[0] = s.out_sx * 2;
+      str[1] = s.out_sy * 2;
+      str[2] = s.out_sn * 2;
+    }
     uint32_t box[4] = {64, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
     uint32_t es[4] = {1, 1, 1, 1};
     LR_TRY(make_tmap(&p.tmC, s.out, 4, dims, str, box, es, true));
@@ -463,6 +475,8 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
       op->stats_ppi = ppi;
     }
   }
+  LR_CHECK(s.out_sx == 0 || (tma_store && ksplit == 1),
+           "conv: a strided output needs the TMA-store epilogue (cout a multiple of 32, 16-byte aligned rows)");
   const int num_units = cdiv(tiles_m, cg) * p.tiles_n * ksplit;
   op->ksplit = ksplit;
   op->ncols = s.ncols;
@@ -834,6 +848,12 @@ int launch_softmax_rows(__half* x, int rows, int T, size_t ld, cudaStream_t st) 
 }
 int launch_transpose_f16(const __half* in, int T, int C, size_t ld_in, __half* out, cudaStream_t st) {
   LR_CUDA(launch_pdl(transpose_f16_kernel, dim3(cdiv(T, 32), cdiv(C, 32)), dim3(32, 8), 0, st, 1, in, T, C, ld_in, out));
+  LR_LAUNCHED();
+  return 0;
+}
+int launch_upfold_weights(const __half* w, int O, int I, __half* out, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(4) * O * 4 * I;
+  upfold_weights_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(w, O, I, out);
   LR_LAUNCHED();
   return 0;
 }

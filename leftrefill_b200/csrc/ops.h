@@ -41,7 +41,11 @@ struct ConvSpec {
   int c1 = 0, lda1 = 0;
   int n_img = 1, in_h = 1, in_w = 1;
   int stride = 1;  // 1 or 2
-  int taps = 1;    // 1 (linear / 1x1 conv) or 9 (3x3, pad 1)
+  int taps = 1;    // 1 (linear / 1x1 conv), 9 (3x3, pad 1) or 4 (2x2 phase of a folded nearest-x2 upsample + 3x3 conv:
+                   // taps at input offsets (up_oy + a, up_ox + b), a, b in {0, 1}; needs out_sx / out_sy / out_sn)
+  int up_oy = 0, up_ox = 0;
+  // output pixel strides in elements (0 = dense [n, Ho, Wo, ld_out]); `out` is the first pixel written
+  size_t out_sx = 0, out_sy = 0, out_sn = 0;
   const __half* w = nullptr;  // [ncols, ldw] fp16, k = tap*(c0+c1) + c
   int ldw = 0;
   int ncols = 0;
@@ -154,6 +158,9 @@ int launch_vae_in(const float* z, int n_img, int e, int zc, int H, int W, float 
                   const float* pq_b, int kpad, __half* out, cudaStream_t st);
 int launch_softmax_rows(__half* x, int rows, int T, size_t ld, cudaStream_t st);
 int launch_transpose_f16(const __half* in, int T, int C, size_t ld_in, __half* out, cudaStream_t st);
+// nearest-x2 upsample folded into the following 3x3 conv: w [O, 9*I] (k = tap*I + i) -> 4 phase matrices [4][O, 4*I]
+// (phase = py*2 + px, k = (a*2 + b)*I + i) with the taps that read the same source pixel summed in fp32
+int launch_upfold_weights(const __half* w, int O, int I, __half* out, cudaStream_t st);
 int launch_cast_f32_f16(const float* x, size_t n, __half* out, cudaStream_t st);
 int launch_nhwc_to_nchw_f32(const __half* x, int ld, int n_img, int cout, int H, int W, float* out, cudaStream_t st);
 int launch_nchw_f32_to_nhwc(const float* x, int n_img, int C, int H, int W, __half* out, cudaStream_t st);

@@ -68,6 +68,19 @@ def conv3x3(x0, wt, bias=None, x1=None, stride=1, bias_img=None, residual=None, 
     return out
 
 
+def upsample2x_conv3x3(x, wt, bias=None):
+    """nearest x2 upsample + 3x3 conv (pad 1) of NHWC fp16 x [n, h, w, cin] without the upsampled tensor: four folded
+    2x2-tap phase convs. wt fp16 [cout, 9*cin] (repack_conv3x3). Returns [n, 2h, 2w, cout]."""
+    _chk(x, torch.float16)
+    n, h, w, cin = x.shape
+    cout = wt.shape[0]
+    out = torch.empty(n, 2 * h, 2 * w, cout, dtype=torch.float16, device=x.device)
+    scratch = torch.empty(16 * cout * cin, dtype=torch.float16, device=x.device)
+    N.check(N.lib().lr_upsample2x_conv3x3_f16(N.ptr(x), n, h, w, cin, N.ptr(_chk(wt, torch.float16)), cout, N.ptr(bias),
+                                              N.ptr(scratch), N.ptr(out), N.current_stream()), "upsample2x_conv3x3")
+    return out
+
+
 def attention(q, k, v, heads, scale=None):
     """q [b, tq, heads*64], k/v [b, tk, heads*64] fp16 (may be column slices of wider tensors). Returns [b, tq, heads*64]."""
     assert q.dtype == k.dtype == v.dtype == torch.float16

@@ -92,6 +92,25 @@ def case_conv(n, h, w, c0, cout, c1=0, stride=1, bias_img=False, residual=False,
                   out.reshape(-1, cout), ref.reshape(-1, cout))
 
 
+def case_upconv(n, h, w, cin, cout, seed=0):
+    """Upsample (nearest x2 + conv3x3) folded into four 2x2-tap phase convs vs F.interpolate + F.conv2d."""
+    import torch
+    import torch.nn.functional as F
+    from leftrefill_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(n, cin, h, w, generator=g).cuda()
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    x0 = ops.to_nhwc_f16(x)
+    out = ops.upsample2x_conv3x3(x0, ops.repack_conv3x3(wt), bias=b)
+    torch.cuda.synchronize()
+    ref = F.conv2d(F.interpolate(x.half().float(), scale_factor=2, mode="nearest"), wt.half().float(), b, padding=1)
+    # the folded weights are fp16(sum of fp16 taps): one extra weight rounding (2^-11) -> rtol 2e-3
+    return report(f"upsample+conv n={n} {h}x{w} {cin}->{cout}", out.reshape(-1, cout),
+                  ref.permute(0, 2, 3, 1).reshape(-1, cout), rtol=2e-3, atol_scale=4e-4)
+
+
 def case_attn(b, heads, tq, tk, fused_qkv=False, seed=0):
     import torch
     from leftrefill_b200 import ops
@@ -403,6 +422,9 @@ CASES = {
     "conv_s2": lambda: case_conv(2, 16, 32, 64, 64, stride=2),
     "conv_s2_big": lambda: case_conv(2, 64, 128, 64, 64, stride=2),
     "conv_cout4": lambda: case_conv(2, 16, 32, 64, 4),
+    "upconv_small": lambda: case_upconv(2, 8, 16, 64, 64),
+    "upconv_ragged": lambda: case_upconv(1, 9, 13, 64, 96),
+    "upconv_big": lambda: case_upconv(2, 32, 64, 640, 640),
     "attn_min": lambda: case_attn(1, 1, 128, 128),
     "attn_q384": lambda: case_attn(2, 1, 384, 256),
     "attn_k4": lambda: case_attn(1, 2, 256, 512),

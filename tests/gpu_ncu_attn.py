@@ -47,6 +47,12 @@ elif kind == "conv1280":
     b = torch.zeros(1280, device="cuda")
     for _ in range(3):
         ops.conv3x3(x, w, bias=b)
+elif kind == "geglu":
+    a = torch.randn(65536, 320, device="cuda").half()
+    w = torch.randn(2560, 320, device="cuda").half() * 0.05
+    b = torch.zeros(2560, device="cuda")
+    for _ in range(3):
+        ops.linear(a, w, bias=b, geglu=True)
 elif kind == "lin320":
     a = torch.randn(65536, 320, device="cuda").half()
     w = torch.randn(320, 320, device="cuda").half() * 0.05
