@@ -598,12 +598,34 @@ struct lr_engine {
     push([raw](cudaStream_t st) { return launch_conv_op(*raw, st); }, 0, raw->flops, d);
     return 0;
   }
+  // Row-statistics hand-over between the Linears of a transformer block (gemm_tc.cuh GemmParams::rowstats_out / ln_part):
+  // the GEMM that writes the residual stream leaves per-row (sum, sum of squares) partials, the GEMM that consumes its
+  // LayerNorm finishes mean / rstd in its epilogue; no statistics pass over the activation in between.
+  struct RowStats {
+    float* table = nullptr;  // [M][ld] float2
+    int ld = 0;
+    int slots = 0;           // valid entries per row (0: the current content of the stream has no partials)
+  };
+  // Measured on B200 (round 2, profiles/r2_ab_ln_rowstats.txt): the 48 ln_stats_kernel passes (0.58 ms) disappear, but the
+  // producing Linears are epilogue bound - the extra 2 FP ops per element and the consumer's per-row partial loads cost
+  // 0.4-0.7 ms: forward 19.72 ms with, 19.57 ms without. OFF by default (LR_LN_ROWSTATS=1 enables; parity-tested).
+  bool ln_rowstats = getenv("LR_LN_ROWSTATS") != nullptr && atoi(getenv("LR_LN_ROWSTATS")) != 0;
   int add_linear(const __half* a, int M, int K, const __half* w, int ncols, const float* bias, const __half* residual,
                  int ld_res, __half* out, int ld_out, int geglu, const float* ln_stats = nullptr,
-                 const float* ln_s = nullptr) {
+                 const float* ln_s = nullptr, const RowStats* ln_from = nullptr, RowStats* stats_to = nullptr) {
     ConvSpec s;
     s.ln_stats = ln_stats;
     s.ln_s = ln_s;
+    if (ln_from != nullptr) {  // LayerNorm statistics from the producer's partials instead of ln_stats
+      s.ln_stats = nullptr;
+      s.ln_part = ln_from->table;
+      s.ln_slots = ln_from->slots;
+      s.ln_ld = ln_from->ld;
+    }
+    if (stats_to != nullptr && stats_to->table != nullptr) {
+      s.rowstats_out = stats_to->table;
+      s.rowstats_ld = stats_to->ld;
+    }
     s.a0 = a;
     s.c0 = K;
     s.lda0 = K;
@@ -620,7 +642,10 @@ struct lr_engine {
     s.out = out;
     s.ld_out = ld_out;
     s.geglu = geglu;
-    return add_conv_step(s);
+    ConvOp* op = nullptr;
+    LR_TRY(add_conv_step(s, &op));
+    if (stats_to != nullptr) stats_to->slots = op->rowstats_slots;
+    return 0;
   }
   // GroupNorm statistics: one (sum, sumsq) slot per call site, all zeroed by a single memset at the start of forward
   unsigned char* gn_stats = nullptr;
@@ -831,6 +856,25 @@ struct lr_engine {
     int M = n * P;
     __half *xn, *h, *t, *qkv, *a, *g, *o;
     LR_TRY(acquire_h(static_cast<size_t>(Mfull) * C, &h));
+    // per-row LayerNorm partials of the residual stream h, rewritten by every Linear that writes h (RowStats)
+    RowStats rs;
+    if (ln_fold && ln_rowstats) {
+      rs.ld = 2 * ((C + 31) / 32);
+      LR_TRY(acquire_f(static_cast<size_t>(Mfull) * rs.ld * 2, &rs.table));
+    }
+    auto dup_rowstats = [&](int rows) {  // CFG-pair prefix: replicate the partials of the first `rows` rows
+      if (rs.table == nullptr || rs.slots == 0) return;
+      float* t_ = rs.table;
+      const size_t half = static_cast<size_t>(rows) * rs.ld * 2;
+      push([=](cudaStream_t st) {
+        cudaError_t e = cudaMemcpyAsync(t_ + half, t_, half * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) {
+          set_error(std::string("cudaMemcpyAsync(dup row stats): ") + cudaGetErrorString(e));
+          return 1;
+        }
+        return 0;
+      });
+    };
     {
       // norm (GroupNorm eps 1e-6, no activation) -> proj_in (attention.py:399-404): the affine map is applied to the
       // activation tiles of the proj_in GEMM in shared memory when the producer of x left statistics
@@ -857,13 +901,19 @@ struct lr_engine {
         cs.xf_shift = sh;
         cs.xf_silu = 0;
         cs.xf_rows_per_img = P;
-        LR_TRY(add_conv_step(cs));
+        if (rs.table != nullptr) {
+          cs.rowstats_out = rs.table;
+          cs.rowstats_ld = rs.ld;
+        }
+        ConvOp* op;
+        LR_TRY(add_conv_step(cs, &op));
+        rs.slots = op->rowstats_slots;
         release(sc);
         release(sh);
       } else {
         LR_TRY(acquire_h(static_cast<size_t>(Mfull) * C, &xn));
         LR_TRY(add_gn_auto(x, Act{}, n, 1e-6f, F(s.gn_g), F(s.gn_b), 0, xn));
-        LR_TRY(add_linear(xn, M, C, H(s.pin_w), C, F(s.pin_b), nullptr, 0, h, C, 0));
+        LR_TRY(add_linear(xn, M, C, H(s.pin_w), C, F(s.pin_b), nullptr, 0, h, C, 0, nullptr, nullptr, nullptr, &rs));
         release(xn);
       }
     }
@@ -875,6 +925,7 @@ struct lr_engine {
     for (const TBlockW& b : s.blocks) {
       if (!first_block && n != n_full) {  // depth > 1: only block 0's self-attention is shared
         add_dup_half(h, static_cast<size_t>(M) * C);
+        dup_rowstats(M);
         add_dup_half(x.p, static_cast<size_t>(M) * C);
         n = n_full;
         M = Mfull;
@@ -882,8 +933,9 @@ struct lr_engine {
       // self-attention: x = attn1(norm1(x)) + x
       LR_TRY(acquire_h(static_cast<size_t>(M) * 3 * C, &qkv));
       if (ln_fold) {  // LayerNorm folded into the QKV projection: stats pass + epilogue correction
-        LR_TRY(add_ln_stats(h, M, C, lnst));
-        LR_TRY(add_linear(h, M, C, H(b.qkv_wf), 3 * C, F(b.qkv_bf), nullptr, 0, qkv, 3 * C, 0, lnst, F(b.qkv_s)));
+        if (rs.slots == 0) LR_TRY(add_ln_stats(h, M, C, lnst));
+        LR_TRY(add_linear(h, M, C, H(b.qkv_wf), 3 * C, F(b.qkv_bf), nullptr, 0, qkv, 3 * C, 0, lnst, F(b.qkv_s),
+                          rs.slots > 0 ? &rs : nullptr));
       } else {
         LR_TRY(add_ln(h, M, C, F(b.ln1_g), F(b.ln1_b), t));
         LR_TRY(add_linear(t, M, C, H(b.qkv_w), 3 * C, nullptr, nullptr, 0, qkv, 3 * C, 0));
@@ -922,6 +974,7 @@ struct lr_engine {
         {
           __half* hdst = h;
           push([=](cudaStream_t st) { return launch_mv_scatter(o_r, C, bs, v, hh, side, hdst, st); });
+          rs.slots = 0;  // h was rewritten by a copy kernel: the next LayerNorm needs its own statistics pass
         }
         release(qkv_r);
         release(a_r);
@@ -942,10 +995,11 @@ struct lr_engine {
         as.scale = 0.125f;
         LR_TRY(add_attn(as));
         release(qkv);
-        LR_TRY(add_linear(a, M, C, H(b.out1_w), C, F(b.out1_b), h, C, h, C, 0));
+        LR_TRY(add_linear(a, M, C, H(b.out1_w), C, F(b.out1_b), h, C, h, C, 0, nullptr, nullptr, nullptr, &rs));
       }
       if (first_block && n != n_full) {  // end of the shared prefix: replicate the residual stream and the ST input
         add_dup_half(h, static_cast<size_t>(M) * C);
+        dup_rowstats(M);
         add_dup_half(x.p, static_cast<size_t>(M) * C);
         n = n_full;
         M = Mfull;
@@ -955,8 +1009,9 @@ struct lr_engine {
       __half* q2;
       LR_TRY(acquire_h(static_cast<size_t>(M) * C, &q2));
       if (ln_fold) {
-        LR_TRY(add_ln_stats(h, M, C, lnst));
-        LR_TRY(add_linear(h, M, C, H(b.q2_wf), C, F(b.q2_bf), nullptr, 0, q2, C, 0, lnst, F(b.q2_s)));
+        if (rs.slots == 0) LR_TRY(add_ln_stats(h, M, C, lnst));
+        LR_TRY(add_linear(h, M, C, H(b.q2_wf), C, F(b.q2_bf), nullptr, 0, q2, C, 0, lnst, F(b.q2_s),
+                          rs.slots > 0 ? &rs : nullptr));
       } else {
         LR_TRY(add_ln(h, M, C, F(b.ln2_g), F(b.ln2_b), t));
         LR_TRY(add_linear(t, M, C, H(b.q2_w), C, nullptr, nullptr, 0, q2, C, 0));
@@ -972,22 +1027,24 @@ struct lr_engine {
         LR_TRY(add_attn(as));
       }
       release(q2);
-      LR_TRY(add_linear(a, M, C, H(b.out2_w), C, F(b.out2_b), h, C, h, C, 0));
+      LR_TRY(add_linear(a, M, C, H(b.out2_w), C, F(b.out2_b), h, C, h, C, 0, nullptr, nullptr, nullptr, &rs));
       // GEGLU feed-forward
       LR_TRY(acquire_h(static_cast<size_t>(M) * 4 * C, &g));
       if (ln_fold) {
-        LR_TRY(add_ln_stats(h, M, C, lnst));
-        LR_TRY(add_linear(h, M, C, H(b.ff1_wf), 8 * C, F(b.ff1_bf), nullptr, 0, g, 4 * C, 1, lnst, F(b.ff1_s)));
+        if (rs.slots == 0) LR_TRY(add_ln_stats(h, M, C, lnst));
+        LR_TRY(add_linear(h, M, C, H(b.ff1_wf), 8 * C, F(b.ff1_bf), nullptr, 0, g, 4 * C, 1, lnst, F(b.ff1_s),
+                          rs.slots > 0 ? &rs : nullptr));
       } else {
         LR_TRY(add_ln(h, M, C, F(b.ln3_g), F(b.ln3_b), t));
         LR_TRY(add_linear(t, M, C, H(b.ff1_w), 8 * C, F(b.ff1_b), nullptr, 0, g, 4 * C, 1));
       }
-      LR_TRY(add_linear(g, M, 4 * C, H(b.ff2_w), C, F(b.ff2_b), h, C, h, C, 0));
+      LR_TRY(add_linear(g, M, 4 * C, H(b.ff2_w), C, F(b.ff2_b), h, C, h, C, 0, nullptr, nullptr, nullptr, &rs));
       release(g);
     }
     release(t);
     release(a);
     release(lnst);
+    if (rs.table) release(rs.table);
     LR_TRY(acquire_h(static_cast<size_t>(M) * C, &o));
     Act oact{o, C, x.H, x.W};
     {

@@ -89,6 +89,16 @@ struct GemmParams {
   // so the normalised activation tensor is never written or re-read; a stats-only pass produces (mean, rstd) per row.
   const float2* ln_stats;  // [M] (mean, rstd) or nullptr
   const float* ln_s;       // [ncols]
+  // ... or the statistics come as per-row PARTIALS left by the epilogue of the GEMM that wrote the rows (rowstats_out
+  // there): ln_part [M][ln_ld] float2 (sum, sum of squares), the first ln_slots entries of a row are summed in order,
+  // mean = S / ln_c, rstd = rsqrt(Q / ln_c - mean^2 + ln_eps). No separate statistics pass over the activation.
+  const float2* ln_part;
+  int ln_slots, ln_ld, ln_c;
+  float ln_eps;
+  // producer side: every epilogue thread owns one output row and adds up (x, x^2) over the columns it converts
+  // (fp32 values before the fp16 rounding); slot = 2 * (N-tile index) + (warp half) of row `grow`
+  float2* rowstats_out;    // [M][rowstats_ld] or nullptr
+  int rowstats_ld;
   int ksplit;        // split-K over the filter taps (1 = off, 3 = taps {0-2}, {3-5}, {6-8} as separate work units): for
                      // convs whose M is too small to fill the GPU. Units then write raw fp32 partial tiles to `partial`
                      // ([ksplit][M][ncols]) and splitk_reduce_kernel applies bias / residual and converts to fp16.
@@ -687,7 +697,7 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
     // The XF instantiation (GroupNorm-consuming convs / proj_in) never runs GEGLU, a folded LayerNorm or split-K: pruning
     // those paths at compile time keeps it inside the 128 registers that 448 threads leave per thread.
     const bool k_geglu = !XF && p.geglu != 0;
-    const bool k_ln = !XF && p.ln_stats != nullptr;
+    const bool k_ln = !XF && (p.ln_stats != nullptr || p.ln_part != nullptr);
     const bool k_partial = !XF && p.partial != nullptr;
     const int ew = warp - 2;
     const int q = hw_warp & 3;  // TMEM lane quarter this warp may access (hardware: warp id % 4)
@@ -782,7 +792,21 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
       // folded LayerNorm: this thread's row statistics (they do not depend on the MMA either)
       float ln_rstd = 1.f, ln_nrm = 0.f;
       if (k_ln && row_ok) {
-        const float2 st = __ldg(p.ln_stats + grow);
+        float2 st;
+        if (p.ln_part != nullptr) {
+          float su = 0.f, sq = 0.f;
+          const float2* pr = p.ln_part + grow * p.ln_ld;
+          for (int i = 0; i < p.ln_slots; ++i) {  // fixed order: bit-reproducible
+            const float2 t = __ldg(pr + i);
+            su += t.x;
+            sq += t.y;
+          }
+          const float inv_c = 1.0f / static_cast<float>(p.ln_c);
+          const float mean = su * inv_c;
+          st = make_float2(mean, rsqrtf(fmaxf(fmaf(-mean, mean, sq * inv_c), 0.f) + p.ln_eps));
+        } else {
+          st = __ldg(p.ln_stats + grow);
+        }
         ln_rstd = st.y;
         ln_nrm = -st.x * st.y;
       }
@@ -804,6 +828,7 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
       if (p.res_tma) mbar_wait(&rfull[tcount & 1], (tcount >> 1) & 1);  // residual tile is in the staging buffer
       if (ew == 0) LR_GEMM_TR(2, tcount, 2);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
+      float rs_s = 0.f, rs_q = 0.f;  // rowstats_out: this thread's row, the columns this warp half converts
       for (; c < p.block_n; c += 64) {
         uint32_t v[32];
         if (p.dbg & 32) {
@@ -924,6 +949,15 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
                   }
                 }
               }
+              if (p.rowstats_out != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (col0 + j < p.n_valid) {
+                    rs_s += f[j];
+                    rs_q = fmaf(f[j], f[j], rs_q);
+                  }
+                }
+              }
               const int slab = c >> 6, cp0 = (c & 63) >> 3;
               uint8_t* rowp = (slab < full_slabs) ? cstage + slab * (kBlockM * 128) + r * 128
                                                   : cstage + full_slabs * (kBlockM * 128) + r * 64;
@@ -944,6 +978,8 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
                 if (col0 + j < p.n_valid) {
                   float t = f[j];
                   if (res_row != nullptr) t += __half2float(res_row[col0 + j]);
+                  rs_s += t;
+                  rs_q = fmaf(t, t, rs_q);
                   o[j] = __float2half_rn(t * p.out_scale);
                 }
               }
@@ -957,6 +993,8 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
       if (lane == 0) {
         if (CG == 2) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]);
       }
+      if (p.rowstats_out != nullptr && row_ok)
+        p.rowstats_out[grow * p.rowstats_ld + tn * 2 + half] = make_float2(rs_s, rs_q);
 #if LR_STORE_WARP
       if (p.tma_store) {
         // the fp16 tile is complete in smem: hand it to the store warp (generic-proxy writes -> async proxy first)

@@ -365,10 +365,26 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
   p.cstage_off = (ring_bytes + kGemmAuxBytes + 1023) & ~1023;  // swizzle needs 1024 B
   p.cstage_bufs = bufs;
   p.cstage_bytes = cstage_bytes;
-  LR_CHECK(s.ln_stats == nullptr || (s.ln_s != nullptr && s.bias != nullptr && s.taps == 1 && ksplit == 1),
+  LR_CHECK((s.ln_stats == nullptr && s.ln_part == nullptr) ||
+               (s.ln_s != nullptr && s.bias != nullptr && s.taps == 1 && ksplit == 1),
            "conv: folded LayerNorm needs ln_s, a (folded) bias and a Linear geometry");
+  LR_CHECK(s.ln_part == nullptr || (s.ln_slots > 0 && s.ln_ld >= s.ln_slots && s.ln_stats == nullptr && s.c1 == 0),
+           "conv: folded LayerNorm from row partials needs ln_slots <= ln_ld and a single source");
   p.ln_stats = reinterpret_cast<const float2*>(s.ln_stats);
   p.ln_s = s.ln_s;
+  p.ln_part = reinterpret_cast<const float2*>(s.ln_part);
+  p.ln_slots = s.ln_slots;
+  p.ln_ld = s.ln_ld;
+  p.ln_c = s.c0;
+  p.ln_eps = s.ln_eps;
+  p.rowstats_out = nullptr;
+  p.rowstats_ld = s.rowstats_ld;
+  op->rowstats_slots = 0;
+  if (s.rowstats_out != nullptr && ksplit == 1 && !s.geglu && s.taps == 1 && s.out_sx == 0 &&
+      s.rowstats_ld >= 2 * cdiv(s.ncols, block_n)) {
+    p.rowstats_out = reinterpret_cast<float2*>(s.rowstats_out);
+    op->rowstats_slots = 2 * cdiv(s.ncols, block_n);
+  }
   p.ksplit = ksplit;
   p.partial = ksplit > 1 ? s.workspace : nullptr;
   p.bias = ksplit > 1 ? nullptr : s.bias;  // split-K: bias / per-image bias / residual are applied by the reduction

@@ -60,6 +60,15 @@ struct ConvSpec {
   float out_scale = 1.0f;  // multiplies the final value (softmax scale of the VAE AttnBlock logits)
   const float* ln_stats = nullptr;  // folded LayerNorm: [M] float2 (mean, rstd) of the input rows, or nullptr
   const float* ln_s = nullptr;      //                   [ncols] column sums of the gamma-folded weight
+  // ... or per-row partials left by the producing GEMM's epilogue (rowstats_out of that op): [M][ln_ld] float2, the first
+  // ln_slots entries of a row are summed; mean / rstd over c0 channels with ln_eps
+  const float* ln_part = nullptr;
+  int ln_slots = 0, ln_ld = 0;
+  float ln_eps = 1e-5f;
+  // producer side: (sum, sum of squares) per output row and (N-tile, warp half) -> rowstats_out [M][rowstats_ld] float2;
+  // ConvOp::rowstats_slots entries per row are written (rowstats_ld >= 2 * ceil(ncols / 32) is always enough)
+  float* rowstats_out = nullptr;
+  int rowstats_ld = 0;
   // GroupNorm fusion (gemm_tc.cuh header): the input is x * xf_scale[n, c] + xf_shift[n, c] (+ SiLU), applied in shared
   // memory by the transform warps. Needs a halo-mode 3x3 conv (stride 1, image >= 16 rows x 8 columns) or taps == 1.
   const float* xf_scale = nullptr;  // [n_img (or M / xf_rows_per_img), c0 + c1]
@@ -93,6 +102,7 @@ struct ConvOp {
   int xf = 0;         // launches the transform-warp instantiation
   int stats_ok = 0;   // stats_out is written by this op
   int stats_ppi = 0;  // statistics rows per image (2 per 128-row tile)
+  int rowstats_slots = 0;  // entries per row written to rowstats_out (0: none)
 };
 // 3x3 convs with at most this many OUTPUT pixels per image run split-K over the taps when scratch is provided
 constexpr int kSplitKMaxPixels = 256;

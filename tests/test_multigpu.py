@@ -47,7 +47,7 @@ def _run(rank, world, port, cfg_name, q):
                            eta=1.0, unconditional_guidance_scale=2.5)
     t_max = P.max_over_ranks(float(rank + 1), dev)
     if rank == 0:
-        q.put((out.cpu(), t_max))
+        q.put((out.cpu().numpy(), t_max))  # by value: the child may exit before the parent reads the queue
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -60,11 +60,11 @@ def _launch(world, cfg_name):
     procs = [ctx.Process(target=_run, args=(r, world, port, cfg_name, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = q.get(timeout=600)
+    arr, t_max = q.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    return res
+    return torch.from_numpy(arr), t_max
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs (NCCL)")

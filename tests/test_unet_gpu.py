@@ -539,3 +539,41 @@ def test_unet_deepcopy_and_invalidate(small):
         y1 = m2(x, t, context=ctx)
     b = m2.out[2].bias.detach()[None, :, None, None]
     assert torch.allclose(y1 - b, 2 * (y0 - b), rtol=5e-3, atol=8e-3)
+
+
+SWITCHES = [{"LR_LN_ROWSTATS": "1"}, {"LR_NO_UPFOLD": "1"}, {"LR_NO_GN_FUSE": "1"}, {"LR_GN_FUSE_CONV": "1"},
+            {"LR_GN_COEF_APPLY": "1"}, {"LR_GN_FUSE_CONV": "1", "LR_GN_COEF_APPLY": "1", "LR_GN_FUSE_LINEAR_MIN_ROWS": "1"},
+            {"LR_NO_LN_FOLD": "1"}]
+
+
+@pytest.mark.parametrize("env", SWITCHES, ids=lambda e: "+".join(f"{k}={v}" for k, v in e.items()))
+def test_engine_variants_keep_parity(env, monkeypatch):
+    """Every optional execution scheme of the engine (fused / coefficient-apply / stand-alone
+    GroupNorm, LayerNorm statistics from the producer epilogue or from a pass, folded or materialised Upsample) must
+    meet the same parity bar: full model, one CFG pair at 64x128 (all levels, halo tiles, folded up-convs) vs the fp32
+    oracle on the GPU. The switches are read when the engine is created."""
+    import leftrefill_b200 as lr
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cfg = O.DEFAULT_CFG
+    sd = O.make_state_dict(cfg, seed=0)
+    m = lr.UNetModel(**cfg)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(404)
+    x = torch.randn(2, 9, 64, 128, generator=g).cuda()
+    ctx = torch.randn(2, 77, 1024, generator=g).cuda()
+    t = torch.tensor([981, 401]).cuda()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        y = m(x, t, context=ctx)
+        y2 = m(x, t, context=ctx)
+        assert torch.equal(y, y2)                    # bit-reproducible in every variant
+        sdc = {k: v.cuda() for k, v in sd.items()}
+        ref = O.unet_forward(sdc, cfg, x, t, ctx)
+        with torch.autocast("cuda"):
+            floor = O.unet_forward(sdc, cfg, x, t, ctx).float()
+    _assert_parity(y, ref, floor)
+    del m, sdc, ref, floor
+    torch.cuda.empty_cache()
