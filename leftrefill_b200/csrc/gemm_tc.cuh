@@ -124,6 +124,10 @@ struct GemmParams {
   int geglu;               // accumulator columns are (value, gate) pairs -> out[:, j] = v * gelu(g) (attention.py:51-58)
   int n_valid;             // valid output columns (after GEGLU halving)
   float out_scale;         // multiplies the final value (1.0 normally)
+  int epi_lean;            // 1: the epilogue takes its LEAN path (host-checked: TMA-store staging, no split-K / folded
+                           // LayerNorm / per-image bias / row statistics / out_scale, residual absent or TMA-loaded,
+                           // ncols % 32 == 0): bias straight from global (L1 broadcast), 32-bit shared addresses, no
+                           // per-row bookkeeping, columns split evenly between the two warps of a TMEM lane quarter
   // ---- GroupNorm fusion (see the header comment) ----
   const float* xf_scale;   // XF kernels: a[n_img][xf_ld] (rstd * gamma) of the (concatenated) input channels
   const float* xf_shift;   //             b[n_img][xf_ld] (beta - mean * rstd * gamma)
@@ -150,20 +154,17 @@ struct GemmParams {
 #ifndef LR_HI_WARP_ISSUE
 #define LR_HI_WARP_ISSUE 0
 #endif
-// -DLR_STORE_WARP=1: a dedicated STORE warp (warp 10) issues the TMA stores of finished output tiles; the epilogue warps
-// hand a staged tile over with one mbarrier arrive each instead of meeting at a named barrier while one of them issues
-// the bulk tensor stores (~900 cycles per tile in the in-kernel trace). Measured on B200 (round 1, r1p): -5 % on the
-// 320->320 and GEGLU linears, +12 % on the QKV projection, no difference for the whole forward (19.8 ms either way),
-// so the simpler 10-warp layout stays the default.
-#ifndef LR_STORE_WARP
-#define LR_STORE_WARP 0
-#endif
-constexpr int kGemmThreads = LR_STORE_WARP ? 352 : 320;
+// (Round 1 also tried a dedicated STORE warp issuing the TMA stores, profiles/r1_ab_store_warp.txt: no gain for the whole
+// forward. Round 2 spreads the issue over the epilogue warps instead: see kStoreIssuers.)
+constexpr int kGemmThreads = 320;
 constexpr int kXfWarps = 4;                                 // transform warps of the XF instantiation (warps 10..13)
 constexpr int kGemmThreadsXf = 320 + kXfWarps * 32;
-static_assert(!LR_STORE_WARP, "the store-warp experiment shares warp 10 with the transform warps");
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
+// Issuing one bulk tensor copy costs the issuing thread 300-450 cycles (in-kernel trace, profiles/r2_trace_linears.txt),
+// and an output tile is up to four slabs: lane 0 of epilogue warp i issues (and later confirms) the store of slab i,
+// and the residual tile of a later unit is fetched by the TMA producer warp, not by an epilogue thread.
+constexpr int kStoreIssuers = 4;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
@@ -249,8 +250,7 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
   uint64_t* a_full = tempty + 2;           // [kMaxStages]  activation tile landed (halo mode; XF: also the plain mode)
   uint64_t* a_empty = a_full + kMaxStages;   // [kMaxStages]
   uint64_t* xready = a_empty + kMaxStages;   // [kMaxStages]  XF: the transform warps (of both CTAs) are done with the tile
-  uint64_t* cfull = xready + kMaxStages;     // [2] staged output tile complete (all epilogue threads arrived)
-  uint64_t* cfree = cfull + 2;               // [2] its TMA stores have finished reading the staging buffer
+  uint64_t* cfree = xready + kMaxStages + 2;  // [2] the TMA stores of staging buffer b have finished reading it
   uint64_t* rfull = cfree + 2;               // [2] residual tile has landed in staging buffer b (res_tma)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);  // [2][256]
@@ -287,8 +287,7 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
       mbar_init(&xready[i], kXfWarps * CG);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&cfull[i], kEpiThreads);
-      mbar_init(&cfree[i], 1);
+      mbar_init(&cfree[i], kEpiWarps);
       mbar_init(&rfull[i], 1);
     }
     fence_barrier_init();
@@ -316,6 +315,33 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
   const int num_units = num_tiles * p.ksplit;  // unit u = (tile u / ksplit, tap range u % ksplit)
   const int unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
   const int b_rows = p.block_n / CG;
+
+  // res_tma: the TMA producer warp fetches the residual tile of its unit number `tcount` into staging buffer
+  // (tcount & 1) right after the operands of that unit, i.e. about one tile period before the epilogue needs it. The
+  // buffer was last read by the TMA stores (and the statistics pass) of unit tcount - 2; the epilogue warps confirm the
+  // end of those reads at the start of unit tcount - 1 and arrive on cfree[].
+  auto fetch_residual = [&](int tcount, int tn, int tx, int ty, int tb) {  // whole warp
+    if (tcount >= 2) mbar_wait(&cfree[tcount & 1], ((tcount >> 1) - 1) & 1);
+    if (elect_one()) {
+      const int buf = tcount & 1;
+      const int ocols_tile = p.block_n, full_slabs = p.block_n >> 6;  // (never combined with GEGLU)
+      const int oc0 = tn * p.block_n;
+      uint8_t* dst = smem + p.cstage_off + buf * p.cstage_bytes;
+      int bytes = 0;
+      for (int sl = 0; sl < full_slabs; ++sl)
+        if (oc0 + sl * 64 < p.n_valid) bytes += kBlockM * 128;
+      const bool rem = (ocols_tile & 63) != 0 && oc0 + full_slabs * 64 < p.n_valid;
+      if (rem) bytes += kBlockM * 64;
+      mbar_arrive_expect_tx(&rfull[buf], bytes);
+      for (int sl = 0; sl < full_slabs; ++sl)
+        if (oc0 + sl * 64 < p.n_valid)
+          tma_load_4d(dst + sl * (kBlockM * 128), &p.tmR, &rfull[buf], oc0 + sl * 64, tx * p.bw, ty * p.bh, tb * p.bn);
+      if (rem)
+        tma_load_4d(dst + full_slabs * (kBlockM * 128), &p.tmR2, &rfull[buf], oc0 + full_slabs * 64, tx * p.bw, ty * p.bh,
+                    tb * p.bn);
+    }
+    __syncwarp();
+  };
 
   if (warp == 0 && p.halo) {
     // ------------------------------- TMA producer, halo mode ------------------------------------------------
@@ -374,6 +400,7 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
           if (++sb == p.stages) { sb = 0; phb ^= 1; }
         }
       }
+      if (p.res_tma) fetch_residual(tcount, tn, tx, ty, tb);
       LR_GEMM_TR(0, tcount, 1);
     }
     };
@@ -433,6 +460,7 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
+      if (p.res_tma) fetch_residual(tcount, tn, tx, ty, tb);
       LR_GEMM_TR(0, tcount, 1);
     }
   } else if (warp == 1 && p.halo) {
@@ -721,64 +749,212 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
       const int col = (tile % p.tiles_n) * p.block_n + etid;
       return col < p.ncols ? __ldg(p.ln_s + col) : 0.f;
     };
-    float bias_next = fetch_bias(unit0 / p.ksplit);
-    float lns_next = fetch_lns(unit0 / p.ksplit);
+    const bool lean = p.epi_lean != 0;
+    float bias_next = lean ? 0.f : fetch_bias(unit0 / p.ksplit);
+    float lns_next = lean ? 0.f : fetch_lns(unit0 / p.ksplit);
+    // pixel of this thread's row inside a tile (the same for every tile)
+    const int xi = r % p.bw;
+    const int yi = (r / p.bw) % p.bh;
+    const int ni = r / (p.bw * p.bh);
+    // lean path: accumulator columns [lean_c0, lean_c1) of every tile belong to this warp (granularity: 16 columns, or
+    // 32 = 16 outputs with GEGLU), so that block_n = 160 / 224 / 96 split 80 / 112 / 48 per warp instead of 96 + 64 ...
+    const int lean_gran = k_geglu ? 32 : 16;
+    const int lean_mid = (((p.block_n / lean_gran) + 1) >> 1) * lean_gran;
+    const int lean_c0 = half ? lean_mid : 0, lean_c1 = half ? p.block_n : lean_mid;
+    const uint32_t cstage_u32 = smem_u32(smem + p.cstage_off);
+    const uint32_t r7x = static_cast<uint32_t>(r & 7) << 4;
     const size_t m_total = static_cast<size_t>(p.n_img) * p.H * p.W;
-    // res_tma: (one thread) loads the residual tile of unit `un` into staging buffer `buf`
-    auto issue_res = [&](int un, int buf) {
-      const int tile2 = un / p.ksplit;
-      int tm2 = min((tile2 / p.tiles_n) * CG + static_cast<int>(rank), tiles_m - 1);
-      const int tx2 = tm2 % p.tiles_x;
-      tm2 /= p.tiles_x;
-      const int ty2 = tm2 % p.tiles_y;
-      const int tb2 = tm2 / p.tiles_y;
-      const int oc0 = (tile2 % p.tiles_n) * p.block_n;
-      uint8_t* dst = smem + p.cstage_off + buf * p.cstage_bytes;
-      int bytes = 0;
-      for (int sl = 0; sl < full_slabs; ++sl)
-        if (oc0 + sl * 64 < p.n_valid) bytes += kBlockM * 128;
-      const bool rem = (ocols_tile & 63) != 0 && oc0 + full_slabs * 64 < p.n_valid;
-      if (rem) bytes += kBlockM * 64;
-      mbar_arrive_expect_tx(&rfull[buf], bytes);
-      for (int sl = 0; sl < full_slabs; ++sl)
-        if (oc0 + sl * 64 < p.n_valid)
-          tma_load_4d(dst + sl * (kBlockM * 128), &p.tmR, &rfull[buf], oc0 + sl * 64, tx2 * p.bw, ty2 * p.bh, tb2 * p.bn);
-      if (rem)
-        tma_load_4d(dst + full_slabs * (kBlockM * 128), &p.tmR2, &rfull[buf], oc0 + full_slabs * 64, tx2 * p.bw,
-                    ty2 * p.bh, tb2 * p.bn);
+    // lane 0 of the first kStoreIssuers epilogue warps: issues the TMA store of slab `ew` of every tile (see kStoreIssuers)
+    const bool issuer = lane == 0 && ew < kStoreIssuers;
+    // the stores this thread issued have finished reading their staging buffer; with two buffers that frees the buffer
+    // of the previous unit for the producer's next residual fetch
+    // Every epilogue warp arrives (after ITS reads of the previous unit's staging buffer: residual, statistics pass), so
+    // a completed cfree phase means nobody in this CTA touches that buffer any more.
+    auto confirm_stores = [&](int tcount) {
+      __syncwarp();
+      if (lane == 0 && tcount > 0) {
+        if (stores_pending) tma_store_wait_read();
+        stores_pending = false;
+        mbar_arrive(&cfree[(tcount - 1) & 1]);
+      }
     };
-    if (p.res_tma && etid == 0 && unit0 < num_units) issue_res(unit0, 0);
+    // unit -> (N-tile, M-tile pair) without a division per unit (ksplit == 1; split-K units divide below)
+    int tn_i = unit0 % p.tiles_n, tmq_i = unit0 / p.tiles_n;
+    const int step_q = unit_step / p.tiles_n, step_r = unit_step % p.tiles_n;
+    const bool lin_geom = p.tiles_y == 1 && p.tiles_b == 1;
     int tcount = 0;
     for (int u = unit0; u < num_units; u += unit_step, ++tcount) {
       if (ew == 0) LR_GEMM_TR(2, tcount, 0);
-      const int tile = u / p.ksplit, sp = u % p.ksplit;
+      int sp = 0, tn, tmq;
+      if (p.ksplit == 1) {
+        tn = tn_i;
+        tmq = tmq_i;
+        tn_i += step_r;
+        tmq_i += step_q;
+        if (tn_i >= p.tiles_n) {
+          tn_i -= p.tiles_n;
+          ++tmq_i;
+        }
+      } else {
+        const int tile = u / p.ksplit;
+        sp = u % p.ksplit;
+        tn = tile % p.tiles_n;
+        tmq = tile / p.tiles_n;
+      }
       uint8_t* cstage = smem + p.cstage_off + ((p.cstage_bufs == 2) ? (tcount & 1) * p.cstage_bytes : 0);
-      const int tn = tile % p.tiles_n;
-      int tm = (tile / p.tiles_n) * CG + static_cast<int>(rank);
+      int tm = tmq * CG + static_cast<int>(rank);
       const bool tile_ok = tm < tiles_m;
       tm = min(tm, tiles_m - 1);
       const int tm_idx = tm;  // linear M-tile index: the row pair of this tile in the statistics table
-      const int tx = tm % p.tiles_x;
-      tm /= p.tiles_x;
-      const int ty = tm % p.tiles_y;
-      const int tb = tm / p.tiles_y;
-      const int xi = r % p.bw;
-      const int yi = (r / p.bw) % p.bh;
-      const int ni = r / (p.bw * p.bh);
-      const int x = tx * p.bw + xi, y = ty * p.bh + yi, n = tb * p.bn + ni;
-      const bool row_ok = tile_ok && (x < p.W) && (y < p.H) && (n < p.n_img);
-      const size_t grow = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+      int tx = tm, ty = 0, tb = 0;
+      if (!lin_geom) {
+        tx = tm % p.tiles_x;
+        tm /= p.tiles_x;
+        ty = tm % p.tiles_y;
+        tb = tm / p.tiles_y;
+      }
       const int ncol0 = tn * p.block_n;
+      float rs_s = 0.f, rs_q = 0.f;  // rowstats_out: this thread's row, the columns this warp half converts
+      bool row_ok = false;
+      size_t grow = 0;
 
-#if LR_STORE_WARP
-      // the TMA stores of the tile that last used this staging buffer must have drained it (free when it was issued a
-      // whole tile ago, i.e. with two buffers)
-      const int cbuf = (p.cstage_bufs == 2) ? (tcount & 1) : 0;
-      if (p.tma_store) mbar_wait(&cfree[cbuf], (((tcount / p.cstage_bufs) & 1) ^ 1));
-#else
+      if (lean) {
+        // ---------------- lean path (see GemmParams::epi_lean) ----------------
+        if (p.cstage_bufs == 1) {  // single staging buffer: the previous tile's TMA stores must have drained it
+          confirm_stores(tcount);
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        }
+        const uint32_t cst = cstage_u32 + ((p.cstage_bufs == 2) ? (tcount & 1) * p.cstage_bytes : 0);
+        // Shared address of 16-byte chunk k of the output columns [oc, oc + 8 * nchunks) of this thread's staged row:
+        // row_base(oc) ^ (k << 4). Full slabs are [128 rows][128 B] with the 128-byte swizzle (chunk index ^ (row & 7)),
+        // the 32-column remainder slab is [128 rows][64 B] unswizzled; a group of 2 (4) chunks starts at an even
+        // (multiple-of-4) chunk index, so adding k never carries and the whole address is one three-input XOR.
+        auto row_base = [&](int oc) -> uint32_t {
+          const int slab = oc >> 6;
+          const uint32_t cpx = static_cast<uint32_t>((oc >> 3) & 7) << 4;
+          return (slab < full_slabs) ? (cst + slab * (kBlockM * 128) + r * 128) ^ (cpx ^ r7x)
+                                     : (cst + full_slabs * (kBlockM * 128) + r * 64) ^ cpx;
+        };
+        if (ew == 0) LR_GEMM_TR(2, tcount, 1);
+        mbar_wait(&tfull[as], aph);
+        tc_fence_after();
+        if (p.cstage_bufs == 2) confirm_stores(tcount);
+        if (p.res_tma) mbar_wait(&rfull[tcount & 1], (tcount >> 1) & 1);  // residual tile is in the staging buffer
+        if (ew == 0) LR_GEMM_TR(2, tcount, 2);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
+        // folded LayerNorm (linear geometry: row index = 128 * M-tile + r): out = rstd * acc + (-mean * rstd) * ln_s + bias
+        float ln_rstd = 1.f, ln_nrm = 0.f;
+        if (k_ln && tile_ok && tm_idx * kBlockM + r < p.W) {
+          const float2 st = __ldg(p.ln_stats + tm_idx * kBlockM + r);
+          ln_rstd = st.y;
+          ln_nrm = -st.x * st.y;
+        }
+        auto run = [&](auto bias_tag, auto res_tag, auto ln_tag) {
+          constexpr bool kBias = decltype(bias_tag)::value != 0;
+          constexpr bool kRes = decltype(res_tag)::value != 0;
+          constexpr bool kLn = decltype(ln_tag)::value != 0;  // (implies kBias)
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + ncol0);
+          const float4* lns4 = reinterpret_cast<const float4*>(p.ln_s + ncol0);
+          // accumulator value -> pre-activation: + bias, or the folded LayerNorm's per-row affine map
+          auto pre = [&](uint32_t acc, float b, float sj) -> float {
+            return kLn ? fmaf(ln_rstd, __uint_as_float(acc), fmaf(ln_nrm, sj, b)) : __uint_as_float(acc) + b;
+          };
+          if (k_geglu) {
+            if constexpr (!kRes) {
+              for (int c = lean_c0; c < lean_c1; c += 32) {
+                if (ncol0 + c >= p.ncols) break;
+                uint32_t v[32];
+                tmem_ld32(t_row + c, v);
+                float4 b4[8], s4[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  b4[j] = kBias ? __ldg(bias4 + (c >> 2) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  s4[j] = kLn ? __ldg(lns4 + (c >> 2) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                const uint32_t a0 = row_base(c >> 1);
+                tmem_ld_wait();
+                float g[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  g[2 * j] = pre(v[4 * j], b4[j].x, s4[j].x) * gelu_erf(pre(v[4 * j + 1], b4[j].y, s4[j].y));
+                  g[2 * j + 1] = pre(v[4 * j + 2], b4[j].z, s4[j].z) * gelu_erf(pre(v[4 * j + 3], b4[j].w, s4[j].w));
+                }
+                sts128(a0, make_uint4(pack_half2(g[0], g[1]), pack_half2(g[2], g[3]), pack_half2(g[4], g[5]),
+                                      pack_half2(g[6], g[7])));
+                sts128(a0 ^ 16u, make_uint4(pack_half2(g[8], g[9]), pack_half2(g[10], g[11]), pack_half2(g[12], g[13]),
+                                            pack_half2(g[14], g[15])));
+              }
+            }
+            return;
+          }
+          // kN accumulator columns (16 or 32) -> kN / 8 chunks of the staged row, the residual added in place
+          auto chunk = [&](auto n_tag, int c) {
+            constexpr int kN = decltype(n_tag)::value;
+            uint32_t v[kN];
+            if constexpr (kN == 32) tmem_ld32(t_row + c, v); else tmem_ld16(t_row + c, v);
+            float4 b4[kN / 4], s4[kN / 4];
+#pragma unroll
+            for (int j = 0; j < kN / 4; ++j) {
+              b4[j] = kBias ? __ldg(bias4 + (c >> 2) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              s4[j] = kLn ? __ldg(lns4 + (c >> 2) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const uint32_t a0 = row_base(c);
+            uint4 rr[kN / 8];
+            if constexpr (kRes) {
+#pragma unroll
+              for (int k = 0; k < kN / 8; ++k) rr[k] = lds128(a0 ^ (k << 4));
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < kN / 8; ++k) {
+              float f[8];
+              f[0] = pre(v[8 * k + 0], b4[2 * k].x, s4[2 * k].x);
+              f[1] = pre(v[8 * k + 1], b4[2 * k].y, s4[2 * k].y);
+              f[2] = pre(v[8 * k + 2], b4[2 * k].z, s4[2 * k].z);
+              f[3] = pre(v[8 * k + 3], b4[2 * k].w, s4[2 * k].w);
+              f[4] = pre(v[8 * k + 4], b4[2 * k + 1].x, s4[2 * k + 1].x);
+              f[5] = pre(v[8 * k + 5], b4[2 * k + 1].y, s4[2 * k + 1].y);
+              f[6] = pre(v[8 * k + 6], b4[2 * k + 1].z, s4[2 * k + 1].z);
+              f[7] = pre(v[8 * k + 7], b4[2 * k + 1].w, s4[2 * k + 1].w);
+              if constexpr (kRes) {
+                const uint32_t rw[4] = {rr[k].x, rr[k].y, rr[k].z, rr[k].w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  const float2 t = unpack_half2(rw[h]);
+                  f[2 * h] += t.x;
+                  f[2 * h + 1] += t.y;
+                }
+              }
+              sts128(a0 ^ (k << 4),
+                     make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7])));
+            }
+          };
+          int c = lean_c0;
+          const int c_end = min(lean_c1, p.ncols - ncol0);  // ncols % 32 == 0: whole 16-column groups
+          if ((c & 16) && c < c_end) {
+            chunk(IntTag<16>{}, c);
+            c += 16;
+          }
+          for (; c + 32 <= c_end; c += 32) chunk(IntTag<32>{}, c);
+          if (c < c_end) chunk(IntTag<16>{}, c);
+        };
+        if (k_ln) {
+          if (p.res_tma) run(IntTag<1>{}, IntTag<1>{}, IntTag<1>{}); else run(IntTag<1>{}, IntTag<0>{}, IntTag<1>{});
+        } else if (p.bias != nullptr) {
+          if (p.res_tma) run(IntTag<1>{}, IntTag<1>{}, IntTag<0>{}); else run(IntTag<1>{}, IntTag<0>{}, IntTag<0>{});
+        } else {
+          if (p.res_tma) run(IntTag<0>{}, IntTag<1>{}, IntTag<0>{}); else run(IntTag<0>{}, IntTag<0>{}, IntTag<0>{});
+        }
+      } else {
+      // ---------------- general path ----------------
+      {
+        const int x = tx * p.bw + xi, y = ty * p.bh + yi, n = tb * p.bn + ni;
+        row_ok = tile_ok && (x < p.W) && (y < p.H) && (n < p.n_img);
+        grow = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+      }
+      const int n = tb * p.bn + ni;  // image of this thread's row (per-image bias)
       // single staging buffer: the previous tile's TMA stores must have drained it before anyone overwrites it
-      if (p.tma_store && p.cstage_bufs == 1 && etid == 0 && stores_pending && !(p.dbg & 8)) tma_store_wait_read();
-#endif
+      if (p.cstage_bufs == 1) confirm_stores(tcount);
       // stage this tile's bias slice (double buffered by accumulator stage; the named barrier orders reuse)
       float* sb = sbias + as * 256;
       float* sl = slns + as * 256;
@@ -825,10 +1001,10 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
       if (ew == 0) LR_GEMM_TR(2, tcount, 1);
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
+      if (p.cstage_bufs == 2) confirm_stores(tcount);
       if (p.res_tma) mbar_wait(&rfull[tcount & 1], (tcount >> 1) & 1);  // residual tile is in the staging buffer
       if (ew == 0) LR_GEMM_TR(2, tcount, 2);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
-      float rs_s = 0.f, rs_q = 0.f;  // rowstats_out: this thread's row, the columns this warp half converts
       for (; c < p.block_n; c += 64) {
         uint32_t v[32];
         if (p.dbg & 32) {
@@ -987,6 +1163,7 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
           }
         }
       }
+      }  // general path
       tc_fence_before();
       __syncwarp();
       if (ew == 0) LR_GEMM_TR(2, tcount, 3);
@@ -995,37 +1172,25 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
       }
       if (p.rowstats_out != nullptr && row_ok)
         p.rowstats_out[grow * p.rowstats_ld + tn * 2 + half] = make_float2(rs_s, rs_q);
-#if LR_STORE_WARP
       if (p.tma_store) {
-        // the fp16 tile is complete in smem: hand it to the store warp (generic-proxy writes -> async proxy first)
-        fence_proxy_async_smem();
-        mbar_arrive(&cfull[cbuf]);
-        if (ew == 0) LR_GEMM_TR(2, tcount, 4);
-        if (ew == 0) LR_GEMM_TR(2, tcount, 5);
-      }
-#else
-      if (p.tma_store) {
-        // the fp16 tile is complete in smem: one thread writes it out with TMA (rows / columns outside the tensor are
-        // clipped by the tensor map, so partial tiles need no masking)
-        // two staging buffers: the store issued a whole tile ago has long finished reading its buffer; confirming it
-        // here (before the barrier) is free and makes that buffer safe for the next tile
-        if (p.cstage_bufs == 2 && etid == 0 && stores_pending && !(p.dbg & 8)) tma_store_wait_read();
+        // the fp16 tile is complete in smem: lane 0 of epilogue warp i writes slab i out with TMA (rows / columns outside
+        // the tensor are clipped by the tensor map, so partial tiles need no masking). The stores that last read this
+        // staging buffer were confirmed before anyone wrote to it (confirm_stores).
         fence_proxy_async_smem();
         asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
         if (ew == 0) LR_GEMM_TR(2, tcount, 4);
-        if (etid == 0 && tile_ok && !(p.dbg & 8)) {
+        if (issuer && tile_ok && !(p.dbg & 8)) {
           const int oc_tile0 = k_geglu ? (ncol0 >> 1) : ncol0;
           const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tb * p.bn;
-          for (int sl = 0; sl < full_slabs; ++sl)
-            if (oc_tile0 + sl * 64 < p.n_valid)
-              tma_store_4d(&p.tmC, cstage + sl * (kBlockM * 128), oc_tile0 + sl * 64, x0, y0, n0);
-          if ((ocols_tile & 63) != 0 && oc_tile0 + full_slabs * 64 < p.n_valid)
-            tma_store_4d(&p.tmC2, cstage + full_slabs * (kBlockM * 128), oc_tile0 + full_slabs * 64, x0, y0, n0);
-          tma_store_commit();
-          stores_pending = true;
+          const int oc = oc_tile0 + ew * 64;
+          if (oc < p.n_valid && ew * 64 < ocols_tile) {
+            if (ew < full_slabs) tma_store_4d(&p.tmC, cstage + ew * (kBlockM * 128), oc, x0, y0, n0);
+            else tma_store_4d(&p.tmC2, cstage + full_slabs * (kBlockM * 128), oc, x0, y0, n0);
+            tma_store_commit();
+            stores_pending = true;
+          }
         }
-        // the other staging buffer is free (its last store was confirmed above): fetch the next tile's residual into it
-        if (p.res_tma && etid == 0 && u + unit_step < num_units) issue_res(u + unit_step, (tcount + 1) & 1);
+        if (ew == 0) LR_GEMM_TR(2, tcount, 6);
         if (p.stats_out != nullptr && tile_ok) {
           // GroupNorm statistics of the tile just staged (the fp16 values the TMA store is writing): thread -> (pair of
           // output columns, half of the rows). 32 consecutive threads read 128 contiguous bytes of one row: no bank
@@ -1079,49 +1244,9 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
         }
         if (ew == 0) LR_GEMM_TR(2, tcount, 5);
       }
-#endif
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-#if !LR_STORE_WARP
-    if (p.tma_store && etid == 0 && stores_pending) tma_store_wait_read();
-#else
-    (void)stores_pending;
-  } else if (p.tma_store) {
-    // ------------------------------- store warp ---------------------------------------------------------------
-    // Writes every staged output tile out with TMA (rows / columns outside the tensor are clipped by the tensor map, so
-    // partial tiles need no masking), then releases the staging buffer once the stores have finished reading it.
-    const int ocols_tile = p.geglu ? p.block_n / 2 : p.block_n;
-    const int full_slabs = ocols_tile >> 6;
-    int tcount = 0;
-    for (int tile = unit0; tile < num_tiles; tile += unit_step, ++tcount) {
-      const int cbuf = (p.cstage_bufs == 2) ? (tcount & 1) : 0;
-      mbar_wait(&cfull[cbuf], (tcount / p.cstage_bufs) & 1);
-      if (lane == 0) {
-        const int tn = tile % p.tiles_n;
-        int tm = (tile / p.tiles_n) * CG + static_cast<int>(rank);
-        const bool tile_ok = tm < tiles_m;
-        if (tile_ok && !(p.dbg & 8)) {
-          const int tx = tm % p.tiles_x;
-          tm /= p.tiles_x;
-          const int ty = tm % p.tiles_y;
-          const int tb = tm / p.tiles_y;
-          const uint8_t* cstage = smem + p.cstage_off + cbuf * p.cstage_bytes;
-          const int ncol0 = tn * p.block_n;
-          const int oc_tile0 = p.geglu ? (ncol0 >> 1) : ncol0;
-          const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tb * p.bn;
-          for (int sl = 0; sl < full_slabs; ++sl)
-            if (oc_tile0 + sl * 64 < p.n_valid)
-              tma_store_4d(&p.tmC, cstage + sl * (kBlockM * 128), oc_tile0 + sl * 64, x0, y0, n0);
-          if ((ocols_tile & 63) != 0 && oc_tile0 + full_slabs * 64 < p.n_valid)
-            tma_store_4d(&p.tmC2, cstage + full_slabs * (kBlockM * 128), oc_tile0 + full_slabs * 64, x0, y0, n0);
-          tma_store_commit();
-          tma_store_wait_read();
-        }
-        mbar_arrive(&cfree[cbuf]);
-      }
-      __syncwarp();
-    }
-#endif
+    if (issuer && stores_pending) tma_store_wait_read();
   }
 
   tc_fence_before();

@@ -448,6 +448,19 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
     LR_TRY(make_tmap(&p.tmR2, s.residual, 4, dims, str, box, es, false));
     p.res_tma = 1;
   }
+  {
+    // lean epilogue path (GemmParams::epi_lean): everything the UNet's Linears and residual convs need, nothing else
+    static const bool lean_enabled = getenv("LR_NO_LEAN_EPI") == nullptr;
+    // (a folded LayerNorm only in its usual form: per-row (mean, rstd) table, token-matrix geometry)
+    const bool ln_ok = p.ln_part == nullptr &&
+                       (p.ln_stats == nullptr || (p.tiles_y == 1 && p.tiles_b == 1 && bw == kBlockM &&
+                                                  (reinterpret_cast<uintptr_t>(s.ln_s) & 15) == 0));
+    p.epi_lean = (lean_enabled && tma_store && ksplit == 1 && ln_ok && p.bias_img == nullptr &&
+                  p.rowstats_out == nullptr && s.out_scale == 1.0f && (s.residual == nullptr || p.res_tma) &&
+                  s.ncols % 32 == 0 && p.dbg == 0 && (reinterpret_cast<uintptr_t>(s.bias) & 15) == 0)
+                     ? 1
+                     : 0;
+  }
   if (tma_store) {
     // output tensor as the kernel tiles it: [cols, W, H, N] over the OUTPUT pixel grid
     uint64_t dims[4] = {static_cast<uint64_t>(n_valid), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
