@@ -12,13 +12,14 @@
 #ifndef LR_B200_H_
 #define LR_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define LR_B200_ABI_VERSION 2
+#define LR_B200_ABI_VERSION 3
 
 /* ---- library ---------------------------------------------------------------------------------------------- */
 int lr_abi_version(void);
@@ -203,7 +204,9 @@ int lr_attention_f16(const void* q, int ldq, int q_col0, const void* k, int ldk,
                      int v_col0, void* out, int ld_out, int batch, int heads, int tq, int tk, float scale,
                      void* stream);
 /* GroupNorm(groups, eps) [+ SiLU] over concat(x0, x1) -> out [n, P, c0+c1] fp16 (util.py:217-219, attention.py:90-91).
- * scratch: at least n*groups*16 + n*(c0+c1)*8 bytes. */
+ * scratch: lr_groupnorm_scratch_bytes(n, groups, P) bytes of device memory, 16-byte aligned (per-chunk partial sums and
+ * the grid-barrier counters of the single-launch kernel; contents need not be preserved between calls). */
+size_t lr_groupnorm_scratch_bytes(int n, int groups, int P);
 int lr_groupnorm_f16(const void* x0, int c0, const void* x1, int c1, int n, int P, int groups, float eps,
                      const float* gamma, const float* beta, int silu, void* out, void* scratch, void* stream);
 int lr_layernorm_f16(const void* x, int M, int C, const float* gamma, const float* beta, float eps, void* out,

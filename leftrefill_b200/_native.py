@@ -4,14 +4,14 @@ There is deliberately no fallback: if the library is missing or a call fails, th
 """
 import ctypes
 import os
-from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_void_p)
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_size_t, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # LR_B200_LIB: A/B experiments against another build of the same ABI (tests/gpu_time_gemm.py); normal use never sets it
 LIB_PATH = os.environ.get("LR_B200_LIB") or os.path.join(_HERE, "liblr_b200.so")
 
 
-ABI_VERSION = 2  # LR_B200_ABI_VERSION of include/lr_b200.h
+ABI_VERSION = 3  # LR_B200_ABI_VERSION of include/lr_b200.h
 
 
 class LRError(RuntimeError):
@@ -109,6 +109,7 @@ SIGNATURES = {
                                           c_void_p, c_void_p]),
     "lr_attention_f16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
                                  c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "lr_groupnorm_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "lr_groupnorm_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                  c_int, c_void_p, c_void_p, c_void_p]),
     "lr_layernorm_f16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),

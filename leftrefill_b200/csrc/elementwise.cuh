@@ -23,8 +23,25 @@ __device__ __forceinline__ void store8(__half* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) =
       make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
 }
-// x * sigmoid(x) with MUFU.EX2 + MUFU.RCP (no IEEE division: the slow path of `/` made GroupNorm+SiLU issue bound)
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// x * sigmoid(x) with MUFU.EX2 + MUFU.RCP (no IEEE division: the slow path of `/` made GroupNorm+SiLU issue bound;
+// flush-to-zero forms: __expf / __fdividef add three range-fixup instructions per element that change nothing here,
+// 1 + e rounds to 1 long before e is denormal)
+__device__ __forceinline__ float silu_f(float x) { return x * rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f)); }
+// [silu](x * sc + sh) on the two fp16 values of one packed word, in packed fp32 pairs (FFMA2 / FMUL2 / FADD2)
+__device__ __forceinline__ uint32_t affine_silu_h2(uint32_t w, f32x2 sc, f32x2 sh, int do_silu) {
+  const float2 t = unpack_half2(w);
+  f32x2 y = fma2(pk2(t.x, t.y), sc, sh);
+  if (do_silu) {
+    float a0, a1;
+    upk2(mul2(y, pk2(-1.4426950408889634f, -1.4426950408889634f)), a0, a1);
+    float d0, d1;
+    upk2(add2(pk2(ex2_ftz(a0), ex2_ftz(a1)), pk2(1.0f, 1.0f)), d0, d1);
+    y = mul2(y, pk2(rcp_ftz(d0), rcp_ftz(d1)));
+  }
+  float y0, y1;
+  upk2(y, y0, y1);
+  return pack_half2(y0, y1);
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // GroupNorm (reference: GroupNorm32, ldm/modules/diffusionmodules/util.py:217-219, fp32 math; Normalize,
@@ -41,14 +58,32 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + _
 //     per-group (sum, sum of squares) in fp64; the CS partials are exchanged through distributed shared memory and
 //     every CTA finalises (mean, rstd) itself; pass 2 re-reads its own pixels (L2 / L1 resident: the whole image is
 //     a few MB at most) and writes y = [silu]((x - mean) * rstd * gamma + beta). One launch, no atomics, no scratch.
-//   * two-pass (gn_stats_kernel + gn_apply_kernel) for images too large for one cluster: fp64 atomics into a per-site
-//     scratch, the last CTA of an image (ticket) finalises (mean, rstd).
-// Scratch layout per call site (zeroed by the caller): double sums[n][G][2]; float2 mr[n][G]; unsigned ticket[n].
+//   * persistent (gn_persistent_kernel) for images too large for one cluster: ONE launch of at most one CTA per SM.
+//     Every image is cut into gn_chunks(P) pixel chunks (a function of the image size only); each CTA owns a contiguous
+//     span of (image, chunk) items. Pass 1 streams its items from HBM and leaves one fp64 (sum, sum of squares) per
+//     (item, group) in the scratch table - plain stores, no atomics; a grid-wide barrier (all CTAs are resident: the
+//     grid never exceeds the SM count); pass 2 sums the chunk partials of an image in chunk order (fixed tree), derives
+//     (mean, rstd) and re-reads its own items - L2 hits, the items were just streamed through it - to write
+//     y = [silu]((x - mean) * rstd * gamma + beta). Bit-reproducible and independent of the batch size and of the
+//     number of CTAs. (Round 1 used a statistics kernel with fp64 atomics + an apply kernel: two launches of short-lived
+//     CTAs that reached 2.2 TB/s; profiles/r2_ab_gn_persistent.txt.)
+// Scratch layout per call site: unsigned counters[4] (arrive, depart: zero on entry, the kernel leaves them zero);
+// at byte 256: double2 part[n][chunks][G].
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kGnBatch = 8;
 
-__host__ __device__ inline size_t gn_scratch_bytes(int n, int groups) {
-  return static_cast<size_t>(n) * groups * (2 * sizeof(double) + sizeof(float2)) + static_cast<size_t>(n) * 8;
+// pixel chunks per image (depends on the image size ONLY): 37 chunks per image - 4 images fill the 148 SMs exactly, 8
+// images give every CTA two items (32 chunks left 40 CTAs with one item and 108 with two) - of 16 to 2048 pixels; the
+// first-stage decoder's 512 x 1024 maps get 256 chunks, enough for a single image to occupy the GPU
+__host__ __device__ inline int gn_chunk_pixels(int P) {
+  int chunk = (P + 36) / 37;
+  if (chunk < 16) chunk = 16;
+  if (chunk > 2048) chunk = 2048;
+  return chunk;
+}
+__host__ __device__ inline int gn_chunks(int P) { const int c = gn_chunk_pixels(P); return (P + c - 1) / c; }
+__host__ __device__ inline size_t gn_scratch_bytes(int n, int groups, int P) {
+  return 256 + static_cast<size_t>(n) * gn_chunks(P) * groups * 2 * sizeof(double);
 }
 
 __device__ __forceinline__ uint4 ldg16(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
@@ -130,120 +165,191 @@ __device__ __forceinline__ float2 gn_finalize(double sum, double sq, double cnt,
 __device__ __forceinline__ void gn_apply_rows(const __half* __restrict__ base, int ld, __half* __restrict__ o, int C,
                                               int p0, int p_end, int rpi, const float (&sc)[8], const float (&sh)[8],
                                               int do_silu) {
-  for (int p = p0; p < p_end; p += kGnBatch * rpi) {
-    uint4 v[kGnBatch];
+  // Software pipeline of two half batches: the loads of one are in flight while the other is normalised and stored.
+  // With SiLU the math alone is MUFU-bound near the HBM rate (EX2 + RCP per element at 16 / clk / SM = 16 B / clk / SM),
+  // so load latency has to hide behind it, not add to it (tests/gpu_time_gn_passes.py: 21 -> 13 us on 8 x 64x128x320).
+  constexpr int kH = kGnBatch / 2;
+  const int step = kH * rpi;
+  f32x2 sc2[4], sh2[4];
 #pragma unroll
-    for (int u = 0; u < kGnBatch; ++u) {
+  for (int i = 0; i < 4; ++i) {
+    sc2[i] = pk2(sc[2 * i], sc[2 * i + 1]);
+    sh2[i] = pk2(sh[2 * i], sh[2 * i + 1]);
+  }
+  auto load = [&](int p, uint4 (&v)[kH]) {
+#pragma unroll
+    for (int u = 0; u < kH; ++u) {
       const int pp = p + u * rpi;
       v[u] = (pp < p_end) ? ldg16(base + static_cast<size_t>(pp) * ld) : make_uint4(0u, 0u, 0u, 0u);
     }
+  };
+  auto proc = [&](int p, const uint4 (&v)[kH]) {
 #pragma unroll
-    for (int u = 0; u < kGnBatch; ++u) {
+    for (int u = 0; u < kH; ++u) {
       const int pp = p + u * rpi;
       if (pp < p_end) {
-        float f[8];
-        unpack8(v[u], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float y = fmaf(f[j], sc[j], sh[j]);
-          f[j] = do_silu ? silu_f(y) : y;
-        }
-        store8(o + static_cast<size_t>(pp) * C, f);
+        uint4 y;
+        y.x = affine_silu_h2(v[u].x, sc2[0], sh2[0], do_silu);
+        y.y = affine_silu_h2(v[u].y, sc2[1], sh2[1], do_silu);
+        y.z = affine_silu_h2(v[u].z, sc2[2], sh2[2], do_silu);
+        y.w = affine_silu_h2(v[u].w, sc2[3], sh2[3], do_silu);
+        *reinterpret_cast<uint4*>(o + static_cast<size_t>(pp) * C) = y;
       }
     }
+  };
+  if (p0 >= p_end) return;
+  uint4 va[kH], vb[kH];
+  int p = p0;
+  load(p, va);
+  while (true) {
+    const int pn = p + step;
+    if (pn < p_end) load(pn, vb);
+    proc(p, va);
+    if (pn >= p_end) break;
+    p = pn + step;
+    if (p < p_end) load(p, va);
+    proc(pn, vb);
+    if (p >= p_end) break;
   }
 }
 
-// grid = (pixel chunks, n); block = kNormThreads; dynamic smem = rpi * 2 * C floats.
-__global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __half* __restrict__ x0, int c0,
-                                                                const __half* __restrict__ x1, int c1, int P,
-                                                                int chunk, int groups, float eps,
-                                                                unsigned char* __restrict__ scratch) {
+// Persistent two-pass GroupNorm (see the header comment). grid = min(#SM, n * chunks) CTAs; block = kNormThreads;
+// dynamic smem = rpi * 2 * C floats.
+__global__ void __launch_bounds__(kNormThreads, 1) gn_persistent_kernel(const __half* __restrict__ x0, int c0,
+                                                                        const __half* __restrict__ x1, int c1, int P,
+                                                                        int n_img, int groups, float eps,
+                                                                        const float* __restrict__ gamma,
+                                                                        const float* __restrict__ beta, int do_silu,
+                                                                        __half* __restrict__ out,
+                                                                        unsigned char* __restrict__ scratch, int dbg) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float sm[];  // [rpi][2][C]
+  __shared__ float2 s_mr[64];
   const int C = c0 + c1;
   const int nvec = C / 8;
-  const int n = blockIdx.y;
-  const int n_img = gridDim.y;
-  double* sums = reinterpret_cast<double*>(scratch);
-  float2* mr = reinterpret_cast<float2*>(sums + static_cast<size_t>(n_img) * groups * 2);
-  unsigned* ticket = reinterpret_cast<unsigned*>(mr + static_cast<size_t>(n_img) * groups);
-  const int p_begin = blockIdx.x * chunk;
-  const int p_end = min(P, p_begin + chunk);
+  const int chunk = gn_chunk_pixels(P), chunks = gn_chunks(P);
+  unsigned* cnt = reinterpret_cast<unsigned*>(scratch);
+  double2* part = reinterpret_cast<double2*>(scratch + 256);
+  const int items = n_img * chunks;
+  const int G = gridDim.x;
+  const int i0 = static_cast<int>(static_cast<long long>(blockIdx.x) * items / G);
+  const int i1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * items / G);
   const int rpi = blockDim.x / nvec;  // pixel rows handled per sweep
   const int vec = threadIdx.x % nvec;
   const int rsub = threadIdx.x / nvec;
   const int ch = vec * 8;
-  float s[8], ss[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
-  if (rsub < rpi) {
-    const __half* base = (ch < c0) ? x0 + ch : x1 + (ch - c0);
-    const int ld = (ch < c0) ? c0 : c1;
-    base += static_cast<size_t>(n) * P * ld;
-    gn_accumulate(base, ld, p_begin + rsub, p_end, rpi, s, ss);
-  }
-  double a, b;
-  gn_cta_group_sums(sm, C, rpi, rsub, ch, groups, s, ss, a, b);
-  if (static_cast<int>(threadIdx.x) < groups) {
-    const int g = threadIdx.x;
-    atomicAdd(&sums[(static_cast<size_t>(n) * groups + g) * 2 + 0], a);
-    atomicAdd(&sums[(static_cast<size_t>(n) * groups + g) * 2 + 1], b);
-  }
-  // last CTA of this image finalises (mean, rstd)
-  __shared__ unsigned s_ticket;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&ticket[n], 1u);
-  __syncthreads();
-  if (s_ticket == gridDim.x - 1) {
-    __threadfence();
-    const double cnt = static_cast<double>(P) * (C / groups);
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-      const double sum = __ldcg(&sums[(static_cast<size_t>(n) * groups + g) * 2 + 0]);
-      const double sq = __ldcg(&sums[(static_cast<size_t>(n) * groups + g) * 2 + 1]);
-      mr[static_cast<size_t>(n) * groups + g] = gn_finalize(sum, sq, cnt, eps);
-    }
-  }
-}
+  const __half* src = (ch < c0) ? x0 + ch : x1 + (ch - c0);
+  const int ld = (ch < c0) ? c0 : c1;
 
-// y = [silu]((x - mean) * rstd * gamma + beta) -> out [n, P, C] fp16 (the concat is materialised only here, already
-// normalised).
-__global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __half* __restrict__ x0, int c0,
-                                                                const __half* __restrict__ x1, int c1, int P,
-                                                                int chunk, const unsigned char* __restrict__ scratch,
-                                                                const float* __restrict__ gamma,
-                                                                const float* __restrict__ beta, int groups,
-                                                                int do_silu, __half* __restrict__ out) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int C = c0 + c1;
-  const int nvec = C / 8;
-  const int n = blockIdx.y;
-  const int n_img = gridDim.y;
-  const float2* mr = reinterpret_cast<const float2*>(reinterpret_cast<const double*>(scratch) +
-                                                     static_cast<size_t>(n_img) * groups * 2);
-  const int p_begin = blockIdx.x * chunk;
-  const int p_end = min(P, p_begin + chunk);
-  const int rpi = blockDim.x / nvec;
-  const int vec = threadIdx.x % nvec;
-  const int rsub = threadIdx.x / nvec;
-  if (rsub >= rpi) return;
-  const int ch = vec * 8;
-  const int cpg = C / groups;
-  float sc[8], sh[8];
+  // ---- pass 1: per-(item, group) partial sums ----
+  long long tr[6] = {0, 0, 0, 0, 0, 0};
+  tr[0] = clock64();
+  for (int it = i0; it < i1 && !(dbg & 1); ++it) {
+    const int n = it / chunks, k = it - n * chunks;
+    const int p_begin = k * chunk, p_end = min(P, p_begin + chunk);
+    float s[8], ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+    if (rsub < rpi) gn_accumulate(src + static_cast<size_t>(n) * P * ld, ld, p_begin + rsub, p_end, rpi, s, ss);
+    double a, b;
+    gn_cta_group_sums(sm, C, rpi, rsub, ch, groups, s, ss, a, b);
+    if (static_cast<int>(threadIdx.x) < groups) part[static_cast<size_t>(it) * groups + threadIdx.x] = make_double2(a, b);
+    __syncthreads();  // sm is rewritten by the next item
+  }
+
+  // (gamma / beta of this thread's channels: fetched here so that the barrier hides the latency)
+  float gam[8], bet[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float2 m = mr[static_cast<size_t>(n) * groups + (ch + j) / cpg];
-    sc[j] = m.y * gamma[ch + j];
-    sh[j] = beta[ch + j] - m.x * sc[j];
+    gam[j] = (rsub < rpi) ? __ldg(gamma + ch + j) : 0.f;
+    bet[j] = (rsub < rpi) ? __ldg(beta + ch + j) : 0.f;
   }
-  const __half* base = (ch < c0) ? x0 + ch : x1 + (ch - c0);
-  const int ld = (ch < c0) ? c0 : c1;
-  base += static_cast<size_t>(n) * P * ld;
-  __half* o = out + static_cast<size_t>(n) * P * C + ch;
-  gn_apply_rows(base, ld, o, C, p_begin + rsub, p_end, rpi, sc, sh, do_silu);
+  // ---- grid barrier: every CTA's partials are visible ----
+  tr[1] = clock64();
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&cnt[0], 1u);
+    const long long t0 = clock64();
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+      if (seen < static_cast<unsigned>(G) && clock64() - t0 > 4000000000LL) {
+        printf("lr_b200: groupnorm grid barrier timed out (%u of %d CTAs arrived)\n", seen, G);
+        __trap();
+      }
+    } while (seen < static_cast<unsigned>(G));
+  }
+  __syncthreads();
+
+  // ---- pass 2: finalise per image, normalise own items ----
+  tr[2] = clock64();
+  const int cpg = C / groups;
+  const int tpg = blockDim.x / groups;  // threads that share the chunk sum of one group (a power of two <= 32)
+  const double cntd = static_cast<double>(P) * cpg;
+  int cur_n = -1;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sc[j] = sh[j] = 0.f;
+  for (int it = i0; it < i1; ++it) {
+    const int n = it / chunks, k = it - n * chunks;
+    if (n != cur_n) {
+      __syncthreads();  // everybody is done with the previous image's s_mr
+      const int g = threadIdx.x / tpg, sub = threadIdx.x % tpg;
+      double a = 0.0, b = 0.0;
+      if (g < groups) {
+        const double2* pr = part + (static_cast<size_t>(n) * chunks) * groups + g;
+        // chunk order within a lane (four loads in flight), then a fixed butterfly over the lanes
+        for (int j = sub; j < chunks; j += 4 * tpg) {
+          double2 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            v[u] = (j + u * tpg < chunks) ? __ldcg(pr + static_cast<size_t>(j + u * tpg) * groups) : make_double2(0.0, 0.0);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            a += v[u].x;
+            b += v[u].y;
+          }
+        }
+      }
+      for (int o = tpg >> 1; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (g < groups && sub == 0) s_mr[g] = gn_finalize(a, b, cntd, eps);
+      __syncthreads();
+      cur_n = n;
+      if (rsub < rpi) {  // the affine coefficients of this thread's 8 channels change with the image only
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 m = s_mr[(ch + j) / cpg];
+          sc[j] = m.y * gam[j];
+          sh[j] = bet[j] - m.x * sc[j];
+        }
+      }
+      if (it == i0) tr[3] = clock64();
+    }
+    if (rsub < rpi && !(dbg & 2)) {
+      const int p_begin = k * chunk, p_end = min(P, p_begin + chunk);
+      gn_apply_rows(src + static_cast<size_t>(n) * P * ld, ld, out + static_cast<size_t>(n) * P * C + ch, C, p_begin + rsub,
+                    p_end, rpi, sc, sh, do_silu);
+    }
+  }
+
+  // ---- leave the counters zero for the next launch on this scratch ----
+  tr[4] = clock64();
+  if ((dbg & 16) && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+    printf("gn trace cta %d items %d: pass1 %lld barrier %lld stats %lld apply %lld\n", blockIdx.x, i1 - i0, tr[1] - tr[0],
+           tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3]);
+  if (threadIdx.x == 0) {
+    const unsigned left = atomicAdd(&cnt[1], 1u);
+    if (left == static_cast<unsigned>(G) - 1) {  // everybody has passed the barrier: nobody reads cnt[0] any more
+      cnt[0] = 0;
+      cnt[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // GroupNorm apply [+ SiLU] from the per-(image, channel) coefficients gn_finalize_kernel derived from the PRODUCER's

@@ -1310,14 +1310,17 @@ struct lr_engine {
     {
       gn_sites_cap = 2 * static_cast<int>(res.size()) + static_cast<int>(sts.size()) + 1;
       gn_sites_planned = 0;
-      gn_site_bytes = groupnorm_scratch_bytes(n, 32);
+      gn_site_bytes = groupnorm_scratch_bytes(n, 32, Hh * Wh);  // sized for the largest map
       const size_t bytes = gn_site_bytes * gn_sites_cap;
       void* p;
       LR_TRY(pool.acquire(bytes, &p));
       gn_stats = static_cast<unsigned char*>(p);
       unsigned char* gs = gn_stats;
+      const size_t pitch = gn_site_bytes;
+      const int sites = gn_sites_cap;
       push([=](cudaStream_t st) {
-        cudaError_t e = cudaMemsetAsync(gs, 0, bytes, st);
+        // only the grid-barrier counters at the head of every site need to be zero (launch_groupnorm)
+        cudaError_t e = cudaMemset2DAsync(gs, pitch, 0, 16, sites, st);
         if (e != cudaSuccess) {
           set_error(std::string("cudaMemsetAsync(gn stats): ") + cudaGetErrorString(e));
           return 1;
@@ -1696,14 +1699,16 @@ struct lr_vae : lr_engine {
     {
       gn_sites_cap = 2 * static_cast<int>(res.size()) + 2;
       gn_sites_planned = 0;
-      gn_site_bytes = groupnorm_scratch_bytes(n, 32);
+      gn_site_bytes = groupnorm_scratch_bytes(n, 32, 64 * Hh * Ww);  // sized for the decoded resolution
       const size_t bytes = gn_site_bytes * gn_sites_cap;
       void* p;
       LR_TRY(pool.acquire(bytes, &p));
       gn_stats = static_cast<unsigned char*>(p);
       unsigned char* gs = gn_stats;
+      const size_t pitch = gn_site_bytes;
+      const int sites = gn_sites_cap;
       push([=](cudaStream_t st) {
-        cudaError_t e = cudaMemsetAsync(gs, 0, bytes, st);
+        cudaError_t e = cudaMemset2DAsync(gs, pitch, 0, 16, sites, st);
         if (e != cudaSuccess) {
           set_error(std::string("cudaMemsetAsync(gn stats): ") + cudaGetErrorString(e));
           return 1;
@@ -2291,6 +2296,7 @@ int lr_attention_f16(const void* q, int ldq, int q_col0, const void* k, int ldk,
   return launch_attn_op(op, static_cast<cudaStream_t>(stream));
 }
 
+size_t lr_groupnorm_scratch_bytes(int n, int groups, int P) { return groupnorm_scratch_bytes(n, groups, P); }
 int lr_groupnorm_f16(const void* x0, int c0, const void* x1, int c1, int n, int P, int groups, float eps,
                      const float* gamma, const float* beta, int silu, void* out, void* scratch, void* stream) {
   LR_CHECK(x0 && gamma && beta && out && scratch, "lr_groupnorm_f16: null argument");

@@ -900,6 +900,7 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
             }
             const uint32_t a0 = row_base(c);
             uint4 rr[kN / 8];
+            (void)rr;
             if constexpr (kRes) {
 #pragma unroll
               for (int k = 0; k < kN / 8; ++k) rr[k] = lds128(a0 ^ (k << 4));

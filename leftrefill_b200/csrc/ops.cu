@@ -641,7 +641,9 @@ int launch_attn_op(const AttnOp& op, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------------------
 // normalisation / elementwise
 // ------------------------------------------------------------------------------------------------------------
-size_t groupnorm_scratch_bytes(int n_img, int groups) { return (gn_scratch_bytes(n_img, groups) + 255) & ~size_t(255); }
+size_t groupnorm_scratch_bytes(int n_img, int groups, int P) {
+  return (gn_scratch_bytes(n_img, groups, P) + 255) & ~size_t(255);
+}
 
 int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_img, int P, int groups, float eps,
                      const float* gamma, const float* beta, int do_silu, void* scratch, int scratch_is_zero,
@@ -654,33 +656,31 @@ int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_i
   LR_CHECK(x1 != nullptr || c1 == 0, "groupnorm: c1 without x1");
   const int rpi = kNormThreads / (C / 8);
   const size_t smem = static_cast<size_t>(rpi) * 2 * C * sizeof(float);
-  // Images of up to 8 x LR_GN_FUSED_KB KB take the single-launch fused kernel (one 8-CTA cluster per image, second pass
-  // hits L2), larger ones the two-pass scheme. Measured on B200 at N = 8 (round 1, r1m): fused wins up to 1.3 MB per
-  // image (16x32x1280: 17.7 vs 18.8 us; 8x16x1280: 9.6 vs 12.6 us), two-pass from 2.6 MB (32x64x640: 24.5 vs 28.1 us);
-  // 16-CTA (non-portable) clusters were slower than both everywhere. No choice depends on the batch size (bit-exact
-  // batch invariance).
+  // Images of up to 8 x LR_GN_FUSED_KB KB take the single-launch cluster kernel (one 8-CTA cluster per image, second pass
+  // hits L2), larger ones the persistent kernel. Measured on B200 at N = 8 (round 1, r1m): the cluster kernel wins up to
+  // 1.3 MB per image (16x32x1280, 8x16x1280); 16-CTA (non-portable) clusters were slower everywhere. No choice depends
+  // on the batch size (bit-exact batch invariance).
   static const int fused_kb = env_int("LR_GN_FUSED_KB", 160);
-  static const int chunk_div = env_int("LR_GN_CHUNK_DIV", 32);
   constexpr int kCS = 8;
   const size_t img_bytes = static_cast<size_t>(P) * C * sizeof(__half);
-  if (fused_kb > 0 && groups <= 64 && img_bytes <= static_cast<size_t>(kCS) * fused_kb * 1024) {
+  // the persistent kernel shares the chunk sums of a group between 512 / groups lanes of one warp
+  const bool persistent_ok = groups >= 16 && groups <= 64 && (groups & (groups - 1)) == 0;
+  if (groups <= 64 && ((fused_kb > 0 && img_bytes <= static_cast<size_t>(kCS) * fused_kb * 1024) || !persistent_ok)) {
     LR_CUDA(launch_pdl(gn_fused_cluster_kernel, dim3(kCS, n_img), dim3(kNormThreads), smem, st, kCS, x0, c0, x1, c1, P,
                        groups, eps, gamma, beta, do_silu, out));
     LR_LAUNCHED();
     return 0;
   }
+  LR_CHECK(persistent_ok, "groupnorm: unsupported group count");
   LR_CHECK(scratch != nullptr, "groupnorm: scratch buffer required");
-  // The chunking must NOT depend on the batch size: the reduction tree has to be identical for any n_img.
-  int chunk = P / chunk_div;
-  if (chunk < 16) chunk = 16;
-  if (chunk > 512) chunk = 512;
-  const dim3 grid(cdiv(P, chunk), n_img);
-  if (!scratch_is_zero) LR_CUDA(cudaMemsetAsync(scratch, 0, gn_scratch_bytes(n_img, groups), st));
-  LR_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(kNormThreads), smem, st, 1, x0, c0, x1, c1, P, chunk, groups, eps,
-                     static_cast<unsigned char*>(scratch)));
-  LR_LAUNCHED();
-  LR_CUDA(launch_pdl(gn_apply_kernel, grid, dim3(kNormThreads), 0, st, 1, x0, c0, x1, c1, P, chunk,
-                     static_cast<const unsigned char*>(scratch), gamma, beta, groups, do_silu, out));
+  LR_CHECK((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "groupnorm: scratch must be 16-byte aligned");
+  const long long items = static_cast<long long>(n_img) * gn_chunks(P);
+  const int grid = static_cast<int>(items < sm_count() ? items : sm_count());  // all CTAs resident: grid-wide barrier inside
+  if (!scratch_is_zero) LR_CUDA(cudaMemsetAsync(scratch, 0, 16, st));
+  // bring-up (tests/gpu_time_gn_passes.py, gpu_gn_trace.py): 1 = skip pass 1, 2 = skip pass 2, 16 = print phase cycles
+  static const int gn_dbg = env_int("LR_GN_DEBUG", 0);
+  LR_CUDA(launch_pdl(gn_persistent_kernel, dim3(grid), dim3(kNormThreads), smem, st, 1, x0, c0, x1, c1, P, n_img, groups,
+                     eps, gamma, beta, do_silu, out, static_cast<unsigned char*>(scratch), gn_dbg));
   LR_LAUNCHED();
   return 0;
 }

@@ -132,9 +132,10 @@ int build_attn_op(AttnOp* op, const AttnSpec& s);
 int launch_attn_op(const AttnOp& op, cudaStream_t st);
 
 // ---- normalisation / elementwise launchers ----
-// GroupNorm over concat(x0[c0], x1[c1]) -> out [n, P, c0+c1]; scratch: groupnorm_scratch_bytes(n, groups) bytes
-// (zeroed here unless the caller guarantees scratch_is_zero).
-size_t groupnorm_scratch_bytes(int n_img, int groups);
+// GroupNorm over concat(x0[c0], x1[c1]) -> out [n, P, c0+c1]; scratch: groupnorm_scratch_bytes(n, groups, P) bytes whose
+// first 16 bytes (grid-barrier counters) must be zero on entry: zeroed here unless the caller guarantees
+// scratch_is_zero; the kernel leaves them zero.
+size_t groupnorm_scratch_bytes(int n_img, int groups, int P);
 int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_img, int P, int groups, float eps,
                      const float* gamma, const float* beta, int do_silu, void* scratch, int scratch_is_zero,
                      __half* out, cudaStream_t st);

@@ -104,7 +104,7 @@ def groupnorm(x0, gamma, beta, eps, silu=False, x1=None, groups=32):
     c1 = x1.shape[3] if x1 is not None else 0
     C = c0 + c1
     out = torch.empty(n, h, w, C, dtype=torch.float16, device=x0.device)
-    scratch = torch.empty(n * groups * 16 + n * C * 8, dtype=torch.uint8, device=x0.device)
+    scratch = torch.empty(N.lib().lr_groupnorm_scratch_bytes(n, groups, h * w), dtype=torch.uint8, device=x0.device)
     N.check(N.lib().lr_groupnorm_f16(N.ptr(x0), c0, N.ptr(x1), c1, n, h * w, groups, float(eps),
                                      N.ptr(_chk(gamma, torch.float32)), N.ptr(_chk(beta, torch.float32)), int(silu),
                                      N.ptr(out), N.ptr(scratch), N.current_stream()), "groupnorm")

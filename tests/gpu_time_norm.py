@@ -83,8 +83,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         run()
     else:
-        schemes = [("default", {}), ("fused<=3.5MB", {"LR_GN_FUSED_KB": "448"}), ("twopass/32", {"LR_GN_FUSED_KB": "0"}),
-                   ("twopass/64", {"LR_GN_FUSED_KB": "0", "LR_GN_CHUNK_DIV": "64"})]
+        schemes = [("default", {}), ("cluster<=3.5MB", {"LR_GN_FUSED_KB": "448"}), ("persistent", {"LR_GN_FUSED_KB": "0"})]
         for tag, env in schemes:
             e = dict(os.environ, LR_TAG=tag, **env)
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "run"], env=e, capture_output=True,

@@ -21,7 +21,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in lr_b200.h but not exported"
     assert declared == set(N.SIGNATURES), "ctypes signature table and header disagree"
-    assert N.lib().lr_abi_version() == N.ABI_VERSION == 2
+    assert N.lib().lr_abi_version() == N.ABI_VERSION == 3
 
 
 def _engine_table(model):
