@@ -488,20 +488,30 @@ __global__ void __launch_bounds__(kGnFinalizeThreads) gn_finalize_kernel(const f
   double s = 0.0, q = 0.0;
   // channels of this group that live in source 0 / source 1 (a group may straddle the concat boundary)
   const int a0 = min(max(c0 - ch0, 0), cpg);  // first a0 channels of the group are in source 0
-  for (int idx = threadIdx.x; idx < ppi0 * a0; idx += kGnFinalizeThreads) {
-    const int i = idx / a0, c = idx - i * a0;
-    const float2 v = __ldg(part0 + (static_cast<size_t>(n) * ppi0 + i) * c0 + ch0 + c);
-    s += static_cast<double>(v.x);
-    q += static_cast<double>(v.y);
-  }
+  // entries of one source: eight independent loads in flight per thread, added in index order (as a plain loop would)
+  auto sum_source = [&](const float2* __restrict__ part, int ppi, int cs, int chs, int na) {
+    const int tot = ppi * na;
+    for (int base = threadIdx.x; base < tot; base += 8 * kGnFinalizeThreads) {
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = base + u * kGnFinalizeThreads;
+        const int i = idx / na, c = idx - i * na;
+        v[u] = (idx < tot) ? __ldg(part + (static_cast<size_t>(n) * ppi + i) * cs + chs + c) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (base + u * kGnFinalizeThreads < tot) {
+          s += static_cast<double>(v[u].x);
+          q += static_cast<double>(v[u].y);
+        }
+      }
+    }
+  };
+  if (a0 > 0) sum_source(part0, ppi0, c0, ch0, a0);
   const int a1 = cpg - a0;
   const int ch1 = ch0 + a0 - c0;  // first channel of the group inside source 1
-  for (int idx = threadIdx.x; idx < ppi1 * a1; idx += kGnFinalizeThreads) {
-    const int i = idx / a1, c = idx - i * a1;
-    const float2 v = __ldg(part1 + (static_cast<size_t>(n) * ppi1 + i) * c1 + ch1 + c);
-    s += static_cast<double>(v.x);
-    q += static_cast<double>(v.y);
-  }
+  if (a1 > 0) sum_source(part1, ppi1, c1, ch1, a1);
   red[0][threadIdx.x] = s;
   red[1][threadIdx.x] = q;
   __syncthreads();
@@ -529,6 +539,45 @@ __global__ void __launch_bounds__(kGnFinalizeThreads) gn_finalize_kernel(const f
 // Persistent: grid-stride over tiles. gamma / beta are staged once per CTA.
 // Dynamic smem: stages * kLnTileRows * C * 2 (tiles) + 2 * C * 4 (gamma, beta) + 2 * stages * 8 (barriers).
 // ------------------------------------------------------------------------------------------------------------
+// (mean, rstd) per token row from the per-row (sum, sum of squares) partials the producing GEMM's epilogue left
+// (GemmParams::rowstats_out): part [M][ld] float2, the first `slots` entries of a row summed in slot order.
+// Replaces the statistics pass over the activation (ln_stats_kernel) when the producer is one of our GEMMs.
+__global__ void __launch_bounds__(256) ln_rows_finalize_kernel(const float2* __restrict__ part, int ld, int slots, int M,
+                                                               int C, float eps, float2* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  const float2* pr = part + static_cast<size_t>(row) * ld;
+  float su = 0.f, sq = 0.f;
+  if ((slots & 1) == 0 && (ld & 1) == 0) {
+    for (int i0 = 0; i0 < slots; i0 += 8) {  // four 16-byte loads (8 slots) in flight
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = (i0 + 2 * u < slots) ? __ldg(reinterpret_cast<const float4*>(pr + i0) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i0 + 2 * u < slots) {
+          su += v[u].x;
+          sq += v[u].y;
+          su += v[u].z;
+          sq += v[u].w;
+        }
+      }
+    }
+  } else {
+    for (int i = 0; i < slots; ++i) {
+      const float2 t = __ldg(pr + i);
+      su += t.x;
+      sq += t.y;
+    }
+  }
+  const float inv_c = 1.0f / static_cast<float>(C);
+  const float mean = su * inv_c;
+  stats[row] = make_float2(mean, rsqrtf(fmaxf(fmaf(-mean, mean, sq * inv_c), 0.f) + eps));
+}
+
 constexpr int kLnConsumerWarps = 8;
 constexpr int kLnRowsPerWarp = 2;
 constexpr int kLnTileRows = kLnConsumerWarps * kLnRowsPerWarp;  // 16

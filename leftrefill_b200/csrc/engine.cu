@@ -606,9 +606,10 @@ struct lr_engine {
     int ld = 0;
     int slots = 0;           // valid entries per row (0: the current content of the stream has no partials)
   };
-  // Measured on B200 (round 2, profiles/r2_ab_ln_rowstats.txt): the 48 ln_stats_kernel passes (0.58 ms) disappear, but the
-  // producing Linears are epilogue bound - the extra 2 FP ops per element and the consumer's per-row partial loads cost
-  // 0.4-0.7 ms: forward 19.72 ms with, 19.57 ms without. OFF by default (LR_LN_ROWSTATS=1 enables; parity-tested).
+  // Measured on B200 (round 2, profiles/r2_ab_ln_rowstats.txt), before and after the lean epilogue: the 48
+  // ln_stats_kernel passes disappear, but the producers' extra work plus either the consumers' scattered partial loads
+  // or 48 tiny finalize kernels cost as much (18.4 ms either way). OFF by default (LR_LN_ROWSTATS=1 enables;
+  // parity-tested).
   bool ln_rowstats = getenv("LR_LN_ROWSTATS") != nullptr && atoi(getenv("LR_LN_ROWSTATS")) != 0;
   int add_linear(const __half* a, int M, int K, const __half* w, int ncols, const float* bias, const __half* residual,
                  int ld_res, __half* out, int ld_out, int geglu, const float* ln_stats = nullptr,
@@ -616,11 +617,16 @@ struct lr_engine {
     ConvSpec s;
     s.ln_stats = ln_stats;
     s.ln_s = ln_s;
-    if (ln_from != nullptr) {  // LayerNorm statistics from the producer's partials instead of ln_stats
-      s.ln_stats = nullptr;
-      s.ln_part = ln_from->table;
-      s.ln_slots = ln_from->slots;
-      s.ln_ld = ln_from->ld;
+    if (ln_from != nullptr) {
+      // LayerNorm statistics from the producer's per-row partials: a tiny kernel turns them into the (mean, rstd) table
+      // the stats pass would have written (the consumer can also sum them itself, ConvSpec::ln_part: measured slower,
+      // every N-tile of the consumer repeats the scattered loads - profiles/r2_ab_ln_rowstats.txt)
+      LR_CHECK(ln_stats != nullptr, "internal: row statistics need the (mean, rstd) table of the block");
+      const float* tb = ln_from->table;
+      const int ld = ln_from->ld, slots = ln_from->slots;
+      float* dst = const_cast<float*>(ln_stats);
+      push([=](cudaStream_t st) { return launch_ln_rows_finalize(tb, ld, slots, M, K, 1e-5f, dst, st); }, 3, 0.0,
+           "layernorm-finalize M=" + std::to_string(M) + " C=" + std::to_string(K));
     }
     if (stats_to != nullptr && stats_to->table != nullptr) {
       s.rowstats_out = stats_to->table;

@@ -835,6 +835,47 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
           return (slab < full_slabs) ? (cst + slab * (kBlockM * 128) + r * 128) ^ (cpx ^ r7x)
                                      : (cst + full_slabs * (kBlockM * 128) + r * 64) ^ cpx;
         };
+        // folded LayerNorm (linear geometry: row index = 128 * M-tile + r): out = rstd * acc + (-mean * rstd) * ln_s + bias.
+        // The row statistics do not depend on the MMA: fetched before the accumulator wait.
+        float ln_rstd = 1.f, ln_nrm = 0.f;
+        const int lrow = tm_idx * kBlockM + r;
+        const bool lrow_ok = tile_ok && lrow < p.W;
+        if (k_ln && lrow_ok) {
+          float2 st;
+          if (p.ln_part != nullptr) {
+            float su = 0.f, sq = 0.f;
+            const float2* pr = p.ln_part + static_cast<size_t>(lrow) * p.ln_ld;
+            if (p.ln_slots <= 16 && (p.ln_slots & 1) == 0 && (p.ln_ld & 1) == 0) {
+              // all partials of the row in flight at once (two per 16-byte load), then summed in slot order
+              float4 v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                v[i] = (2 * i < p.ln_slots) ? __ldg(reinterpret_cast<const float4*>(pr) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (2 * i < p.ln_slots) {
+                  su += v[i].x;
+                  sq += v[i].y;
+                  su += v[i].z;
+                  sq += v[i].w;
+                }
+              }
+            } else {
+              for (int i = 0; i < p.ln_slots; ++i) {  // fixed order: bit-reproducible
+                const float2 t = __ldg(pr + i);
+                su += t.x;
+                sq += t.y;
+              }
+            }
+            const float inv_c = 1.0f / static_cast<float>(p.ln_c);
+            const float mean = su * inv_c;
+            st = make_float2(mean, rsqrtf(fmaxf(fmaf(-mean, mean, sq * inv_c), 0.f) + p.ln_eps));
+          } else {
+            st = __ldg(p.ln_stats + lrow);
+          }
+          ln_rstd = st.y;
+          ln_nrm = -st.x * st.y;
+        }
         if (ew == 0) LR_GEMM_TR(2, tcount, 1);
         mbar_wait(&tfull[as], aph);
         tc_fence_after();
@@ -842,17 +883,12 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
         if (p.res_tma) mbar_wait(&rfull[tcount & 1], (tcount >> 1) & 1);  // residual tile is in the staging buffer
         if (ew == 0) LR_GEMM_TR(2, tcount, 2);
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
-        // folded LayerNorm (linear geometry: row index = 128 * M-tile + r): out = rstd * acc + (-mean * rstd) * ln_s + bias
-        float ln_rstd = 1.f, ln_nrm = 0.f;
-        if (k_ln && tile_ok && tm_idx * kBlockM + r < p.W) {
-          const float2 st = __ldg(p.ln_stats + tm_idx * kBlockM + r);
-          ln_rstd = st.y;
-          ln_nrm = -st.x * st.y;
-        }
-        auto run = [&](auto bias_tag, auto res_tag, auto ln_tag) {
+        f32x2 rs2_s = pk2(0.f, 0.f), rs2_q = pk2(0.f, 0.f);  // row statistics, even / odd columns
+        auto run = [&](auto bias_tag, auto res_tag, auto ln_tag, auto rs_tag) {
           constexpr bool kBias = decltype(bias_tag)::value != 0;
           constexpr bool kRes = decltype(res_tag)::value != 0;
           constexpr bool kLn = decltype(ln_tag)::value != 0;  // (implies kBias)
+          constexpr bool kRs = decltype(rs_tag)::value != 0;  // row statistics of the values written (rowstats_out)
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + ncol0);
           const float4* lns4 = reinterpret_cast<const float4*>(p.ln_s + ncol0);
           // accumulator value -> pre-activation: + bias, or the folded LayerNorm's per-row affine map
@@ -926,6 +962,14 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
                   f[2 * h + 1] += t.y;
                 }
               }
+              if constexpr (kRs) {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  const f32x2 v2 = pk2(f[2 * h], f[2 * h + 1]);
+                  rs2_s = add2(rs2_s, v2);
+                  rs2_q = fma2(v2, v2, rs2_q);
+                }
+              }
               sts128(a0 ^ (k << 4),
                      make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7])));
             }
@@ -939,12 +983,23 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
           for (; c + 32 <= c_end; c += 32) chunk(IntTag<32>{}, c);
           if (c < c_end) chunk(IntTag<16>{}, c);
         };
+        using T0 = IntTag<0>;
+        using T1 = IntTag<1>;
         if (k_ln) {
-          if (p.res_tma) run(IntTag<1>{}, IntTag<1>{}, IntTag<1>{}); else run(IntTag<1>{}, IntTag<0>{}, IntTag<1>{});
+          if (p.res_tma) run(T1{}, T1{}, T1{}, T0{}); else run(T1{}, T0{}, T1{}, T0{});
+        } else if (p.rowstats_out != nullptr) {  // (host: only with a bias, never with GEGLU or a folded LayerNorm)
+          if (p.res_tma) run(T1{}, T1{}, T0{}, T1{}); else run(T1{}, T0{}, T0{}, T1{});
+          float s0, s1, q0, q1;
+          upk2(rs2_s, s0, s1);
+          upk2(rs2_q, q0, q1);
+          rs_s = s0 + s1;
+          rs_q = q0 + q1;
+          row_ok = lrow_ok;
+          grow = static_cast<size_t>(lrow);
         } else if (p.bias != nullptr) {
-          if (p.res_tma) run(IntTag<1>{}, IntTag<1>{}, IntTag<0>{}); else run(IntTag<1>{}, IntTag<0>{}, IntTag<0>{});
+          if (p.res_tma) run(T1{}, T1{}, T0{}, T0{}); else run(T1{}, T0{}, T0{}, T0{});
         } else {
-          if (p.res_tma) run(IntTag<0>{}, IntTag<1>{}, IntTag<0>{}); else run(IntTag<0>{}, IntTag<0>{}, IntTag<0>{});
+          if (p.res_tma) run(T0{}, T1{}, T0{}, T0{}); else run(T0{}, T0{}, T0{}, T0{});
         }
       } else {
       // ---------------- general path ----------------

@@ -452,11 +452,14 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
     // lean epilogue path (GemmParams::epi_lean): everything the UNet's Linears and residual convs need, nothing else
     static const bool lean_enabled = getenv("LR_NO_LEAN_EPI") == nullptr;
     // (a folded LayerNorm only in its usual form: per-row (mean, rstd) table, token-matrix geometry)
-    const bool ln_ok = p.ln_part == nullptr &&
-                       (p.ln_stats == nullptr || (p.tiles_y == 1 && p.tiles_b == 1 && bw == kBlockM &&
-                                                  (reinterpret_cast<uintptr_t>(s.ln_s) & 15) == 0));
-    p.epi_lean = (lean_enabled && tma_store && ksplit == 1 && ln_ok && p.bias_img == nullptr &&
-                  p.rowstats_out == nullptr && s.out_scale == 1.0f && (s.residual == nullptr || p.res_tma) &&
+    const bool token_matrix = p.tiles_y == 1 && p.tiles_b == 1 && bw == kBlockM;
+    const bool ln_ok = (p.ln_stats == nullptr && p.ln_part == nullptr) ||
+                       (token_matrix && (reinterpret_cast<uintptr_t>(s.ln_s) & 15) == 0);
+    // (per-row statistics of the output: token matrix, plain epilogue with a bias)
+    const bool rs_ok = p.rowstats_out == nullptr ||
+                       (token_matrix && s.bias != nullptr && !s.geglu && p.ln_stats == nullptr && p.ln_part == nullptr);
+    p.epi_lean = (lean_enabled && tma_store && ksplit == 1 && ln_ok && rs_ok && p.bias_img == nullptr &&
+                  s.out_scale == 1.0f && (s.residual == nullptr || p.res_tma) &&
                   s.ncols % 32 == 0 && p.dbg == 0 && (reinterpret_cast<uintptr_t>(s.bias) & 15) == 0)
                      ? 1
                      : 0;
@@ -768,6 +771,14 @@ static int launch_ln_stats_t(const __half* x, int M, int C, float eps, float* st
   if (blocks > cap) blocks = cap;
   LR_CUDA(launch_pdl(ln_stats_kernel<VPL, RPW>, dim3(blocks), dim3(256), 0, st, 1, x, M, C, eps,
                      reinterpret_cast<float2*>(stats)));
+  LR_LAUNCHED();
+  return 0;
+}
+
+int launch_ln_rows_finalize(const float* part, int ld, int slots, int M, int C, float eps, float* stats, cudaStream_t st) {
+  LR_CHECK(part != nullptr && stats != nullptr && slots > 0 && ld >= slots, "ln_rows_finalize: bad arguments");
+  LR_CUDA(launch_pdl(ln_rows_finalize_kernel, dim3(cdiv(M, 256)), dim3(256), 0, st, 1,
+                     reinterpret_cast<const float2*>(part), ld, slots, M, C, eps, reinterpret_cast<float2*>(stats)));
   LR_LAUNCHED();
   return 0;
 }

@@ -150,6 +150,8 @@ int launch_layernorm(const __half* x, int M, int C, const float* gamma, const fl
                      cudaStream_t st);
 // (mean, rstd) per row -> stats [M] float2; the normalisation itself is folded into the consuming GEMM
 int launch_layernorm_stats(const __half* x, int M, int C, float eps, float* stats, cudaStream_t st);
+// the same (mean, rstd) table from the per-row partials a GEMM epilogue left (ConvSpec::rowstats_out)
+int launch_ln_rows_finalize(const float* part, int ld, int slots, int M, int C, float eps, float* stats, cudaStream_t st);
 int launch_ln_fold(const __half* w, int rows, int K, const float* gamma, const float* beta, const float* bias, __half* wf,
                    float* s_out, float* bf_out, cudaStream_t st);
 int launch_im2col_nchw_f32(const float* x, int n_img, int cin, int H, int W, int kpad, __half* out, cudaStream_t st);
