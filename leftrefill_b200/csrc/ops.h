@@ -126,6 +126,7 @@ struct AttnSpec {
 struct AttnOp {
   alignas(64) unsigned char params[1024];
   dim3 grid;
+  int persist = 0;  // attention_persist_kernel (grid = CTAs walking the work items) instead of one CTA per item
   double flops = 0;
 };
 int build_attn_op(AttnOp* op, const AttnSpec& s);

@@ -1,4 +1,4 @@
-"""Single-kernel driver for ncu captures: python tests/gpu_ncu_attn.py [attn|conv|geglu|lin320]"""
+"""Single-kernel driver for ncu captures: python tests/gpu_ncu_attn.py [attn|conv|geglu|lin320|gn|gnconv|gnlin]"""
 import os
 import sys
 
@@ -31,6 +31,12 @@ elif kind == "gnconv":      # fused GroupNorm + SiLU conv (transform warps), pre
         ops.conv3x3(x, w, bias=b, residual=r)
     for _ in range(3):
         ops.gn_conv3x3(x, w, gn=(sc, sh), silu=True, bias=b, residual=r, want_stats=True)
+elif kind == "gn":          # persistent GroupNorm + SiLU, 8 x 64x128 x 320
+    x = torch.randn(8, 64, 128, 320, device="cuda").half()
+    g = torch.randn(320, device="cuda")
+    b = torch.randn(320, device="cuda")
+    for _ in range(3):
+        ops.groupnorm(x, g, b, 1e-5, silu=True)
 elif kind == "gnlin":
     a = torch.randn(65536, 320, device="cuda").half()
     w = torch.randn(320, 320, device="cuda").half() * 0.05

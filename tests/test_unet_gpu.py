@@ -543,7 +543,7 @@ def test_unet_deepcopy_and_invalidate(small):
 
 SWITCHES = [{"LR_LN_ROWSTATS": "1"}, {"LR_NO_UPFOLD": "1"}, {"LR_NO_GN_FUSE": "1"}, {"LR_GN_FUSE_CONV": "1"},
             {"LR_GN_COEF_APPLY": "1"}, {"LR_GN_FUSE_CONV": "1", "LR_GN_COEF_APPLY": "1", "LR_GN_FUSE_LINEAR_MIN_ROWS": "1"},
-            {"LR_NO_LN_FOLD": "1"}]
+            {"LR_NO_LN_FOLD": "1"}, {"LR_NO_LEAN_EPI": "1"}, {"LR_ATTN_PERSIST": "1", "LR_ATTN_PERSIST_MAX_TILES": "64"}]
 
 
 @pytest.mark.parametrize("env", SWITCHES, ids=lambda e: "+".join(f"{k}={v}" for k, v in e.items()))
