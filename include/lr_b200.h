@@ -163,7 +163,8 @@ int lr_ddim_update_dev(const float* x, const float* eps_uncond, const float* eps
 
 /* force_block_n (testing hook, 0 = heuristic): 1000*cg + block_n with cg in {0: heuristic, 1: single CTA, 2: CTA pair
  * (tcgen05 cta_group::2)} and block_n a multiple of 32 (0 = heuristic).
- * out[M, n_out] = A[M, K] * W[n_out(*2 if geglu), K]^T (+bias) (+residual) ; geglu: W/bias rows interleaved
+ * out[M, n_out] = A[M, K] * W[n_out(*2 if geglu), K]^T (+bias) (+residual) ; geglu: W/bias rows in groups of four
+ * (value_2k, value_2k+1, gate_2k, gate_2k+1), the order lr_repack_linear_weight(geglu = 1) writes; n_out even
  * (value_j, gate_j) and out[:, j] = v_j * gelu(g_j) (attention.py:51-58). fp16 in/out, fp32 accumulate. */
 int lr_linear_f16(const void* a, int lda, int M, int K, const void* w, int ldw, int n_cols, const float* bias,
                   const void* residual, int ld_res, void* out, int ld_out, int geglu, int force_block_n, void* stream);

@@ -1374,24 +1374,28 @@ __global__ void repack_conv_kernel(const float* __restrict__ w, int O, int I, in
   }
   out[idx] = __float2half_rn(v);
 }
-// linear [O, I] fp32 -> fp16 rows at dst_row0 (+ row interleave for GEGLU: src row o -> dst row 2*o (value, o < O/2)
-// or 2*(o - O/2) + 1 (gate))
+// GEGLU row order of the fused projection: groups of four rows (value_2k, value_2k+1, gate_2k, gate_2k+1), so that the
+// epilogue finds the two values and the two gates of an output PAIR in adjacent accumulator columns (packed fp32 math,
+// one fp16x2 result). Source rows: [0, O/2) values, [O/2, O) gates (attention.py:51-58: chunk(2, dim=-1)).
+__host__ __device__ inline int geglu_row(int o, int O) {
+  const int half = O / 2;
+  const int j = (o < half) ? o : o - half;
+  return 4 * (j >> 1) + (j & 1) + ((o < half) ? 0 : 2);
+}
+// linear [O, I] fp32 -> fp16 rows at dst_row0 (+ the GEGLU row order)
 __global__ void repack_linear_kernel(const float* __restrict__ w, int O, int I, int geglu, int dst_row0,
                                      __half* __restrict__ out) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<size_t>(O) * I) return;
   const int i = static_cast<int>(idx % I);
   const int o = static_cast<int>(idx / I);
-  int d = o;
-  if (geglu) d = (o < O / 2) ? 2 * o : 2 * (o - O / 2) + 1;
+  const int d = geglu ? geglu_row(o, O) : o;
   out[(static_cast<size_t>(dst_row0) + d) * I + i] = __float2half_rn(w[idx]);
 }
 __global__ void repack_bias_kernel(const float* __restrict__ b, int O, int geglu, float* __restrict__ out) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= O) return;
-  int d = o;
-  if (geglu) d = (o < O / 2) ? 2 * o : 2 * (o - O / 2) + 1;
-  out[d] = b[o];
+  out[geglu ? geglu_row(o, O) : o] = b[o];
 }
 
 }  // namespace lr

@@ -197,6 +197,29 @@ __device__ __forceinline__ float fast_erf(float x) {
   return copysignf(fmaf(-p, e, 1.0f), x);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
+// The same GELU on a packed pair (FFMA2 / FMUL2: half the issue slots of the FMA-pipe part; the four MUFU operations and
+// the sign handling stay scalar). z = x / sqrt(2); erf(|z|) = 1 - (a1 t + ... + a5 t^5) e^{-z^2}, t = 1 / (1 + p |z|).
+__device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
+  float x0, x1;
+  upk2(x, x0, x1);
+  const f32x2 ax = pk2(fabsf(x0), fabsf(x1));
+  float d0, d1;
+  upk2(fma2(pk2(0.3275911f * 0.70710678118654752f, 0.3275911f * 0.70710678118654752f), ax, pk2(1.0f, 1.0f)), d0, d1);
+  const f32x2 t = pk2(rcp_ftz(d0), rcp_ftz(d1));
+  // -(a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5): the sign is folded into the coefficients
+  f32x2 p = fma2(pk2(-1.061405429f, -1.061405429f), t, pk2(1.453152027f, 1.453152027f));
+  p = fma2(p, t, pk2(-1.421413741f, -1.421413741f));
+  p = fma2(p, t, pk2(0.284496736f, 0.284496736f));
+  p = fma2(p, t, pk2(-0.254829592f, -0.254829592f));
+  p = mul2(p, t);
+  float a0, a1;  // -z^2 log2(e) = x^2 * (-0.5 log2(e))
+  upk2(mul2(mul2(x, x), pk2(-0.72134752044448170f, -0.72134752044448170f)), a0, a1);
+  float e0, e1;
+  upk2(fma2(p, pk2(ex2_ftz(a0), ex2_ftz(a1)), pk2(1.0f, 1.0f)), e0, e1);  // erf(|z|)
+  const f32x2 erf = pk2(copysignf(e0, x0), copysignf(e1, x1));
+  const f32x2 h = mul2(x, pk2(0.5f, 0.5f));
+  return fma2(h, erf, h);  // 0.5 x (1 + erf(z))
+}
 
 template <int V>
 struct IntTag {
@@ -909,16 +932,26 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
                 }
                 const uint32_t a0 = row_base(c >> 1);
                 tmem_ld_wait();
-                float g[16];
+                // accumulator columns 4j .. 4j+3 = (value, value', gate, gate') of output pair j: packed fp32 throughout
+                uint32_t o16[8];
+                const f32x2 rstd2 = pk2(ln_rstd, ln_rstd), nrm2 = pk2(ln_nrm, ln_nrm);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  g[2 * j] = pre(v[4 * j], b4[j].x, s4[j].x) * gelu_erf(pre(v[4 * j + 1], b4[j].y, s4[j].y));
-                  g[2 * j + 1] = pre(v[4 * j + 2], b4[j].z, s4[j].z) * gelu_erf(pre(v[4 * j + 3], b4[j].w, s4[j].w));
+                  f32x2 val = pk2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]));
+                  f32x2 gate = pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                  if constexpr (kLn) {
+                    val = fma2(rstd2, val, fma2(nrm2, pk2(s4[j].x, s4[j].y), pk2(b4[j].x, b4[j].y)));
+                    gate = fma2(rstd2, gate, fma2(nrm2, pk2(s4[j].z, s4[j].w), pk2(b4[j].z, b4[j].w)));
+                  } else {
+                    val = add2(val, pk2(b4[j].x, b4[j].y));
+                    gate = add2(gate, pk2(b4[j].z, b4[j].w));
+                  }
+                  float r0, r1;
+                  upk2(mul2(val, gelu_erf2(gate)), r0, r1);
+                  o16[j] = pack_half2(r0, r1);
                 }
-                sts128(a0, make_uint4(pack_half2(g[0], g[1]), pack_half2(g[2], g[3]), pack_half2(g[4], g[5]),
-                                      pack_half2(g[6], g[7])));
-                sts128(a0 ^ 16u, make_uint4(pack_half2(g[8], g[9]), pack_half2(g[10], g[11]), pack_half2(g[12], g[13]),
-                                            pack_half2(g[14], g[15])));
+                sts128(a0, make_uint4(o16[0], o16[1], o16[2], o16[3]));
+                sts128(a0 ^ 16u, make_uint4(o16[4], o16[5], o16[6], o16[7]));
               }
             }
             return;
@@ -1138,7 +1171,10 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
             __half* o = p.out + grow * p.ld_out + oc0;
             float g[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = f[2 * j] * gelu_erf(f[2 * j + 1]);  // (out_scale is never used with GEGLU)
+            for (int j = 0; j < 8; ++j) {  // columns (v, v', g, g') -> outputs v * gelu(g), v' * gelu(g')
+              g[2 * j] = f[4 * j] * gelu_erf(f[4 * j + 2]);
+              g[2 * j + 1] = f[4 * j + 1] * gelu_erf(f[4 * j + 3]);
+            }  // (out_scale is never used with GEGLU)
             if (p.tma_store) {
               const uint4 w0 = make_uint4(pack_half2(g[0], g[1]), pack_half2(g[2], g[3]), pack_half2(g[4], g[5]),
                                           pack_half2(g[6], g[7]));

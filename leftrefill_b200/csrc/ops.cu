@@ -307,7 +307,7 @@ int build_conv_op(ConvOp* op, const ConvSpec& s) {
     ksplit = best_ks;
   }
   LR_CHECK(block_n % 32 == 0 && block_n >= 32 && block_n <= 256, "conv: bad block_n");
-  LR_CHECK(!s.geglu || (s.ncols % 2 == 0), "conv: GEGLU needs an even column count");
+  LR_CHECK(!s.geglu || (s.ncols % 4 == 0), "conv: GEGLU needs an even number of outputs (rows in groups of four)");
   p.block_n = block_n;
   p.tiles_n = cdiv(s.ncols, block_n);
   // TMA-store epilogue: needs 16-byte aligned output rows, output-tile widths made of 64-column slabs plus at most

@@ -23,8 +23,16 @@ def repack_conv3x3(w_oihw):
     return out
 
 
+def geglu_interleave(t):
+    """Row order of a fused GEGLU projection (weights [2n, I] or bias [2n]): source rows [0, n) values, [n, 2n) gates ->
+    groups of four (value_2k, value_2k+1, gate_2k, gate_2k+1), the order lr_repack_linear_weight(geglu=1) produces."""
+    n = t.shape[0] // 2
+    v, g = t[:n], t[n:]
+    return torch.stack([v[0::2], v[1::2], g[0::2], g[1::2]], dim=1).reshape(t.shape).contiguous()
+
+
 def repack_linear(w, geglu=False):
-    """fp32 [O, I] -> fp16 [O, I]; geglu interleaves (value_j, gate_j) rows."""
+    """fp32 [O, I] -> fp16 [O, I]; geglu puts the rows in the order of geglu_interleave."""
     w = _chk(w.float().contiguous())
     O, I = w.shape
     out = torch.empty(O, I, dtype=torch.float16, device=w.device)

@@ -50,9 +50,7 @@ def case_linear(M, K, Nn, bias=False, residual=False, geglu=False, force=0, seed
     wp = ops.repack_linear(w32, geglu=geglu)
     bp = b
     if geglu and b is not None:
-        bp = torch.empty_like(b)
-        bp[0::2] = b[:Nn]
-        bp[1::2] = b[Nn:]
+        bp = ops.geglu_interleave(b)
     out = ops.linear(a, wp, bias=bp, residual=r, geglu=geglu, force_block_n=force)
     torch.cuda.synchronize()
     ref = a.float() @ w32.half().float().t()
@@ -197,9 +195,7 @@ def case_geglu_big(M, K, Nn, seed=0):
     w32 = (torch.randn(2 * Nn, K, generator=g) * (50.0 / K ** 0.5)).cuda()
     b = (torch.randn(2 * Nn, generator=g) * 20.0).cuda()
     wp = ops.repack_linear(w32, geglu=True)
-    bp = torch.empty_like(b)
-    bp[0::2] = b[:Nn]
-    bp[1::2] = b[Nn:]
+    bp = ops.geglu_interleave(b)
     out = ops.linear(a, wp, bias=bp, geglu=True)
     torch.cuda.synchronize()
     h = a.double() @ w32.half().double().t() + b.double()
