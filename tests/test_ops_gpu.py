@@ -35,6 +35,46 @@ def test_bad_arguments_raise():
         ops.linear(a, w)
 
 
+def test_geglu_row_order_of_the_repack_kernel():
+    """lr_repack_linear_weight(geglu=1) writes groups of four rows (value_2k, value_2k+1, gate_2k, gate_2k+1): the order
+    ops.geglu_interleave documents and the GEGLU epilogue assumes."""
+    from leftrefill_b200 import ops
+    w = torch.randn(2 * 96, 64, generator=torch.Generator().manual_seed(3)).cuda()
+    got = ops.repack_linear(w, geglu=True)
+    assert torch.equal(got, ops.geglu_interleave(w).half())
+    n = 96
+    assert torch.equal(got[0], w[0].half()) and torch.equal(got[1], w[1].half())
+    assert torch.equal(got[2], w[n].half()) and torch.equal(got[3], w[n + 1].half())
+    assert torch.equal(got[4], w[2].half()) and torch.equal(got[6], w[n + 2].half())
+
+
+@pytest.mark.parametrize("shape", [(64, 128, 320, 0), (32, 64, 640, 320)])
+def test_persistent_groupnorm_is_batch_invariant_and_deterministic(shape):
+    """Images above 1.3 MB take gn_persistent_kernel (one launch, per-chunk fp64 partials, grid barrier). Its result for
+    an image must not depend on the batch it is normalised in, on the number of CTAs, or on the run (fixed reduction
+    order, no atomics): bit-identical outputs for n = 1, 3, 8 and across repeats; and it must leave its barrier counters
+    reusable (second call on the same scratch inside ops.groupnorm's allocator)."""
+    from leftrefill_b200 import ops
+    h, w, c0, c1 = shape
+    g = torch.Generator().manual_seed(11)
+    x0 = (torch.randn(8, h, w, c0, generator=g) * 2.0 + 0.5).cuda().half()
+    x1 = torch.randn(8, h, w, c1, generator=g).cuda().half() if c1 else None
+    gamma = torch.randn(c0 + c1, generator=g).cuda()
+    beta = torch.randn(c0 + c1, generator=g).cuda()
+    full = ops.groupnorm(x0, gamma, beta, 1e-5, silu=True, x1=x1)
+    again = ops.groupnorm(x0, gamma, beta, 1e-5, silu=True, x1=x1)
+    assert torch.equal(full, again)
+    for n in (1, 3):
+        part = ops.groupnorm(x0[:n].contiguous(), gamma, beta, 1e-5, silu=True,
+                             x1=x1[:n].contiguous() if x1 is not None else None)
+        assert torch.equal(part, full[:n])
+    last = ops.groupnorm(x0[7:].contiguous(), gamma, beta, 1e-5, silu=True, x1=x1[7:].contiguous() if x1 is not None else None)
+    assert torch.equal(last, full[7:])
+    xs = torch.cat([x0.float(), x1.float()], dim=3) if x1 is not None else x0.float()
+    ref = torch.nn.functional.silu(torch.nn.functional.group_norm(xs.permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)).permute(0, 2, 3, 1)
+    assert (full.float() - ref).abs().max().item() <= 2e-4 * ref.abs().max().item() + 1e-3 * ref.abs().max().item()
+
+
 @pytest.mark.parametrize("cfg_scale,sigma", [(2.5, 0.0), (2.5, 0.37), (1.0, 0.2)])
 def test_ddim_update_matches_oracle(cfg_scale, sigma):
     from leftrefill_b200 import ops
