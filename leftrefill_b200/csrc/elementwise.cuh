@@ -8,6 +8,11 @@
 namespace lr {
 
 constexpr int kNormThreads = 512;
+// -DLR_GN_TRACE=1: gn_persistent_kernel keeps clock64 stamps of its phases and prints them with LR_GN_DEBUG=16
+// (tests/gpu_gn_trace.py; costs registers, off in the shipped build)
+#ifndef LR_GN_TRACE
+#define LR_GN_TRACE 0
+#endif
 
 __device__ __forceinline__ void load8(const __half* p, float (&f)[8]) {
   const uint4 v = *reinterpret_cast<const uint4*>(p);
@@ -71,6 +76,7 @@ __device__ __forceinline__ uint32_t affine_silu_h2(uint32_t w, f32x2 sc, f32x2 s
 // at byte 256: double2 part[n][chunks][G].
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kGnBatch = 8;
+constexpr int kGnPersistBatch = 4;  // gn_persistent_kernel: two CTAs per SM at <= 64 registers instead of deeper batches
 
 // pixel chunks per image (depends on the image size ONLY): 37 chunks per image - 4 images fill the 148 SMs exactly, 8
 // images give every CTA two items (32 chunks left 40 CTAs with one item and 108 with two) - of 16 to 2048 pixels; the
@@ -102,17 +108,18 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 __device__ __forceinline__ void keep_packed(uint4& v) { asm volatile("" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)); }
 
 // per-thread partial (sum, sum of squares) of 8 channels over pixels p0, p0 + rpi, ... < p_end
+template <int kB = kGnBatch>
 __device__ __forceinline__ void gn_accumulate(const __half* __restrict__ base, int ld, int p0, int p_end, int rpi,
                                               float (&s)[8], float (&ss)[8]) {
-  for (int p = p0; p < p_end; p += kGnBatch * rpi) {
-    uint4 v[kGnBatch];
+  for (int p = p0; p < p_end; p += kB * rpi) {
+    uint4 v[kB];
 #pragma unroll
-    for (int u = 0; u < kGnBatch; ++u) {
+    for (int u = 0; u < kB; ++u) {
       const int pp = p + u * rpi;
       v[u] = (pp < p_end) ? ldg16(base + static_cast<size_t>(pp) * ld) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
-    for (int u = 0; u < kGnBatch; ++u) {
+    for (int u = 0; u < kB; ++u) {
       float f[8];
       unpack8(v[u], f);
 #pragma unroll
@@ -162,13 +169,14 @@ __device__ __forceinline__ float2 gn_finalize(double sum, double sq, double cnt,
 }
 
 // y = [silu](x * sc + sh) for pixels p0, p0 + rpi, ... < p_end of one 8-channel column
+template <int kB = kGnBatch>
 __device__ __forceinline__ void gn_apply_rows(const __half* __restrict__ base, int ld, __half* __restrict__ o, int C,
                                               int p0, int p_end, int rpi, const float (&sc)[8], const float (&sh)[8],
                                               int do_silu) {
   // Software pipeline of two half batches: the loads of one are in flight while the other is normalised and stored.
   // With SiLU the math alone is MUFU-bound near the HBM rate (EX2 + RCP per element at 16 / clk / SM = 16 B / clk / SM),
   // so load latency has to hide behind it, not add to it (tests/gpu_time_gn_passes.py: 21 -> 13 us on 8 x 64x128x320).
-  constexpr int kH = kGnBatch / 2;
+  constexpr int kH = kB / 2;
   const int step = kH * rpi;
   f32x2 sc2[4], sh2[4];
 #pragma unroll
@@ -213,9 +221,9 @@ __device__ __forceinline__ void gn_apply_rows(const __half* __restrict__ base, i
   }
 }
 
-// Persistent two-pass GroupNorm (see the header comment). grid = min(#SM, n * chunks) CTAs; block = kNormThreads;
+// Persistent two-pass GroupNorm (see the header comment). grid = min(2 * #SM, n * chunks) CTAs; block = kNormThreads;
 // dynamic smem = rpi * 2 * C floats.
-__global__ void __launch_bounds__(kNormThreads, 1) gn_persistent_kernel(const __half* __restrict__ x0, int c0,
+__global__ void __launch_bounds__(kNormThreads, 2) gn_persistent_kernel(const __half* __restrict__ x0, int c0,
                                                                         const __half* __restrict__ x1, int c1, int P,
                                                                         int n_img, int groups, float eps,
                                                                         const float* __restrict__ gamma,
@@ -243,30 +251,27 @@ __global__ void __launch_bounds__(kNormThreads, 1) gn_persistent_kernel(const __
   const int ld = (ch < c0) ? c0 : c1;
 
   // ---- pass 1: per-(item, group) partial sums ----
+#if LR_GN_TRACE
   long long tr[6] = {0, 0, 0, 0, 0, 0};
   tr[0] = clock64();
+#endif
   for (int it = i0; it < i1 && !(dbg & 1); ++it) {
     const int n = it / chunks, k = it - n * chunks;
     const int p_begin = k * chunk, p_end = min(P, p_begin + chunk);
     float s[8], ss[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
-    if (rsub < rpi) gn_accumulate(src + static_cast<size_t>(n) * P * ld, ld, p_begin + rsub, p_end, rpi, s, ss);
+    if (rsub < rpi) gn_accumulate<kGnPersistBatch>(src + static_cast<size_t>(n) * P * ld, ld, p_begin + rsub, p_end, rpi, s, ss);
     double a, b;
     gn_cta_group_sums(sm, C, rpi, rsub, ch, groups, s, ss, a, b);
     if (static_cast<int>(threadIdx.x) < groups) part[static_cast<size_t>(it) * groups + threadIdx.x] = make_double2(a, b);
     __syncthreads();  // sm is rewritten by the next item
   }
 
-  // (gamma / beta of this thread's channels: fetched here so that the barrier hides the latency)
-  float gam[8], bet[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    gam[j] = (rsub < rpi) ? __ldg(gamma + ch + j) : 0.f;
-    bet[j] = (rsub < rpi) ? __ldg(beta + ch + j) : 0.f;
-  }
   // ---- grid barrier: every CTA's partials are visible ----
+#if LR_GN_TRACE
   tr[1] = clock64();
+#endif
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -284,7 +289,9 @@ __global__ void __launch_bounds__(kNormThreads, 1) gn_persistent_kernel(const __
   __syncthreads();
 
   // ---- pass 2: finalise per image, normalise own items ----
+#if LR_GN_TRACE
   tr[2] = clock64();
+#endif
   const int cpg = C / groups;
   const int tpg = blockDim.x / groups;  // threads that share the chunk sum of one group (a power of two <= 32)
   const double cntd = static_cast<double>(P) * cpg;
@@ -296,6 +303,14 @@ __global__ void __launch_bounds__(kNormThreads, 1) gn_persistent_kernel(const __
     const int n = it / chunks, k = it - n * chunks;
     if (n != cur_n) {
       __syncthreads();  // everybody is done with the previous image's s_mr
+      // gamma / beta of this thread's channels (in flight while the chunk partials are summed)
+      float4 gam[2], bet[2];
+      if (rsub < rpi) {
+        gam[0] = __ldg(reinterpret_cast<const float4*>(gamma + ch));
+        gam[1] = __ldg(reinterpret_cast<const float4*>(gamma + ch) + 1);
+        bet[0] = __ldg(reinterpret_cast<const float4*>(beta + ch));
+        bet[1] = __ldg(reinterpret_cast<const float4*>(beta + ch) + 1);
+      }
       const int g = threadIdx.x / tpg, sub = threadIdx.x % tpg;
       double a = 0.0, b = 0.0;
       if (g < groups) {
@@ -321,27 +336,33 @@ __global__ void __launch_bounds__(kNormThreads, 1) gn_persistent_kernel(const __
       __syncthreads();
       cur_n = n;
       if (rsub < rpi) {  // the affine coefficients of this thread's 8 channels change with the image only
+        const float gm[8] = {gam[0].x, gam[0].y, gam[0].z, gam[0].w, gam[1].x, gam[1].y, gam[1].z, gam[1].w};
+        const float bt[8] = {bet[0].x, bet[0].y, bet[0].z, bet[0].w, bet[1].x, bet[1].y, bet[1].z, bet[1].w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float2 m = s_mr[(ch + j) / cpg];
-          sc[j] = m.y * gam[j];
-          sh[j] = bet[j] - m.x * sc[j];
+          sc[j] = m.y * gm[j];
+          sh[j] = bt[j] - m.x * sc[j];
         }
       }
+#if LR_GN_TRACE
       if (it == i0) tr[3] = clock64();
+#endif
     }
     if (rsub < rpi && !(dbg & 2)) {
       const int p_begin = k * chunk, p_end = min(P, p_begin + chunk);
-      gn_apply_rows(src + static_cast<size_t>(n) * P * ld, ld, out + static_cast<size_t>(n) * P * C + ch, C, p_begin + rsub,
+      gn_apply_rows<kGnPersistBatch>(src + static_cast<size_t>(n) * P * ld, ld, out + static_cast<size_t>(n) * P * C + ch, C, p_begin + rsub,
                     p_end, rpi, sc, sh, do_silu);
     }
   }
 
   // ---- leave the counters zero for the next launch on this scratch ----
+#if LR_GN_TRACE
   tr[4] = clock64();
   if ((dbg & 16) && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
     printf("gn trace cta %d items %d: pass1 %lld barrier %lld stats %lld apply %lld\n", blockIdx.x, i1 - i0, tr[1] - tr[0],
            tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3]);
+#endif
   if (threadIdx.x == 0) {
     const unsigned left = atomicAdd(&cnt[1], 1u);
     if (left == static_cast<unsigned>(G) - 1) {  // everybody has passed the barrier: nobody reads cnt[0] any more

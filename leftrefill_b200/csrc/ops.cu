@@ -701,7 +701,10 @@ int launch_groupnorm(const __half* x0, int c0, const __half* x1, int c1, int n_i
   LR_CHECK(scratch != nullptr, "groupnorm: scratch buffer required");
   LR_CHECK((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "groupnorm: scratch must be 16-byte aligned");
   const long long items = static_cast<long long>(n_img) * gn_chunks(P);
-  const int grid = static_cast<int>(items < sm_count() ? items : sm_count());  // all CTAs resident: grid-wide barrier inside
+  // all CTAs must be resident (grid-wide barrier inside): two per SM (__launch_bounds__(512, 2): 64 registers, <= 33 KB
+  // of shared memory each)
+  const long long slots = 2LL * sm_count();
+  const int grid = static_cast<int>(items < slots ? items : slots);
   if (!scratch_is_zero) LR_CUDA(cudaMemsetAsync(scratch, 0, 16, st));
   // bring-up (tests/gpu_time_gn_passes.py, gpu_gn_trace.py): 1 = skip pass 1, 2 = skip pass 2, 16 = print phase cycles
   static const int gn_dbg = env_int("LR_GN_DEBUG", 0);

@@ -1,4 +1,5 @@
-"""LR_GN_DEBUG=16: the persistent GroupNorm prints clock64 deltas of its phases (CTA 0 and CTA 77)."""
+"""LR_GN_DEBUG=16 on a build with -DLR_GN_TRACE=1 (LR_B200_LIB=...): the persistent GroupNorm prints clock64 deltas of its
+phases (CTA 0 and CTA 77). The shipped build carries no trace code (it costs registers)."""
 import os, sys
 os.environ.setdefault("LR_GN_DEBUG", "16")
 os.environ.setdefault("LR_GN_FUSED_KB", "0")
