@@ -1172,8 +1172,9 @@ __global__ void __launch_bounds__(XF ? kGemmThreadsXf : kGemmThreads, 1) gemm_co
             float g[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {  // columns (v, v', g, g') -> outputs v * gelu(g), v' * gelu(g')
-              g[2 * j] = f[4 * j] * gelu_erf(f[4 * j + 2]);
-              g[2 * j + 1] = f[4 * j + 1] * gelu_erf(f[4 * j + 3]);
+              // the SAME packed arithmetic as the lean path: which path a launch takes depends on its geometry (hence on
+              // the batch size for tiny token counts), the result must not (tests/test_multigpu.py)
+              upk2(mul2(pk2(f[4 * j], f[4 * j + 1]), gelu_erf2(pk2(f[4 * j + 2], f[4 * j + 3]))), g[2 * j], g[2 * j + 1]);
             }  // (out_scale is never used with GEGLU)
             if (p.tma_store) {
               const uint4 w0 = make_uint4(pack_half2(g[0], g[1]), pack_half2(g[2], g[3]), pack_half2(g[4], g[5]),

@@ -35,6 +35,27 @@ def test_bad_arguments_raise():
         ops.linear(a, w)
 
 
+@pytest.mark.parametrize("kind", ["bias_res", "geglu", "plain"])
+def test_lean_and_general_epilogue_are_bit_identical(kind, monkeypatch):
+    """Which epilogue path a GEMM takes depends on its geometry (for tiny token counts: on the batch size), so both must
+    produce the same bits - otherwise results would depend on how a batch is sharded over GPUs."""
+    from leftrefill_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    M, K, Nn = 1000, 320, 320
+    a = (torch.randn(M, K, generator=g) * 0.7).cuda().half()
+    geglu = kind == "geglu"
+    w32 = (torch.randn(2 * Nn if geglu else Nn, K, generator=g) / K ** 0.5).cuda()
+    wp = ops.repack_linear(w32, geglu=geglu)
+    b = torch.randn(2 * Nn if geglu else Nn, generator=g).cuda() if kind != "plain" else None
+    if geglu:
+        b = ops.geglu_interleave(b)
+    r = torch.randn(M, Nn, generator=g).cuda().half() if kind == "bias_res" else None
+    lean = ops.linear(a, wp, bias=b, residual=r, geglu=geglu)
+    monkeypatch.setenv("LR_NO_LEAN_EPI", "1")
+    general = ops.linear(a, wp, bias=b, residual=r, geglu=geglu)
+    assert torch.equal(lean, general)
+
+
 def test_geglu_row_order_of_the_repack_kernel():
     """lr_repack_linear_weight(geglu=1) writes groups of four rows (value_2k, value_2k+1, gate_2k, gate_2k+1): the order
     ops.geglu_interleave documents and the GEGLU epilogue assumes."""

@@ -172,6 +172,35 @@ def test_ddim_multi_sampling_vs_reference_golden(small):
     _assert_parity(samples, g["samples"])
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_sampler_is_invariant_to_batch_sharding(small, world):
+    """The single-GPU form of tests/test_multigpu.py: sampling a global batch of 4 canvases in `world` shards (same
+    global noise, sliced) must reproduce the unsharded samples bit for bit. Catches every kernel / path choice that
+    depends on the batch size (GEMM epilogue path, split-K, GroupNorm scheme, tile configuration)."""
+    import leftrefill_b200 as lr
+    from leftrefill_b200 import parallel as P
+    m, _ = small
+    dev = torch.device("cuda")
+    S, B, H, W = 4, 4, 16, 32
+    x_T, c_cat, ctx, uc = synthetic_inputs(B, h=H, w=W, ctx_dim=256, device=dev)
+    noise = P.global_randn((S, B, 4, H, W), seed=11, device=dev)
+    cond = {"c_concat": [c_cat], "c_crossattn": [ctx]}
+    ucond = {"c_concat": [c_cat], "c_crossattn": [uc]}
+
+    def run(lo, hi):
+        s = lr.DDIMSampler(FakeLDM(m, dev))
+        s.noise_source = lambda shp, d, i: noise[i, lo:hi].to(d)
+        cut = lambda c: {k: [t[lo:hi] for t in v] for k, v in c.items()}
+        y, _ = s.sample(S, hi - lo, (4, H, W), cut(cond), x_T=x_T[lo:hi], unconditional_conditioning=cut(ucond),
+                        verbose=False, eta=1.0, unconditional_guidance_scale=2.5)
+        return y
+
+    whole = run(0, B)
+    per = B // world
+    parts = torch.cat([run(r * per, (r + 1) * per) for r in range(world)], dim=0)
+    assert torch.equal(whole, parts), (whole - parts).abs().max().item()
+
+
 def test_sampler_generic_path_equals_fast_path(small):
     """apply_model route (any model) and the hoisted native route must agree; RNG consumption must be identical."""
     import leftrefill_b200 as lr
