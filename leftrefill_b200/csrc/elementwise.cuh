@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kNormThreads, 2) gn_persistent_kernel(const __
 
 // GroupNorm apply [+ SiLU] from the per-(image, channel) coefficients gn_finalize_kernel derived from the PRODUCER's
 // statistics: y = [silu](x * scale[n, c] + shift[n, c]). One read + one write pass (the stand-alone scheme reads twice).
-// Same thread mapping and chunking as gn_apply_kernel. grid = (pixel chunks, n); block = kNormThreads.
+// Same thread mapping as the other GroupNorm kernels. grid = (pixel chunks, n); block = kNormThreads.
 __global__ void __launch_bounds__(kNormThreads) gn_apply_coef_kernel(const __half* __restrict__ x0, int c0,
                                                                      const __half* __restrict__ x1, int c1, int P,
                                                                      int chunk, const float* __restrict__ scale,
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(kNormThreads) gn_fused_cluster_kernel(const __
 // and channel, (sum, sum of squares) of the fp16 values in part[rows][C]; the rows of image n are [n*ppi, (n+1)*ppi).
 // One CTA per (group, image) sums its group's entries in a FIXED order (thread-local sequence, then a fixed shared-memory
 // tree; fp64), and writes the affine coefficients the consumer's transform warps apply:
-//   scale[n, c] = rstd * gamma[c],  shift[n, c] = beta[c] - mean * scale[n, c]      (same formulas as gn_apply_kernel)
+//   scale[n, c] = rstd * gamma[c],  shift[n, c] = beta[c] - mean * scale[n, c]      (same formulas as the stand-alone GroupNorm kernels)
 // Two sources = the channel concat of the skip connection (openaimodel.py:781); their tables may have different ppi.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kGnFinalizeThreads = 128;
