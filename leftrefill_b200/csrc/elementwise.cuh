@@ -1212,11 +1212,13 @@ __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, int n_i
 // ------------------------------------------------------------------------------------------------------------
 // Small-M linear layers of the timestep path (time_embed, 22 x emb_layers; openaimodel.py:527-532,217-223).
 // out[n, o] = bias[o] + sum_k act(in[n, k]) * W[o, k]; fp16 weights streamed once, fp32 activations/accumulate.
-// One warp per output feature; handles up to kMaxSmallBatch batch rows per pass.
+// One warp per kOut output features (4 for the big emb_layers block; 1 for the 1280-wide time_embed layers, which would
+// otherwise run on 40 CTAs); handles up to kMaxSmallBatch batch rows per pass.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kMaxSmallBatch = 8;
 constexpr int kSmallOutPerWarp = 4;
 // dynamic smem: min(n_rows, 8) * K floats (the activation block, SiLU already applied when silu_in)
+template <int kOut>
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in, int ld_in, int n_rows, int K,
                                                            const __half* __restrict__ w,
                                                            const float* __restrict__ bias, int n_out, int silu_in,
@@ -1225,13 +1227,30 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
   pdl_wait();
   extern __shared__ float act[];  // [rows][K]
   const int lane = threadIdx.x & 31;
+  constexpr int kSmallOutPerWarp = kOut;
   const int o0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kSmallOutPerWarp;
   for (int r0 = 0; r0 < n_rows; r0 += kMaxSmallBatch) {
     const int rows = min(kMaxSmallBatch, n_rows - r0);
     __syncthreads();
-    for (int i = threadIdx.x; i < rows * K; i += blockDim.x) {
-      float a = in[static_cast<size_t>(r0 + i / K) * ld_in + (i % K)];
-      act[i] = silu_in ? silu_f(a) : a;
+    // stage the activation block: 16-byte loads, four in flight per thread (a scalar load -> SiLU -> store loop left
+    // every CTA of the 630-CTA emb_layers launch waiting ~40 dependent L2 round trips before its first weight load)
+    const int kq = K >> 2;  // float4 per row (K % 8 == 0)
+    for (int i0 = threadIdx.x; i0 < rows * kq; i0 += 4 * blockDim.x) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        v[u] = (i < rows * kq) ? *reinterpret_cast<const float4*>(in + static_cast<size_t>(r0 + i / kq) * ld_in + (i % kq) * 4)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < rows * kq) {
+          if (silu_in) v[u] = make_float4(silu_f(v[u].x), silu_f(v[u].y), silu_f(v[u].z), silu_f(v[u].w));
+          *reinterpret_cast<float4*>(act + static_cast<size_t>(i / kq) * K + (i % kq) * 4) = v[u];
+        }
+      }
     }
     __syncthreads();
     if (o0 < n_out) {
@@ -1240,6 +1259,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
       for (int u = 0; u < kSmallOutPerWarp; ++u)
 #pragma unroll
         for (int r = 0; r < kMaxSmallBatch; ++r) acc[u][r] = 0.f;
+#pragma unroll 4
       for (int k = lane * 8; k < K; k += 32 * 8) {
         float wv[kSmallOutPerWarp][8];
 #pragma unroll

@@ -955,8 +955,14 @@ int launch_small_linear(const float* in, int ld_in, int n_rows, int K, const __h
   const int rows = n_rows < kMaxSmallBatch ? n_rows : kMaxSmallBatch;
   const size_t smem = static_cast<size_t>(rows) * K * sizeof(float);
   LR_CHECK(smem <= 48 * 1024, "small_linear: K too large for the activation staging buffer");
-  LR_CUDA(launch_pdl(small_linear_kernel, dim3(cdiv(n_out, 8 * kSmallOutPerWarp)), dim3(256), smem, st, 1, in, ld_in,
-                     n_rows, K, w, bias, n_out, silu_in, silu_out, out, ld_out));
+  LR_CHECK(ld_in % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "small_linear: input rows must be 16-byte aligned");
+  if (n_out <= 4096) {  // narrow layers: one output per warp keeps >= 40 CTAs x 4 busy instead of 40
+    LR_CUDA(launch_pdl(small_linear_kernel<1>, dim3(cdiv(n_out, 8)), dim3(256), smem, st, 1, in, ld_in, n_rows, K, w, bias,
+                       n_out, silu_in, silu_out, out, ld_out));
+  } else {
+    LR_CUDA(launch_pdl(small_linear_kernel<kSmallOutPerWarp>, dim3(cdiv(n_out, 8 * kSmallOutPerWarp)), dim3(256), smem, st, 1,
+                       in, ld_in, n_rows, K, w, bias, n_out, silu_in, silu_out, out, ld_out));
+  }
   LR_LAUNCHED();
   return 0;
 }

@@ -1,10 +1,6 @@
 #!/bin/bash
-# cooperative launch of gn_persistent_kernel: with / without PDL on that launch, vs the plain launch
+# small_linear_kernel (timestep path): vectorised staging, one output per warp for the narrow layers
 mkdir -p gpurun_out
-LR_CASE_TIMEOUT=90 timeout 300 python tests/gpu_diag_ops.py --only gn_bigmean_twopass,gn 2>&1 | tail -1
-LR_GN_COOP_PDL=1 LR_CASE_TIMEOUT=90 timeout 300 python tests/gpu_diag_ops.py --only gn_bigmean_twopass 2>&1 | tail -2
-for rep in 1 2; do
-  echo "coop:      $(timeout 300 python tests/gpu_time_forward.py 40 2>&1 | tail -1)"
-  echo "coop+pdl:  $(LR_GN_COOP_PDL=1 timeout 300 python tests/gpu_time_forward.py 40 2>&1 | tail -1)"
-  echo "plain:     $(LR_GN_NO_COOP=1 timeout 300 python tests/gpu_time_forward.py 40 2>&1 | tail -1)"
-done
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum -k regex:small_linear --clock-control none --csv --log-file gpurun_out/r2y_small_linear.csv python tests/gpu_ncu_forward.py > /dev/null 2>&1; grep -o '"gpu__time_duration.sum","ns","[0-9]*"' gpurun_out/r2y_small_linear.csv
+for rep in 1 2; do echo "$(timeout 300 python tests/gpu_time_forward.py 40 2>&1 | tail -1)"; done
+timeout 1800 python -m pytest tests/test_unet_gpu.py -m gpu -x -q 2>&1 | tail -2
