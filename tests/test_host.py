@@ -238,3 +238,18 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_geglu_interleave_is_the_documented_row_permutation():
+    """ops.geglu_interleave (the host-side mirror of lr_repack_linear_weight(geglu=1), checked against the kernel in
+    tests/test_ops_gpu.py): source rows [0, n) values, [n, 2n) gates -> groups (v_2k, v_2k+1, g_2k, g_2k+1)."""
+    import torch
+    from leftrefill_b200 import ops
+    n = 10
+    src = torch.arange(2 * n, dtype=torch.float32)
+    out = ops.geglu_interleave(src)
+    assert sorted(out.tolist()) == src.tolist()                       # a permutation
+    for k in range(n // 2):
+        assert out[4 * k:4 * k + 4].tolist() == [2 * k, 2 * k + 1, n + 2 * k, n + 2 * k + 1]
+    w = torch.randn(2 * n, 3)
+    assert torch.equal(ops.geglu_interleave(w)[:, 1], ops.geglu_interleave(w[:, 1].contiguous()))
