@@ -19,6 +19,9 @@
 extern "C" {
 #endif
 
+/* 2: lr_vae_*, lr_unet_cfg.use_sep, lr_unet_set_c_input, GroupNorm-fusion entry points (round 2).
+ * 3: lr_groupnorm_scratch_bytes (the scratch of lr_groupnorm_f16 now depends on P); GEGLU weight / bias rows in groups of
+ *    four (value, value', gate, gate') - lr_repack_linear_weight(geglu = 1) writes that order. */
 #define LR_B200_ABI_VERSION 3
 
 /* ---- library ---------------------------------------------------------------------------------------------- */
