@@ -861,26 +861,34 @@ __global__ void __launch_bounds__(256) ln_fold_kernel(const __half* __restrict__
 // Boundary conversions
 // ------------------------------------------------------------------------------------------------------------
 // First conv (in_channels=9, openaimodel.py:539-545): gather the 3x3 neighbourhood of the NCHW fp32 input into
-// an fp16 [M, kpad] matrix, k = tap*cin + c, zero padded, consumed by the GEMM as a Linear.
+// an fp16 [M, kpad] matrix, k = tap*cin + c, zero padded, consumed by the GEMM as a Linear. One thread per 8 consecutive
+// k (one 16-byte store; kpad % 8 == 0); consecutive threads walk k first, so a warp covers 2-3 pixels and its gathers of
+// one (tap, channel) plane hit neighbouring addresses.
 __global__ void im2col_nchw_f32_kernel(const float* __restrict__ x, int n_img, int cin, int H, int W, int kpad,
                                        __half* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
+  const int kv = kpad >> 3;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t total = static_cast<size_t>(n_img) * H * W * kpad;
+  const size_t total = static_cast<size_t>(n_img) * H * W * kv;
   if (idx >= total) return;
-  const int k = static_cast<int>(idx % kpad);
-  const size_t m = idx / kpad;
+  const int k0 = static_cast<int>(idx % kv) * 8;
+  const size_t m = idx / kv;
   const int xw = static_cast<int>(m % W);
   const int yh = static_cast<int>((m / W) % H);
   const int n = static_cast<int>(m / (static_cast<size_t>(W) * H));
-  float v = 0.f;
-  if (k < 9 * cin) {
-    const int tap = k / cin, c = k % cin;
-    const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x[((static_cast<size_t>(n) * cin + c) * H + yy) * W + xx];
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = k0 + j;
+    v[j] = 0.f;
+    if (k < 9 * cin) {
+      const int tap = k / cin, c = k - tap * cin;
+      const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v[j] = __ldg(x + ((static_cast<size_t>(n) * cin + c) * H + yy) * W + xx);
+    }
   }
-  out[idx] = __float2half_rn(v);
+  store8(out + m * kpad + k0, v);
 }
 
 // Upsample (openaimodel.py:108-116): F.interpolate(scale_factor=2, mode="nearest"), NHWC fp16, 8-channel vectors.

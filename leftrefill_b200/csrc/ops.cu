@@ -842,7 +842,8 @@ int launch_ln_fold(const __half* w, int rows, int K, const float* gamma, const f
 }
 
 int launch_im2col_nchw_f32(const float* x, int n_img, int cin, int H, int W, int kpad, __half* out, cudaStream_t st) {
-  const size_t total = static_cast<size_t>(n_img) * H * W * kpad;
+  LR_CHECK(kpad % 8 == 0, "im2col: kpad must be a multiple of 8");
+  const size_t total = static_cast<size_t>(n_img) * H * W * (kpad / 8);
   LR_CUDA(launch_pdl(im2col_nchw_f32_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, 1, x,
                      n_img, cin, H, W, kpad, out));
   LR_LAUNCHED();
