@@ -174,7 +174,7 @@ __device__ __forceinline__ void gn_apply_rows(const __half* __restrict__ base, i
                                               int p0, int p_end, int rpi, const float (&sc)[8], const float (&sh)[8],
                                               int do_silu) {
   // Software pipeline of two half batches: the loads of one are in flight while the other is normalised and stored.
-  // With SiLU the math alone is MUFU-bound near the HBM rate (EX2 + RCP per element at 16 / clk / SM = 16 B / clk / SM),
+  // With SiLU the math alone runs near the HBM rate (EX2 -> RCP per element at 16 / clk / SM = 16 B / clk / SM at best),
   // so load latency has to hide behind it, not add to it (tests/gpu_time_gn_passes.py: 21 -> 13 us on 8 x 64x128x320).
   constexpr int kH = kB / 2;
   const int step = kH * rpi;
